@@ -1,0 +1,101 @@
+/* libtblup_b200 -- C ABI of the B200-native GBLUP fitness path.
+ *
+ * The reference (ianwhale/tblup, pure Python) has no FFI: its seam for this path is the evaluator
+ * object that tblup/utils.py:48,59 builds through `get_evaluator(args)` and that
+ * tblup/population.py:47,68 and main.py:35 call.  These entry points are what a ctypes binding placed
+ * behind that seam needs (INTEGRATION.md shows the binding); each one names the reference code whose
+ * work it takes over.  Conventions: plain pointers and sizes, caller keeps ownership of every host
+ * buffer, return 0 on success / negative on error (message via tb_last_error), nothing throws across
+ * the boundary, one host thread per context, every call returns with its results valid
+ * (internally asynchronous on the context's own CUDA stream).
+ */
+#ifndef TBLUP_B200_H
+#define TBLUP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct TbCtx tb_ctx;
+
+#define TB_ABI_VERSION 1
+
+/* branch rule of BlupParallelEvaluator.blup (tblup/evaluator.py:257-263) */
+#define TB_MODE_AUTO 0    /* len(indices) > n  -> gblup, else snp_blup */
+#define TB_MODE_GBLUP 1   /* allele frequencies over ALL animals, raw y      (evaluator.py:265-286) */
+#define TB_MODE_SNPBLUP 2 /* frequencies over the training animals, centred y (evaluator.py:288-314) */
+
+/* pipeline stages, index into tb_stage_times() and `stop_after` */
+enum {
+  TB_STAGE_H2D = 0, TB_STAGE_GATHER, TB_STAGE_CENTRE, TB_STAGE_GRAM, TB_STAGE_SCALE,
+  TB_STAGE_CHOL_UPDATE, TB_STAGE_CHOL_PANEL, TB_STAGE_SOLVE, TB_STAGE_D2H, TB_STAGE_COUNT
+};
+
+/* what tb_debug_fetch() can copy back from the last wave (job = individual * n_slots + slot) */
+enum {
+  TB_DBG_C = 0,     /* int32  [rpad*rpad]      uncentred cross-products (lower triangle valid)      */
+  TB_DBG_S = 1,     /* int64  [rpad]           s_a = sum_j x_aj colsum_j                             */
+  TB_DBG_SQ = 2,    /* int64  [2]              S = sum colsum, Q = sum colsum^2                      */
+  TB_DBG_M = 3,     /* double [(ntp+n_v)*ntp]  [A ; G_vt] (A holds L after the factorisation)        */
+  TB_DBG_ALPHA = 4, /* double [ntp]                                                                  */
+  TB_DBG_PRED = 5,  /* double [n_v]                                                                  */
+  TB_DBG_DIMS = 6   /* int32  [4]              rpad, ntp, n_v, kstride                               */
+};
+
+int tb_abi_version(void);
+
+/* Message of the last failed call on ctx (ctx == NULL: last failed tb_create). */
+const char* tb_last_error(const tb_ctx* ctx);
+
+/* Upload a data set once.  Takes over `np.load(data_path)` / `np.load(labels_path)` of every worker
+ * (tblup/evaluator.py:215-216).  geno: [n][m] dosages in {0,1,2}, animal-major (the .npy layout);
+ * y: [n]; perm: [n] or NULL, animal stored at "universe" position p is perm[p] (put the animals the
+ * fitness reads first: training, validation, testing -- the Gram then only covers that prefix). */
+int tb_create(const int8_t* geno, int n, int m, const double* y, const int32_t* perm, int device, tb_ctx** out);
+int tb_destroy(tb_ctx* ctx);
+
+/* Define row set `slot`: the (train_indices, validation_indices) pair of tblup/evaluator.py:316-322,
+ * :485-491, :555-561 (original animal indices).  Precomputes the training-row dosage sums
+ * (np.mean(X_train, axis=0) of evaluator.py:304) and the centred phenotypes. */
+int tb_set_rowset(tb_ctx* ctx, int slot, const int32_t* train, int n_train, const int32_t* valid, int n_valid);
+
+/* Copy a batch of genomes (ragged marker-index lists, duplicates allowed; idx_off has P+1 entries) to
+ * the device: the payload of P enqueue() calls (tblup/evaluator.py:227-241, :392-393). */
+int tb_stage_genomes(tb_ctx* ctx, const int32_t* idx_flat, const int64_t* idx_off, int P);
+
+/* Evaluate the staged batch on each listed row set: fitness_out[i * n_slots + s] =
+ * BlupParallelEvaluator.blup(genome_i, train_s, valid_s, data, labels, h2) (tblup/evaluator.py:244-314),
+ * the work of the worker loop at evaluator.py:205-225 and the gather at :396-398.
+ * fitness_out is a host pointer, or a device pointer on ctx's device when out_is_device != 0. */
+int tb_eval_staged(tb_ctx* ctx, const int32_t* slots, int n_slots, double h2, int mode_rule,
+                   double* fitness_out, int out_is_device);
+
+/* tb_stage_genomes + tb_eval_staged with host buffers: one call per _evaluate() (evaluator.py:380-405). */
+int tb_eval(tb_ctx* ctx, const int32_t* slots, int n_slots, const int32_t* idx_flat, const int64_t* idx_off,
+            int P, double h2, int mode_rule, double* fitness_out);
+
+/* Raw uncentred cross-products of one genome over universe rows [0, rows): out[a*rows + b], b <= a
+ * (upper triangle zero).  impl 0 = tcgen05 kernel, 1 = plain dp4a verification kernel.
+ * The integer part of make_grm (tblup/utils.py:17). */
+int tb_gram_debug(tb_ctx* ctx, const int32_t* idx, int k, int rows, int impl, int32_t* out);
+
+int tb_debug_fetch(tb_ctx* ctx, int what, int job, void* out, size_t nbytes);
+
+/* options: "profile" (0/1: per-stage CUDA-event timing), "stop_after" (stage index, -1 = run all),
+ * "workspace_mb" (cap for the wave workspace, 0 = auto), "max_wave" (cap individuals per wave, 0 = auto) */
+int tb_set_option(tb_ctx* ctx, const char* name, long long value);
+
+/* Accumulated per-stage device milliseconds (valid with profile=1) and kernel launches since the last
+ * tb_reset_counters(); either pointer may be NULL. */
+int tb_stage_times(tb_ctx* ctx, double* ms_out, uint64_t* launches_out);
+uint64_t tb_launch_count(const tb_ctx* ctx);
+int tb_reset_counters(tb_ctx* ctx);
+int tb_last_wave(const tb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

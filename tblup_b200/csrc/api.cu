@@ -1,0 +1,699 @@
+// C-ABI of libtblup_b200 (see include/tblup_b200.h): context lifetime, row sets, genome staging and the
+// wave scheduler that drives gather -> centring terms -> tcgen05 Gram -> scale -> batched Cholesky ->
+// solve/predict/Pearson for one generation's batch.  Takes over _evaluate() / worker() / blup() of
+// tblup/evaluator.py:205-263,380-405.
+#include "tb_internal.h"
+#include "../../include/tblup_b200.h"
+
+#include <algorithm>
+#include <cmath>
+
+namespace {
+
+std::string g_create_err;
+
+struct Arena {
+  char* base = nullptr;
+  size_t off = 0, cap = 0;
+  template <typename T>
+  T* take(size_t n) {
+    off = (off + 255) & ~size_t(255);
+    T* p = reinterpret_cast<T*>(base + off);
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+int fail(TbCtx* c, const std::string& msg, int code = -1) {
+  c->err = msg;
+  return code;
+}
+
+void free_rowset(TbRowSet& r) {
+  cudaFree(r.d_tpos);
+  cudaFree(r.d_vpos);
+  cudaFree(r.d_colsum_train);
+  cudaFree(r.d_yt_raw);
+  cudaFree(r.d_yt_ctr);
+  cudaFree(r.d_yv);
+  r = TbRowSet();
+}
+
+size_t span_begin(TbCtx* c, int stage) {
+  if (!c->profile) return 0;
+  if (c->ev_used + 2 > c->ev_pool.size()) {
+    size_t old = c->ev_pool.size();
+    c->ev_pool.resize(old + 256);
+    for (size_t i = old; i < c->ev_pool.size(); ++i) cudaEventCreate(&c->ev_pool[i]);
+  }
+  size_t b = c->ev_used;
+  c->ev_used += 2;
+  cudaEventRecord(c->ev_pool[b], c->stream);
+  c->spans.push_back({stage, b, b + 1});
+  return b;
+}
+void span_end(TbCtx* c, size_t b) {
+  if (!c->profile) return;
+  cudaEventRecord(c->ev_pool[b + 1], c->stream);
+}
+void spans_collect(TbCtx* c) {
+  if (!c->profile) return;
+  for (auto& s : c->spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, c->ev_pool[s.b], c->ev_pool[s.e]) == cudaSuccess) c->stage_ms[s.stage] += ms;
+  }
+  c->spans.clear();
+  c->ev_used = 0;
+}
+inline void count(TbCtx* c, int stage, int n) {
+  c->stage_launches[stage] += n;
+  c->launches += n;
+}
+
+// all tiles (128 x 256) that intersect the lower triangle of [0, rpad)^2 and touch a training row or column
+void build_tiles(int rpad, const std::vector<unsigned char>& has_train, std::vector<int>& tiles) {
+  tiles.clear();
+  const int nI = rpad / TB_GRAM_BM, nJ = (rpad + TB_GRAM_BN - 1) / TB_GRAM_BN;
+  for (int I = 0; I < nI; ++I) {
+    for (int J = 0; J < nJ; ++J) {
+      if (J * TB_GRAM_BN > I * TB_GRAM_BM + TB_GRAM_BM - 1) continue;
+      bool need = has_train.empty() || has_train[I];
+      for (int h = 0; h < 2 && !need; ++h) {
+        int blk = 2 * J + h;
+        if (blk < nI && has_train[blk]) need = true;
+      }
+      if (need) tiles.push_back((I << 16) | J);
+    }
+  }
+}
+
+int ensure_ws(TbCtx* c, size_t bytes) {
+  if (bytes <= c->ws_bytes) return 0;
+  if (c->ws) cudaFree(c->ws);
+  c->ws = nullptr;
+  c->ws_bytes = 0;
+  TB_CUDA(c, cudaMalloc(&c->ws, bytes));
+  c->ws_bytes = bytes;
+  return 0;
+}
+
+struct SlotView {
+  const TbRowSet* rs;
+  size_t m_elems, linv_elems;
+};
+
+int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_rule, double* d_fit) {
+  if (c->P <= 0) return fail(c, "tb_eval_staged: no genomes staged");
+  if (n_slots <= 0 || n_slots > TB_MAX_SLOTS) return fail(c, "tb_eval_staged: bad n_slots");
+  if (!(h2 > 0.0) || !(h2 <= 1.0)) return fail(c, "tb_eval_staged: heritability must be in (0, 1]");
+  if (mode_rule < 0 || mode_rule > 2) return fail(c, "tb_eval_staged: bad mode_rule");
+  const double lambda = (1.0 - h2) / h2;   // tblup/evaluator.py:277
+  std::vector<SlotView> sv(n_slots);
+  int rpad = 0, max_ntp = 0, max_rows = 0;
+  std::vector<unsigned char> has_train;
+  size_t per_ind = 0;
+  for (int s = 0; s < n_slots; ++s) {
+    if (slots[s] < 0 || slots[s] >= TB_MAX_SLOTS || !c->slots[slots[s]].valid)
+      return fail(c, "tb_eval_staged: row set " + std::to_string(slots[s]) + " is not defined");
+    const TbRowSet* rs = &c->slots[slots[s]];
+    sv[s].rs = rs;
+    sv[s].m_elems = (size_t)(rs->ntp + rs->n_v) * rs->ntp;
+    sv[s].linv_elems = (size_t)rs->ntp * TB_NB;
+    rpad = std::max(rpad, rs->rpad);
+    max_ntp = std::max(max_ntp, rs->ntp);
+    max_rows = std::max(max_rows, rs->ntp + rs->n_v);
+    if (has_train.size() < rs->has_train.size()) has_train.resize(rs->has_train.size(), 0);
+    for (size_t i = 0; i < rs->has_train.size(); ++i) has_train[i] |= rs->has_train[i];
+    per_ind += (sv[s].m_elems + sv[s].linv_elems + rs->ntp + rs->n_v) * sizeof(double) + 1024;
+  }
+  has_train.resize(rpad / TB_GRAM_BM, 0);
+  const int P = c->P;
+  int kmax = 0;
+  for (int i = 0; i < P; ++i) {
+    const int k = (int)(c->h_off[i + 1] - c->h_off[i]);
+    if (k <= 0) return fail(c, "tb_eval_staged: empty genome at position " + std::to_string(i));
+    kmax = std::max(kmax, k);
+  }
+  const int kstride_max = tb_round_up(kmax, TB_GRAM_BK);
+  per_ind += (size_t)rpad * kstride_max + (size_t)rpad * rpad * sizeof(int32_t) +
+             (size_t)n_slots * (rpad + 2) * sizeof(long long) + 4096;
+
+  size_t free_b = 0, total_b = 0;
+  TB_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+  size_t budget = c->ws_limit ? c->ws_limit : (size_t)((double)(free_b + c->ws_bytes) * 0.80);
+  const size_t fixed = (size_t)128 * kstride_max + (size_t)P * n_slots * 256 + (1 << 20);
+  if (budget < fixed + per_ind) budget = fixed + per_ind;
+  long long Wll = (long long)((budget - fixed) / per_ind);
+  int W = (int)std::min<long long>(Wll, P);
+  if (c->max_wave > 0) W = std::min(W, c->max_wave);
+  W = std::max(1, std::min(W, 1024));
+  c->last_wave = W;
+  if (int rc = ensure_ws(c, fixed + per_ind * (size_t)W)) return rc;
+
+  cudaStream_t st = c->stream;
+  // tile list + genome offsets (device copies live at the start of the arena)
+  std::vector<int> tiles;
+  build_tiles(rpad, has_train, tiles);
+  const int n_tiles = (int)tiles.size();
+
+  Arena ar;
+  ar.base = (char*)c->ws;
+  ar.cap = c->ws_bytes;
+  int* d_tiles = ar.take<int>(tiles.size());
+  long long* d_off = ar.take<long long>(P + 1);
+  TB_CUDA(c, cudaMemcpyAsync(d_tiles, tiles.data(), tiles.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+  TB_CUDA(c, cudaMemcpyAsync(d_off, c->h_off.data(), (P + 1) * sizeof(long long), cudaMemcpyHostToDevice, st));
+  const size_t arena_mark = ar.off;
+
+  std::vector<TbScaleJob> h_scale;
+  std::vector<TbCholJob> h_chol;
+  std::vector<TbSolveJob> h_solve;
+  std::vector<const int*> h_cs;
+  std::vector<int> h_kb;
+
+  for (int w0 = 0; w0 < P; w0 += W) {
+    const int Wc = std::min(W, P - w0);
+    const int n_jobs = Wc * n_slots;
+    int kw = 0;
+    h_kb.resize(Wc);
+    for (int w = 0; w < Wc; ++w) {
+      const int k = (int)(c->h_off[w0 + w + 1] - c->h_off[w0 + w]);
+      kw = std::max(kw, k);
+      h_kb[w] = tb_round_up(k, TB_GRAM_BK) / TB_GRAM_BK;
+    }
+    const int kstride = tb_round_up(kw, TB_GRAM_BK);
+
+    ar.off = arena_mark;
+    int8_t* d_panel = ar.take<int8_t>(((size_t)Wc * rpad + 128) * kstride);
+    int32_t* d_C = ar.take<int32_t>((size_t)Wc * rpad * rpad);
+    long long* d_s = ar.take<long long>((size_t)n_jobs * rpad);
+    long long* d_SQ = ar.take<long long>((size_t)n_jobs * 2);
+    int* d_status = ar.take<int>(n_jobs);
+    int* d_kb = ar.take<int>(Wc);
+    const int** d_cs = ar.take<const int*>(n_jobs);
+    TbScaleJob* d_scale = ar.take<TbScaleJob>(n_jobs);
+    TbCholJob* d_chol = ar.take<TbCholJob>(n_jobs);
+    TbSolveJob* d_solve = ar.take<TbSolveJob>(n_jobs);
+
+    h_scale.resize(n_jobs);
+    h_chol.resize(n_jobs);
+    h_solve.resize(n_jobs);
+    h_cs.resize(n_jobs);
+    c->dbg.W = Wc;
+    c->dbg.n_slots = n_slots;
+    c->dbg.rpad = rpad;
+    c->dbg.kstride = kstride;
+    c->dbg.C = d_C;
+    c->dbg.s = d_s;
+    c->dbg.SQ = d_SQ;
+    c->dbg.M.assign(n_jobs, nullptr);
+    c->dbg.alpha.assign(n_jobs, nullptr);
+    c->dbg.pred.assign(n_jobs, nullptr);
+    c->dbg.ntp.assign(n_jobs, 0);
+    c->dbg.n_v.assign(n_jobs, 0);
+    for (int w = 0; w < Wc; ++w) {
+      const int k = (int)(c->h_off[w0 + w + 1] - c->h_off[w0 + w]);
+      const bool gblup = mode_rule == TB_MODE_GBLUP || (mode_rule == TB_MODE_AUTO && k > c->n);
+      for (int s = 0; s < n_slots; ++s) {
+        const int job = w * n_slots + s;
+        const TbRowSet* rs = sv[s].rs;
+        double* Mj = ar.take<double>(sv[s].m_elems);
+        double* Lj = ar.take<double>(sv[s].linv_elems);
+        double* aj = ar.take<double>(rs->ntp);
+        double* pj = ar.take<double>(rs->n_v);
+        h_cs[job] = gblup ? c->d_colsum_all : rs->d_colsum_train;
+        TbScaleJob& sj = h_scale[job];
+        sj.C = d_C + (size_t)w * rpad * rpad;
+        sj.s = d_s + (size_t)job * rpad;
+        sj.SQ = d_SQ + (size_t)job * 2;
+        sj.tpos = rs->d_tpos;
+        sj.vpos = rs->d_vpos;
+        sj.M = Mj;
+        sj.N = gblup ? c->n : rs->n_t;
+        sj.n_t = rs->n_t;
+        sj.n_v = rs->n_v;
+        sj.ntp = rs->ntp;
+        sj.rpad = rpad;
+        sj.lambda = lambda;
+        TbCholJob& cj = h_chol[job];
+        cj.M = Mj;
+        cj.Linv = Lj;
+        cj.ntp = rs->ntp;
+        cj.status = d_status + job;
+        TbSolveJob& oj = h_solve[job];
+        oj.M = Mj;
+        oj.Linv = Lj;
+        oj.y_t = gblup ? rs->d_yt_raw : rs->d_yt_ctr;
+        oj.y_v = rs->d_yv;
+        oj.status = d_status + job;
+        oj.alpha = aj;
+        oj.pred = pj;
+        oj.fitness = d_fit + (size_t)(w0 + w) * n_slots + s;
+        oj.n_t = rs->n_t;
+        oj.n_v = rs->n_v;
+        oj.ntp = rs->ntp;
+        c->dbg.M[job] = Mj;
+        c->dbg.alpha[job] = aj;
+        c->dbg.pred[job] = pj;
+        c->dbg.ntp[job] = rs->ntp;
+        c->dbg.n_v[job] = rs->n_v;
+      }
+    }
+    if (ar.off > ar.cap) return fail(c, "internal: wave workspace overflow");
+
+    size_t sp = span_begin(c, TB_ST_H2D);
+    TB_CUDA(c, cudaMemcpyAsync(d_kb, h_kb.data(), Wc * sizeof(int), cudaMemcpyHostToDevice, st));
+    TB_CUDA(c, cudaMemcpyAsync(d_cs, h_cs.data(), n_jobs * sizeof(int*), cudaMemcpyHostToDevice, st));
+    TB_CUDA(c, cudaMemcpyAsync(d_scale, h_scale.data(), n_jobs * sizeof(TbScaleJob), cudaMemcpyHostToDevice, st));
+    TB_CUDA(c, cudaMemcpyAsync(d_chol, h_chol.data(), n_jobs * sizeof(TbCholJob), cudaMemcpyHostToDevice, st));
+    TB_CUDA(c, cudaMemcpyAsync(d_solve, h_solve.data(), n_jobs * sizeof(TbSolveJob), cudaMemcpyHostToDevice, st));
+    TB_CUDA(c, cudaMemsetAsync(d_status, 0, n_jobs * sizeof(int), st));
+    span_end(c, sp);
+
+    sp = span_begin(c, TB_ST_GATHER);
+    TB_CUDA(c, tb_launch_gather(c->d_x, c->ldn, c->d_idx, d_off, w0, Wc, rpad, kstride, d_panel, st));
+    span_end(c, sp);
+    count(c, TB_ST_GATHER, 1);
+    if (c->stop_after == TB_ST_GATHER) continue;
+
+    sp = span_begin(c, TB_ST_CENTRE);
+    TB_CUDA(c, tb_launch_centre_terms(d_panel, rpad, kstride, c->d_idx, d_off, w0, Wc, n_slots, d_cs, d_s, d_SQ, st));
+    span_end(c, sp);
+    count(c, TB_ST_CENTRE, 2);
+    if (c->stop_after == TB_ST_CENTRE) continue;
+
+    sp = span_begin(c, TB_ST_GRAM);
+    {
+      std::string e;
+      cudaError_t ce = tb_launch_gram_tc(d_panel, Wc, rpad, kstride, d_kb, d_tiles, n_tiles, d_C, c->n_sm, st, &e);
+      if (ce != cudaSuccess) return fail(c, "gram launch: " + (e.empty() ? std::string(cudaGetErrorString(ce)) : e), -2);
+    }
+    span_end(c, sp);
+    count(c, TB_ST_GRAM, 1);
+    if (c->stop_after == TB_ST_GRAM) continue;
+
+    sp = span_begin(c, TB_ST_SCALE);
+    TB_CUDA(c, tb_launch_scale(d_scale, n_jobs, max_rows, max_ntp, st));
+    span_end(c, sp);
+    count(c, TB_ST_SCALE, 1);
+    if (c->stop_after == TB_ST_SCALE) continue;
+
+    const int nb = max_ntp / TB_NB;
+    for (int j = 0; j < nb; ++j) {
+      if (j > 0) {
+        sp = span_begin(c, TB_ST_CHOL_UPDATE);
+        TB_CUDA(c, tb_launch_chol_update(d_chol, n_jobs, max_ntp, j, st));
+        span_end(c, sp);
+        count(c, TB_ST_CHOL_UPDATE, 1);
+      }
+      sp = span_begin(c, TB_ST_CHOL_PANEL);
+      TB_CUDA(c, tb_launch_chol_diag(d_chol, n_jobs, max_ntp, j, st));
+      count(c, TB_ST_CHOL_PANEL, 1);
+      if (j + 1 < nb) {
+        TB_CUDA(c, tb_launch_chol_panel(d_chol, n_jobs, max_ntp, j, st));
+        count(c, TB_ST_CHOL_PANEL, 1);
+      }
+      span_end(c, sp);
+    }
+    if (c->stop_after == TB_ST_CHOL_UPDATE || c->stop_after == TB_ST_CHOL_PANEL) continue;
+
+    sp = span_begin(c, TB_ST_SOLVE);
+    TB_CUDA(c, tb_launch_solve(d_solve, n_jobs, max_ntp, st));
+    span_end(c, sp);
+    count(c, TB_ST_SOLVE, 1);
+  }
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int tb_abi_version(void) { return TB_ABI_VERSION; }
+
+const char* tb_last_error(const tb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
+
+int tb_create(const int8_t* geno, int n, int m, const double* y, const int32_t* perm, int device, tb_ctx** out) {
+  if (!out) return -1;
+  *out = nullptr;
+  if (!geno || !y || n <= 0 || m <= 0) {
+    g_create_err = "tb_create: null or empty input";
+    return -1;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    g_create_err = std::string("tb_create: no CUDA device (") + cudaGetErrorString(e) + "); there is no CPU fallback";
+    return -3;
+  }
+  if (device < 0 || device >= ndev) {
+    g_create_err = "tb_create: bad device ordinal";
+    return -1;
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) {
+    g_create_err = std::string("tb_create: device '") + prop.name + "' is sm_" + std::to_string(prop.major) +
+                   std::to_string(prop.minor) + "; this library is built for sm_100a only";
+    return -3;
+  }
+  TbCtx* c = new TbCtx();
+  auto bail = [&](const std::string& msg) {
+    g_create_err = msg.empty() ? c->err : msg;
+    tb_destroy(c);
+    return -2;
+  };
+  c->device = device;
+  c->n = n;
+  c->m = m;
+  c->ldn = tb_round_up(n, 128);
+  c->n_sm = prop.multiProcessorCount;
+  if (cudaSetDevice(device) != cudaSuccess) return bail("cudaSetDevice failed");
+  std::vector<int> p(n);
+  c->pos_of.assign(n, -1);
+  for (int i = 0; i < n; ++i) {
+    p[i] = perm ? perm[i] : i;
+    if (p[i] < 0 || p[i] >= n || c->pos_of[p[i]] != -1) return bail("tb_create: perm is not a permutation of 0..n-1");
+    c->pos_of[p[i]] = i;
+  }
+  c->y_univ.resize(n);
+  for (int i = 0; i < n; ++i) c->y_univ[i] = y[p[i]];
+
+  auto chk = [&](cudaError_t ce, const char* what) {
+    if (ce == cudaSuccess) return false;
+    c->err = std::string(what) + ": " + cudaGetErrorString(ce);
+    return true;
+  };
+  if (chk(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return bail("");
+  if (chk(cudaMalloc(&c->d_x, (size_t)m * c->ldn), "cudaMalloc genotypes")) return bail("");
+  if (chk(cudaMemsetAsync(c->d_x, 0, (size_t)m * c->ldn, c->stream), "memset")) return bail("");
+  if (chk(cudaMalloc(&c->d_colsum_all, (size_t)m * sizeof(int)), "cudaMalloc colsum")) return bail("");
+
+  // upload in universe order, transposing chunks of animals to SNP-major on the device
+  int chunk = (int)std::max<long long>(64, std::min<long long>(n, ((long long)256 << 20) / m));
+  chunk = std::min(chunk, n);
+  int8_t *h_stage = nullptr, *d_stage = nullptr;
+  if (chk(cudaMallocHost(&h_stage, (size_t)chunk * m), "cudaMallocHost staging")) return bail("");
+  if (chk(cudaMalloc(&d_stage, (size_t)chunk * m), "cudaMalloc staging")) {
+    cudaFreeHost(h_stage);
+    return bail("");
+  }
+  bool bad_value = false, cuda_bad = false;
+  for (int p0 = 0; p0 < n && !cuda_bad && !bad_value; p0 += chunk) {
+    const int rows = std::min(chunk, n - p0);
+    unsigned char maxv = 0;
+    for (int r = 0; r < rows; ++r) {
+      const int8_t* src = geno + (size_t)p[p0 + r] * m;
+      int8_t* dst = h_stage + (size_t)r * m;
+      for (int j = 0; j < m; ++j) {
+        const int8_t v = src[j];
+        dst[j] = v;
+        maxv = std::max(maxv, (unsigned char)v);   // negative values map to >= 128
+      }
+    }
+    if (maxv > 2) {
+      bad_value = true;
+      break;
+    }
+    cuda_bad |= chk(cudaMemcpyAsync(d_stage, h_stage, (size_t)rows * m, cudaMemcpyHostToDevice, c->stream), "H2D genotypes");
+    cuda_bad |= chk(tb_launch_transpose_rows(d_stage, rows, m, c->d_x, c->ldn, p0, c->stream), "transpose");
+    cuda_bad |= chk(cudaStreamSynchronize(c->stream), "sync after transpose");
+    c->launches += 1;
+  }
+  cudaFreeHost(h_stage);
+  cudaFree(d_stage);
+  if (bad_value) return bail("tb_create: genotype values must be dosages in {0, 1, 2}");
+  if (cuda_bad) return bail("");
+  {
+    std::vector<int> ident(n);
+    for (int i = 0; i < n; ++i) ident[i] = i;
+    int* d_pos = nullptr;
+    if (chk(cudaMalloc(&d_pos, n * sizeof(int)), "cudaMalloc")) return bail("");
+    bool b2 = chk(cudaMemcpyAsync(d_pos, ident.data(), n * sizeof(int), cudaMemcpyHostToDevice, c->stream), "H2D");
+    b2 |= chk(tb_launch_colsum(c->d_x, c->ldn, m, d_pos, n, c->d_colsum_all, c->stream), "colsum");
+    b2 |= chk(cudaStreamSynchronize(c->stream), "sync after colsum");
+    cudaFree(d_pos);
+    c->launches += 1;
+    if (b2) return bail("");
+  }
+  if (chk(tb_gram_tc_init(), "gram kernel init") || chk(tb_chol_init(), "cholesky kernel init") ||
+      chk(tb_solve_init(), "solve kernel init"))
+    return bail("");
+  *out = c;
+  return 0;
+}
+
+int tb_destroy(tb_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  for (auto& r : c->slots) free_rowset(r);
+  for (auto ev : c->ev_pool) cudaEventDestroy(ev);
+  cudaFree(c->d_x);
+  cudaFree(c->d_colsum_all);
+  cudaFree(c->d_idx);
+  cudaFree(c->ws);
+  if (c->stream) cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+int tb_set_rowset(tb_ctx* c, int slot, const int32_t* train, int n_t, const int32_t* valid, int n_v) {
+  if (!c) return -1;
+  if (slot < 0 || slot >= TB_MAX_SLOTS) return fail(c, "tb_set_rowset: slot out of range");
+  if (!train || !valid || n_t < 2 || n_v < 2) return fail(c, "tb_set_rowset: need at least 2 training and 2 validation animals");
+  TB_CUDA(c, cudaSetDevice(c->device));
+  TB_CUDA(c, cudaStreamSynchronize(c->stream));
+  TbRowSet& r = c->slots[slot];
+  free_rowset(r);
+  std::vector<int> tpos(n_t), vpos(n_v);
+  int maxpos = 0;
+  for (int i = 0; i < n_t; ++i) {
+    if (train[i] < 0 || train[i] >= c->n) return fail(c, "tb_set_rowset: training index out of range");
+    tpos[i] = c->pos_of[train[i]];
+    maxpos = std::max(maxpos, tpos[i]);
+  }
+  for (int i = 0; i < n_v; ++i) {
+    if (valid[i] < 0 || valid[i] >= c->n) return fail(c, "tb_set_rowset: validation index out of range");
+    vpos[i] = c->pos_of[valid[i]];
+    maxpos = std::max(maxpos, vpos[i]);
+  }
+  r.n_t = n_t;
+  r.n_v = n_v;
+  r.ntp = tb_round_up(n_t, TB_NB);
+  r.rows = maxpos + 1;
+  r.rpad = tb_round_up(r.rows, TB_GRAM_BM);
+  r.has_train.assign(r.rpad / TB_GRAM_BM, 0);
+  for (int i = 0; i < n_t; ++i) r.has_train[tpos[i] / TB_GRAM_BM] = 1;
+  std::vector<double> yt(r.ntp, 0.0), ytc(r.ntp, 0.0), yv(n_v);
+  double mean = 0.0;
+  for (int i = 0; i < n_t; ++i) {
+    yt[i] = c->y_univ[tpos[i]];
+    mean += yt[i];
+  }
+  mean /= n_t;
+  for (int i = 0; i < n_t; ++i) ytc[i] = yt[i] - mean;
+  for (int i = 0; i < n_v; ++i) yv[i] = c->y_univ[vpos[i]];
+  TB_CUDA(c, cudaMalloc(&r.d_tpos, n_t * sizeof(int)));
+  TB_CUDA(c, cudaMalloc(&r.d_vpos, n_v * sizeof(int)));
+  TB_CUDA(c, cudaMalloc(&r.d_colsum_train, (size_t)c->m * sizeof(int)));
+  TB_CUDA(c, cudaMalloc(&r.d_yt_raw, r.ntp * sizeof(double)));
+  TB_CUDA(c, cudaMalloc(&r.d_yt_ctr, r.ntp * sizeof(double)));
+  TB_CUDA(c, cudaMalloc(&r.d_yv, n_v * sizeof(double)));
+  TB_CUDA(c, cudaMemcpyAsync(r.d_tpos, tpos.data(), n_t * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  TB_CUDA(c, cudaMemcpyAsync(r.d_vpos, vpos.data(), n_v * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  TB_CUDA(c, cudaMemcpyAsync(r.d_yt_raw, yt.data(), r.ntp * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  TB_CUDA(c, cudaMemcpyAsync(r.d_yt_ctr, ytc.data(), r.ntp * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  TB_CUDA(c, cudaMemcpyAsync(r.d_yv, yv.data(), n_v * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  TB_CUDA(c, tb_launch_colsum(c->d_x, c->ldn, c->m, r.d_tpos, n_t, r.d_colsum_train, c->stream));
+  c->launches += 1;
+  TB_CUDA(c, cudaStreamSynchronize(c->stream));
+  r.valid = true;
+  return 0;
+}
+
+int tb_stage_genomes(tb_ctx* c, const int32_t* idx_flat, const int64_t* idx_off, int P) {
+  if (!c) return -1;
+  if (!idx_flat || !idx_off || P <= 0) return fail(c, "tb_stage_genomes: null or empty batch");
+  if (idx_off[0] != 0) return fail(c, "tb_stage_genomes: idx_off[0] must be 0");
+  for (int i = 0; i < P; ++i)
+    if (idx_off[i + 1] < idx_off[i]) return fail(c, "tb_stage_genomes: offsets must be non-decreasing");
+  const size_t total = (size_t)idx_off[P];
+  for (size_t q = 0; q < total; ++q)
+    if (idx_flat[q] < 0 || idx_flat[q] >= c->m)
+      return fail(c, "tb_stage_genomes: marker index " + std::to_string(idx_flat[q]) + " out of range [0, " +
+                         std::to_string(c->m) + ")");
+  TB_CUDA(c, cudaSetDevice(c->device));
+  if (total > c->idx_cap) {
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->d_idx);
+    c->d_idx = nullptr;
+    c->idx_cap = 0;
+    TB_CUDA(c, cudaMalloc(&c->d_idx, std::max<size_t>(total, 1) * sizeof(int)));
+    c->idx_cap = total;
+  }
+  size_t sp = span_begin(c, TB_ST_H2D);
+  TB_CUDA(c, cudaMemcpyAsync(c->d_idx, idx_flat, total * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  span_end(c, sp);
+  c->h_off.assign(idx_off, idx_off + P + 1);
+  c->P = P;
+  return 0;
+}
+
+int tb_eval_staged(tb_ctx* c, const int32_t* slots, int n_slots, double h2, int mode_rule, double* fitness_out,
+                   int out_is_device) {
+  if (!c) return -1;
+  if (!slots || !fitness_out) return fail(c, "tb_eval_staged: null argument");
+  TB_CUDA(c, cudaSetDevice(c->device));
+  const size_t n_out = (size_t)c->P * (size_t)std::max(n_slots, 0);
+  double* d_fit = fitness_out;
+  double* d_tmp = nullptr;
+  if (!out_is_device) {
+    TB_CUDA(c, cudaMalloc(&d_tmp, std::max<size_t>(n_out, 1) * sizeof(double)));
+    d_fit = d_tmp;
+  }
+  int rc = eval_core(c, slots, n_slots, h2, mode_rule, d_fit);
+  cudaError_t ce = cudaSuccess;
+  if (rc == 0 && !out_is_device) {
+    size_t sp = span_begin(c, TB_ST_D2H);
+    ce = cudaMemcpyAsync(fitness_out, d_tmp, n_out * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    span_end(c, sp);
+  }
+  cudaError_t se = cudaStreamSynchronize(c->stream);
+  spans_collect(c);
+  if (d_tmp) cudaFree(d_tmp);
+  if (rc != 0) return rc;
+  if (ce != cudaSuccess) return fail(c, std::string("D2H fitness: ") + cudaGetErrorString(ce), -2);
+  if (se != cudaSuccess) return fail(c, std::string("device execution failed: ") + cudaGetErrorString(se), -2);
+  return 0;
+}
+
+int tb_eval(tb_ctx* c, const int32_t* slots, int n_slots, const int32_t* idx_flat, const int64_t* idx_off, int P,
+            double h2, int mode_rule, double* fitness_out) {
+  int rc = tb_stage_genomes(c, idx_flat, idx_off, P);
+  if (rc) return rc;
+  return tb_eval_staged(c, slots, n_slots, h2, mode_rule, fitness_out, 0);
+}
+
+int tb_gram_debug(tb_ctx* c, const int32_t* idx, int k, int rows, int impl, int32_t* out) {
+  if (!c) return -1;
+  if (!idx || !out || k <= 0 || rows <= 0 || rows > c->n) return fail(c, "tb_gram_debug: bad argument");
+  for (int q = 0; q < k; ++q)
+    if (idx[q] < 0 || idx[q] >= c->m) return fail(c, "tb_gram_debug: marker index out of range");
+  TB_CUDA(c, cudaSetDevice(c->device));
+  const int rpad = tb_round_up(rows, TB_GRAM_BM), kstride = tb_round_up(k, TB_GRAM_BK);
+  std::vector<int> tiles;
+  build_tiles(rpad, std::vector<unsigned char>(), tiles);
+  const long long off[2] = {0, k};
+  const int kb = kstride / TB_GRAM_BK;
+  int8_t* d_panel = nullptr;
+  int32_t* d_C = nullptr;
+  int *d_i = nullptr, *d_t = nullptr, *d_kb = nullptr;
+  long long* d_off = nullptr;
+  cudaStream_t st = c->stream;
+  int rc = 0;
+  auto ck = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess && rc == 0) rc = fail(c, std::string("tb_gram_debug ") + what + ": " + cudaGetErrorString(e), -2);
+  };
+  ck(cudaMalloc(&d_panel, ((size_t)rpad + 128) * kstride), "malloc");
+  ck(cudaMalloc(&d_C, (size_t)rpad * rpad * sizeof(int32_t)), "malloc");
+  ck(cudaMalloc(&d_i, k * sizeof(int)), "malloc");
+  ck(cudaMalloc(&d_t, tiles.size() * sizeof(int)), "malloc");
+  ck(cudaMalloc(&d_kb, sizeof(int)), "malloc");
+  ck(cudaMalloc(&d_off, 2 * sizeof(long long)), "malloc");
+  if (rc == 0) {
+    ck(cudaMemsetAsync(d_C, 0, (size_t)rpad * rpad * sizeof(int32_t), st), "memset");
+    ck(cudaMemcpyAsync(d_i, idx, k * sizeof(int), cudaMemcpyHostToDevice, st), "H2D");
+    ck(cudaMemcpyAsync(d_t, tiles.data(), tiles.size() * sizeof(int), cudaMemcpyHostToDevice, st), "H2D");
+    ck(cudaMemcpyAsync(d_kb, &kb, sizeof(int), cudaMemcpyHostToDevice, st), "H2D");
+    ck(cudaMemcpyAsync(d_off, off, sizeof(off), cudaMemcpyHostToDevice, st), "H2D");
+    ck(tb_launch_gather(c->d_x, c->ldn, d_i, d_off, 0, 1, rpad, kstride, d_panel, st), "gather");
+    if (impl == 0) {
+      std::string e;
+      cudaError_t ce = tb_launch_gram_tc(d_panel, 1, rpad, kstride, d_kb, d_t, (int)tiles.size(), d_C, c->n_sm, st, &e);
+      if (ce != cudaSuccess && rc == 0) rc = fail(c, "tb_gram_debug gram_tc: " + (e.empty() ? std::string(cudaGetErrorString(ce)) : e), -2);
+    } else {
+      ck(tb_launch_gram_simt(d_panel, 1, rpad, kstride, d_kb, d_C, st), "gram_simt");
+    }
+    c->launches += 2;
+    std::vector<int32_t> h((size_t)rpad * rpad);
+    ck(cudaMemcpyAsync(h.data(), d_C, h.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st), "D2H");
+    ck(cudaStreamSynchronize(st), "execution");
+    if (rc == 0) {
+      for (int a = 0; a < rows; ++a)
+        for (int b = 0; b < rows; ++b) out[(size_t)a * rows + b] = b <= a ? h[(size_t)a * rpad + b] : 0;
+    }
+  }
+  cudaFree(d_panel);
+  cudaFree(d_C);
+  cudaFree(d_i);
+  cudaFree(d_t);
+  cudaFree(d_kb);
+  cudaFree(d_off);
+  return rc;
+}
+
+int tb_debug_fetch(tb_ctx* c, int what, int job, void* out, size_t nbytes) {
+  if (!c) return -1;
+  if (!out) return fail(c, "tb_debug_fetch: null output");
+  const auto& d = c->dbg;
+  const int n_jobs = d.W * d.n_slots;
+  if (n_jobs == 0) return fail(c, "tb_debug_fetch: nothing evaluated yet");
+  if (job < 0 || job >= n_jobs) return fail(c, "tb_debug_fetch: job out of range");
+  TB_CUDA(c, cudaSetDevice(c->device));
+  const void* src = nullptr;
+  size_t need = 0;
+  int dims[4] = {d.rpad, d.ntp[job], d.n_v[job], d.kstride};
+  switch (what) {
+    case TB_DBG_C: src = d.C + (size_t)(job / d.n_slots) * d.rpad * d.rpad; need = (size_t)d.rpad * d.rpad * 4; break;
+    case TB_DBG_S: src = d.s + (size_t)job * d.rpad; need = (size_t)d.rpad * 8; break;
+    case TB_DBG_SQ: src = d.SQ + (size_t)job * 2; need = 16; break;
+    case TB_DBG_M: src = d.M[job]; need = (size_t)(d.ntp[job] + d.n_v[job]) * d.ntp[job] * 8; break;
+    case TB_DBG_ALPHA: src = d.alpha[job]; need = (size_t)d.ntp[job] * 8; break;
+    case TB_DBG_PRED: src = d.pred[job]; need = (size_t)d.n_v[job] * 8; break;
+    case TB_DBG_DIMS:
+      if (nbytes < sizeof(dims)) return fail(c, "tb_debug_fetch: buffer too small");
+      memcpy(out, dims, sizeof(dims));
+      return 0;
+    default: return fail(c, "tb_debug_fetch: unknown item");
+  }
+  if (nbytes < need) return fail(c, "tb_debug_fetch: buffer too small (need " + std::to_string(need) + " bytes)");
+  TB_CUDA(c, cudaMemcpy(out, src, need, cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+int tb_set_option(tb_ctx* c, const char* name, long long value) {
+  if (!c || !name) return -1;
+  const std::string s(name);
+  if (s == "profile") c->profile = value != 0;
+  else if (s == "stop_after") c->stop_after = (int)value;
+  else if (s == "workspace_mb") c->ws_limit = value > 0 ? (size_t)value << 20 : 0;
+  else if (s == "max_wave") c->max_wave = (int)value;
+  else return fail(c, "tb_set_option: unknown option '" + s + "'");
+  return 0;
+}
+
+int tb_stage_times(tb_ctx* c, double* ms_out, uint64_t* launches_out) {
+  if (!c) return -1;
+  for (int i = 0; i < TB_ST_COUNT; ++i) {
+    if (ms_out) ms_out[i] = c->stage_ms[i];
+    if (launches_out) launches_out[i] = c->stage_launches[i];
+  }
+  return 0;
+}
+
+uint64_t tb_launch_count(const tb_ctx* c) { return c ? c->launches : 0; }
+
+int tb_reset_counters(tb_ctx* c) {
+  if (!c) return -1;
+  for (int i = 0; i < TB_ST_COUNT; ++i) {
+    c->stage_ms[i] = 0.0;
+    c->stage_launches[i] = 0;
+  }
+  c->launches = 0;
+  return 0;
+}
+
+int tb_last_wave(const tb_ctx* c) { return c ? c->last_wave : 0; }
+
+}  // extern "C"

@@ -1,0 +1,144 @@
+// Marker gather for one wave of individuals, and the integer ingredients of the exact centring.
+//
+//   panel[w][a][j] = x[idx_w[j]][a]          (a: universe animal position, j: position in the genome)
+//
+// i.e. the reference's `data[:, indices]` (tblup/evaluator.py:275 and :298) restricted to the animals the
+// fitness depends on, written K-major (markers contiguous) so the tcgen05 Gram kernel can stream it with
+// TMA.  A marker listed twice is copied twice (numpy fancy-indexing semantics).  HBM-bound: every
+// selected marker row is read once (coalesced, 128 B per warp) and every panel byte written once.
+#include "tb_internal.h"
+
+namespace {
+
+// 128 markers x 128 animals per block, transposed through shared memory as 32-bit words.
+// Word (jl, c) holds animals 4c..4c+3 of marker jl and is stored at column (c + (jl >> 2)) & 31,
+// which makes both the row-wise fill and the 4x4 byte-transposing drain bank-conflict free.
+__global__ void __launch_bounds__(256) gather_kernel(const int8_t* __restrict__ x, int ldn,
+                                                     const int* __restrict__ idx, const long long* __restrict__ off,
+                                                     int w0, int rpad, int kstride, int8_t* __restrict__ panel) {
+  __shared__ uint32_t tile[128][32];
+  const int w = blockIdx.z;
+  const long long o0 = off[w0 + w];
+  const int k = (int)(off[w0 + w + 1] - o0);
+  const int j0 = blockIdx.x * 128;
+  if (j0 >= tb_round_up(k, TB_GRAM_BK)) return;  // beyond this individual's (padded) K extent: never read
+  const int a0 = blockIdx.y * 128;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  for (int jl = warp; jl < 128; jl += 8) {
+    const int j = j0 + jl;
+    uint32_t v = 0;
+    if (j < k) {
+      const int src = idx[o0 + j];
+      v = *reinterpret_cast<const uint32_t*>(x + (size_t)src * ldn + a0 + lane * 4);
+    }
+    tile[jl][(lane + (jl >> 2)) & 31] = v;
+  }
+  __syncthreads();
+
+  int8_t* out = panel + ((size_t)w * rpad + a0) * kstride + j0;
+  // each warp drains 4 animals (one word column c) per iteration; lane q covers markers 4q..4q+3
+  for (int c = warp; c < 32; c += 8) {
+    const int q = lane;
+    const int col = (c + q) & 31;
+    const uint32_t r0 = tile[4 * q + 0][col], r1 = tile[4 * q + 1][col], r2 = tile[4 * q + 2][col],
+                   r3 = tile[4 * q + 3][col];
+    // 4x4 byte transpose: output word for animal 4c+i = bytes i of (r0, r1, r2, r3)
+    const uint32_t t0 = __byte_perm(r0, r1, 0x5140);  // r0.b0 r1.b0 r0.b1 r1.b1
+    const uint32_t t1 = __byte_perm(r2, r3, 0x5140);
+    const uint32_t t2 = __byte_perm(r0, r1, 0x7362);  // r0.b2 r1.b2 r0.b3 r1.b3
+    const uint32_t t3 = __byte_perm(r2, r3, 0x7362);
+    const uint32_t o_0 = __byte_perm(t0, t1, 0x5410);
+    const uint32_t o_1 = __byte_perm(t0, t1, 0x7632);
+    const uint32_t o_2 = __byte_perm(t2, t3, 0x5410);
+    const uint32_t o_3 = __byte_perm(t2, t3, 0x7632);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out + (size_t)(4 * c) * kstride) + q;
+    const size_t rs = kstride / 4;
+    dst[0] = o_0;
+    dst[rs] = o_1;
+    dst[2 * rs] = o_2;
+    dst[3 * rs] = o_3;
+  }
+}
+
+// s[a] = sum_j panel[a][j] * colsum[idx[j]]  (exact, int64).  One warp per animal row.
+__global__ void __launch_bounds__(256) centre_rows_kernel(const int8_t* __restrict__ panel, int rpad, int kstride,
+                                                          const int* __restrict__ idx,
+                                                          const long long* __restrict__ off, int w0, int n_slots,
+                                                          const int* const* __restrict__ colsum_of,
+                                                          long long* __restrict__ s) {
+  const int job = blockIdx.y;  // w * n_slots + slot
+  const int w = job / n_slots;
+  const int a = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (a >= rpad) return;
+  const long long o0 = off[w0 + w];
+  const int k = (int)(off[w0 + w + 1] - o0);
+  const int* cs = colsum_of[job];
+  const int8_t* row = panel + ((size_t)w * rpad + a) * kstride;
+  long long acc = 0;
+  for (int j = lane * 4; j < k; j += 128) {
+    const uint32_t v = *reinterpret_cast<const uint32_t*>(row + j);  // bytes past k are zero padding
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      if (j + b < k) acc += (long long)((v >> (8 * b)) & 0xff) * (long long)cs[idx[o0 + j + b]];
+    }
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) s[(size_t)job * rpad + a] = acc;
+}
+
+// SQ[job] = { sum_j colsum[idx[j]], sum_j colsum[idx[j]]^2 }.
+__global__ void __launch_bounds__(256) centre_sq_kernel(const int* __restrict__ idx, const long long* __restrict__ off,
+                                                        int w0, int n_slots, const int* const* __restrict__ colsum_of,
+                                                        long long* __restrict__ SQ) {
+  __shared__ long long sh[2][8];
+  const int job = blockIdx.x, w = job / n_slots;
+  const long long o0 = off[w0 + w];
+  const int k = (int)(off[w0 + w + 1] - o0);
+  const int* cs = colsum_of[job];
+  long long S = 0, Q = 0;
+  for (int j = threadIdx.x; j < k; j += blockDim.x) {
+    const long long c = cs[idx[o0 + j]];
+    S += c;
+    Q += c * c;
+  }
+  for (int o = 16; o; o >>= 1) {
+    S += __shfl_xor_sync(0xffffffffu, S, o);
+    Q += __shfl_xor_sync(0xffffffffu, Q, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    sh[0][threadIdx.x >> 5] = S;
+    sh[1][threadIdx.x >> 5] = Q;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    S = Q = 0;
+    for (int i = 0; i < 8; ++i) {
+      S += sh[0][i];
+      Q += sh[1][i];
+    }
+    SQ[2 * job] = S;
+    SQ[2 * job + 1] = Q;
+  }
+}
+
+}  // namespace
+
+cudaError_t tb_launch_gather(const int8_t* d_x, int ldn, const int* d_idx, const long long* d_off, int w0, int W,
+                             int rpad, int kstride, int8_t* d_panel, cudaStream_t st) {
+  dim3 grid(kstride / 128, rpad / 128, W);
+  gather_kernel<<<grid, 256, 0, st>>>(d_x, ldn, d_idx, d_off, w0, rpad, kstride, d_panel);
+  return cudaGetLastError();
+}
+
+cudaError_t tb_launch_centre_terms(const int8_t* d_panel, int rpad, int kstride, const int* d_idx,
+                                   const long long* d_off, int w0, int W, int n_slots,
+                                   const int* const* d_colsum_of, long long* d_s, long long* d_SQ,
+                                   cudaStream_t st) {
+  dim3 grid((rpad + 7) / 8, W * n_slots);
+  centre_rows_kernel<<<grid, 256, 0, st>>>(d_panel, rpad, kstride, d_idx, d_off, w0, n_slots, d_colsum_of, d_s);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  centre_sq_kernel<<<W * n_slots, 256, 0, st>>>(d_idx, d_off, w0, n_slots, d_colsum_of, d_SQ);
+  return cudaGetLastError();
+}

@@ -1,0 +1,212 @@
+// Masked Gram kernel: C_w = Z_w Z_w^T (uncentred integer cross-products) for a wave of individuals,
+// where Z_w = panel[w] is the K-major int8 gather of the individual's markers.
+//
+// This is the `np.matmul(W, W^T)` of tblup/utils.py:17 (called from tblup/evaluator.py:275) with the
+// centring factored out: the uncentred cross-products are exact integers (bit-for-bit equal to the
+// oracle), the centring is applied afterwards as exact rank-1 integer corrections (scale.cu).
+//
+// sm_100a design: persistent, warp-specialised, one CTA per SM.
+//   warp 0      TMA producer   cp.async.bulk.tensor 2-D loads (128-byte swizzle) into a 4-stage smem ring
+//   warp 1      MMA issuer     one thread issues tcgen05.mma.kind::i8 (M=128, N=256, K=32), s32 accumulators
+//                              in TMEM, two accumulator stages (2 x 256 columns) so the epilogue of tile t
+//                              overlaps the main loop of tile t+1
+//   warps 2..5  epilogue       tcgen05.ld 32x32b -> registers -> 16-byte global stores of the int32 tile
+// Only tiles that touch the lower triangle are scheduled (tile list built on the host per row set).
+#include "tb_internal.h"
+#include "tb_ptx.cuh"
+
+namespace {
+
+using namespace tbptx;
+
+constexpr int BM = TB_GRAM_BM, BN = TB_GRAM_BN, BK = TB_GRAM_BK;
+constexpr int STAGES = 4;
+constexpr int A_BYTES = BM * BK;                 // 16 KiB
+constexpr int B_BYTES = BN * BK;                 // 32 KiB
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 48 KiB
+constexpr int ACC_STAGES = 2;
+constexpr int TMEM_COLS = ACC_STAGES * BN;       // 512
+constexpr int NUM_THREADS = 192;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr uint32_t IDESC = umma_idesc_s8(BM, BN);
+
+struct Barriers {
+  uint64_t full[STAGES];
+  uint64_t empty[STAGES];
+  uint64_t acc_full[ACC_STAGES];
+  uint64_t acc_empty[ACC_STAGES];
+  uint32_t tmem_base;
+};
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int* __restrict__ tiles, int n_tiles,
+               const int* __restrict__ kblocks, int W, int rpad, int32_t* __restrict__ C) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + STAGES * STAGE_BYTES);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = W * n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmap);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int s = 0; s < ACC_STAGES; ++s) {
+      mbar_init(&bars->acc_full[s], 1);
+      mbar_init(&bars->acc_empty[s], 4);   // one arrival per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int w = item / n_tiles, t = tiles[item - w * n_tiles];
+        const int row_a = w * rpad + (t >> 16) * BM;
+        const int row_b = w * rpad + (t & 0xffff) * BN;
+        const int nkb = kblocks[w];
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          mbar_arrive_expect_tx(&bars->full[stage], STAGE_BYTES);
+          tma_load_2d(sa, &tmap, &bars->full[stage], kb * BK, row_a);
+          tma_load_2d(sa + A_BYTES, &tmap, &bars->full[stage], kb * BK, row_b);
+          tma_load_2d(sa + A_BYTES + B_BYTES / 2, &tmap, &bars->full[stage], kb * BK, row_b + BN / 2);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int w = item / n_tiles;
+        const int nkb = kblocks[w];
+        mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t adesc = umma_desc_k_sw128(sa);
+          const uint64_t bdesc = umma_desc_k_sw128(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / 32; ++k) {
+            // advance 32 bytes along K inside the 128-byte swizzle span: +2 in 16-byte units
+            umma_s8(tmem_d, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+          }
+          umma_commit(&bars->empty[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&bars->acc_full[acc]);
+        if (++acc == ACC_STAGES) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (4 warps) =====================
+    const int q = warp & 3;   // TMEM lane quarter this warp may access
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int w = item / n_tiles, t = tiles[item - w * n_tiles];
+      const int ti = t >> 16, tj = t & 0xffff;
+      const int row = ti * BM + q * 32 + lane;
+      const int row_hi = ti * BM + BM - 1;
+      mbar_wait(&bars->acc_full[acc], acc_phase);
+      tc_fence_after();
+      int32_t* crow = C + ((size_t)w * rpad + row) * rpad;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = tj * BN + c * 32;
+        if (col0 >= rpad || col0 > row_hi) continue;   // outside the matrix / strictly above the diagonal
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, v);
+        tmem_ld_wait();
+        int4* dst = reinterpret_cast<int4*>(crow + col0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          dst[i] = make_int4((int)v[4 * i], (int)v[4 * i + 1], (int)v[4 * i + 2], (int)v[4 * i + 3]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+      if (++acc == ACC_STAGES) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+
+}  // namespace
+
+cudaError_t tb_gram_tc_init() {
+  if (!g_encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess) return e;
+    if (!fn || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+    g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  return cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+}
+
+// d_panel must have (W * rpad + 128) rows of kstride bytes allocated (slack for the last B half-tile).
+cudaError_t tb_launch_gram_tc(const int8_t* d_panel, int W, int rpad, int kstride, const int* d_kblocks,
+                              const int* d_tiles, int n_tiles, int32_t* d_C, int n_sm, cudaStream_t st,
+                              std::string* err) {
+  CUtensorMap tmap;
+  const cuuint64_t dims[2] = {(cuuint64_t)kstride, (cuuint64_t)W * rpad + 128};
+  const cuuint64_t strides[1] = {(cuuint64_t)kstride};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, 128};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(d_panel), dims, strides, box,
+                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
+    return cudaErrorInvalidValue;
+  }
+  const int n_items = W * n_tiles;
+  const int grid = n_items < n_sm ? n_items : n_sm;
+  gram_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmap, d_tiles, n_tiles, d_kblocks, W, rpad, d_C);
+  return cudaGetLastError();
+}

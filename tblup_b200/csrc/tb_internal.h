@@ -1,0 +1,166 @@
+// Internal declarations shared by the translation units of libtblup_b200.so (not part of the C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#define TB_MAX_SLOTS 64
+#define TB_NB 64          // Cholesky block size (rows/cols per block column)
+#define TB_GRAM_BM 128    // Gram tile rows
+#define TB_GRAM_BN 256    // Gram tile cols
+#define TB_GRAM_BK 128    // Gram K bytes per pipeline stage (one 128-byte swizzle span)
+
+enum TbStage {
+  TB_ST_H2D = 0,
+  TB_ST_GATHER,
+  TB_ST_CENTRE,
+  TB_ST_GRAM,
+  TB_ST_SCALE,
+  TB_ST_CHOL_UPDATE,
+  TB_ST_CHOL_PANEL,
+  TB_ST_SOLVE,
+  TB_ST_D2H,
+  TB_ST_COUNT
+};
+
+struct TbRowSet {
+  bool valid = false;
+  int n_t = 0, n_v = 0;
+  int ntp = 0;          // n_t rounded up to TB_NB
+  int rows = 0;         // universe rows the Gram must cover (1 + max position used)
+  int rpad = 0;         // rows rounded up to TB_GRAM_BM
+  int* d_tpos = nullptr;        // [n_t] universe positions of the training animals
+  int* d_vpos = nullptr;        // [n_v]
+  int* d_colsum_train = nullptr;  // [m] dosage sums over the training animals
+  double* d_yt_raw = nullptr;   // [ntp] (zero padded)
+  double* d_yt_ctr = nullptr;   // [ntp] y_t minus its mean
+  double* d_yv = nullptr;       // [n_v]
+  std::vector<unsigned char> has_train;   // per 128-row universe block: contains a training animal
+};
+
+struct TbCtx {
+  int device = 0;
+  int n = 0, m = 0, ldn = 0;
+  int8_t* d_x = nullptr;          // [m][ldn] SNP-major dosages, animals in universe order
+  int* d_colsum_all = nullptr;    // [m]
+  std::vector<double> y_univ;     // phenotypes in universe order
+  std::vector<int> pos_of;        // original animal index -> universe position
+  TbRowSet slots[TB_MAX_SLOTS];
+  cudaStream_t stream = nullptr;
+
+  // staged genomes
+  int* d_idx = nullptr;           // flat marker lists
+  size_t idx_cap = 0;
+  std::vector<long long> h_off;   // [P+1]
+  int P = 0;
+
+  // wave workspace (grown on demand, reused)
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  size_t ws_limit = 0;            // user cap (0 = auto)
+  int last_wave = 0;              // matrices per wave used by the last eval (diagnostics)
+
+  // debug capture of the last wave's first individual
+  int debug_keep = 0;
+
+  std::vector<cudaEvent_t> ev_pool;     // events for profile mode
+  size_t ev_used = 0;
+  struct Span { int stage; size_t b, e; };
+  std::vector<Span> spans;
+  int profile = 0;                // 1: bracket every stage with events (serialises nothing: one stream)
+  int stop_after = -1;            // debug: stop the pipeline after this stage
+  int max_wave = 0;
+  int n_sm = 148;
+  // layout of the last wave (for tb_debug_fetch)
+  struct DbgLayout {
+    int W = 0, n_slots = 0, rpad = 0, kstride = 0;
+    int32_t* C = nullptr; long long* s = nullptr; long long* SQ = nullptr;
+    std::vector<double*> M, alpha, pred;
+    std::vector<int> ntp, n_v;
+  } dbg;
+  double stage_ms[TB_ST_COUNT] = {};
+  unsigned long long stage_launches[TB_ST_COUNT] = {};
+  unsigned long long launches = 0;
+  std::string err;
+};
+
+#define TB_CUDA(ctx, call)                                                                             \
+  do {                                                                                                 \
+    cudaError_t e__ = (call);                                                                          \
+    if (e__ != cudaSuccess) {                                                                          \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__) + " @" + __FILE__ + ":" +       \
+                   std::to_string(__LINE__);                                                           \
+      return -2;                                                                                       \
+    }                                                                                                  \
+  } while (0)
+
+__host__ __device__ static inline int tb_round_up(int x, int q) { return (x + q - 1) / q * q; }
+
+// ---- launchers (each defined in its own .cu); all asynchronous on `st`, return cudaGetLastError() ----
+
+// ingest.cu
+cudaError_t tb_launch_transpose_rows(const int8_t* d_rows, int n_rows, int m, int8_t* d_x, int ldn, int pos0,
+                                     cudaStream_t st);
+cudaError_t tb_launch_colsum(const int8_t* d_x, int ldn, int m, const int* d_pos, int n_pos, int* d_colsum,
+                             cudaStream_t st);
+
+// gather.cu
+cudaError_t tb_launch_gather(const int8_t* d_x, int ldn, const int* d_idx, const long long* d_off, int w0, int W,
+                             int rpad, int kstride, int8_t* d_panel, cudaStream_t st);
+cudaError_t tb_launch_centre_terms(const int8_t* d_panel, int rpad, int kstride, const int* d_idx,
+                                   const long long* d_off, int w0, int W, int n_slots,
+                                   const int* const* d_colsum_of, /* [W*n_slots] device ptrs */
+                                   long long* d_s, long long* d_SQ, cudaStream_t st);
+
+// gram_tc.cu / gram_simt.cu
+cudaError_t tb_gram_tc_init();
+cudaError_t tb_launch_gram_tc(const int8_t* d_panel, int W, int rpad, int kstride, const int* d_kblocks,
+                              const int* d_tiles, int n_tiles, int32_t* d_C, int n_sm, cudaStream_t st,
+                              std::string* err);
+cudaError_t tb_launch_gram_simt(const int8_t* d_panel, int W, int rpad, int kstride, const int* d_kblocks,
+                                int32_t* d_C, cudaStream_t st);
+
+// scale.cu
+struct TbScaleJob {       // one (individual, rowset) matrix
+  const int32_t* C;       // [rpad][rpad] lower triangle valid
+  const long long* s;     // [rpad]
+  const long long* SQ;    // {S, Q}
+  const int* tpos;
+  const int* vpos;
+  double* M;              // [ntp + n_v][ntp]: A on top (lower triangle + ridge), G_vt below
+  long long N;            // animals behind the allele frequencies
+  int n_t, n_v, ntp, rpad;
+  double lambda;
+};
+cudaError_t tb_launch_scale(const TbScaleJob* d_jobs, int n_jobs, int max_rows, int max_ntp, cudaStream_t st);
+
+// chol.cu
+struct TbCholJob {
+  double* M;        // [ntp + n_v][ntp]
+  double* Linv;     // [ntp / TB_NB][TB_NB][TB_NB] inverses of the diagonal blocks
+  int ntp;
+  int* status;      // set to 1 if a pivot was not positive
+};
+cudaError_t tb_chol_init();
+cudaError_t tb_launch_chol_update(const TbCholJob* d_jobs, int n_jobs, int max_ntp, int j, cudaStream_t st);
+cudaError_t tb_launch_chol_diag(const TbCholJob* d_jobs, int n_jobs, int max_ntp, int j, cudaStream_t st);
+cudaError_t tb_launch_chol_panel(const TbCholJob* d_jobs, int n_jobs, int max_ntp, int j, cudaStream_t st);
+
+// solve.cu
+struct TbSolveJob {
+  const double* M;
+  const double* Linv;
+  const double* y_t;   // [ntp]
+  const double* y_v;   // [n_v]
+  const int* status;
+  double* alpha;       // [ntp] scratch / debug
+  double* pred;        // [n_v] scratch / debug
+  double* fitness;     // one value
+  int n_t, n_v, ntp;
+};
+cudaError_t tb_solve_init();
+cudaError_t tb_launch_solve(const TbSolveJob* d_jobs, int n_jobs, int max_ntp, cudaStream_t st);

@@ -1,0 +1,196 @@
+"""Host-side handle on one GPU context of libtblup_b200.so.
+
+``GblupEngine`` owns a data set resident on one B200 (genotypes as int8 dosages, SNP-major; phenotypes;
+row sets) and evaluates batches of genomes (marker-index lists) on it.  It is the object the evaluator
+classes in ``tblup_b200.evaluator`` hold in place of the reference's worker pool
+(tblup/evaluator.py:116-131): where the reference pickles one job per individual into an ``mp.Queue``
+(evaluator.py:227-241) this class ships the whole generation in one call.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+MODE_AUTO, MODE_GBLUP, MODE_SNPBLUP = 0, 1, 2
+STAGES = ["h2d", "gather", "centre", "gram", "scale", "chol_update", "chol_panel", "solve", "d2h"]
+DBG_C, DBG_S, DBG_SQ, DBG_M, DBG_ALPHA, DBG_PRED, DBG_DIMS = range(7)
+
+
+def as_dosage_int8(geno):
+    """Validate a genotype matrix (any real dtype) holds dosages {0,1,2} and return it as C-contiguous int8.
+
+    The reference keeps ``data`` as the float64 ``.npy`` it loaded (tblup/evaluator.py:215); the dosages are
+    small integers, so int8 is lossless and an eighth of the bytes."""
+    g = np.asarray(geno)
+    if g.ndim != 2:
+        raise ValueError("genotype matrix must be 2-D (animals x markers), got shape %r" % (g.shape,))
+    if g.dtype != np.int8:
+        gi = g.astype(np.int8)
+        if not np.array_equal(gi, g):
+            raise ValueError("genotype matrix must hold integer dosages 0/1/2")
+        g = gi
+    if g.size and (g.min() < 0 or g.max() > 2):
+        raise ValueError("genotype matrix must hold dosages in {0, 1, 2}")
+    return np.ascontiguousarray(g)
+
+
+def pack_genomes(genomes, n_markers):
+    """Ragged list of index arrays -> (flat int32, offsets int64) with numpy fancy-indexing semantics
+    (tblup/evaluator.py:275, :298): negative indices wrap, out-of-range raises IndexError, duplicates stay."""
+    lens = np.fromiter((len(g) for g in genomes), dtype=np.int64, count=len(genomes))
+    off = np.zeros(len(genomes) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    flat = np.empty(int(off[-1]), dtype=np.int64)
+    for i, g in enumerate(genomes):
+        a = np.asarray(g)
+        if a.dtype.kind not in "iu":
+            ai = a.astype(np.int64)
+            if not np.array_equal(ai, a):
+                raise IndexError("arrays used as indices must be of integer type")
+            a = ai
+        flat[off[i]:off[i + 1]] = a
+    if flat.size:
+        if flat.max() >= n_markers or flat.min() < -n_markers:
+            bad = flat[(flat >= n_markers) | (flat < -n_markers)][0]
+            raise IndexError("index %d is out of bounds for axis 1 with size %d" % (bad, n_markers))
+        flat = np.where(flat < 0, flat + n_markers, flat)
+    return np.ascontiguousarray(flat.astype(np.int32)), off
+
+
+class GblupEngine:
+    """One data set on one GPU.  Not thread-safe (one host thread per context, like the C-ABI)."""
+
+    def __init__(self, geno, pheno, perm=None, device=0):
+        self._lib = _lib.load()
+        self._ctx = C.c_void_p()
+        g = as_dosage_int8(geno)
+        y = np.ascontiguousarray(np.asarray(pheno, dtype=np.float64).ravel())
+        if y.shape[0] != g.shape[0]:
+            raise ValueError("phenotype vector has %d entries for %d animals" % (y.shape[0], g.shape[0]))
+        self.n, self.m = g.shape
+        p = None
+        if perm is not None:
+            p = np.ascontiguousarray(np.asarray(perm, dtype=np.int32))
+            if p.shape != (self.n,):
+                raise ValueError("perm must list every animal exactly once")
+        rc = self._lib.tb_create(g.ctypes.data, self.n, self.m, y.ctypes.data,
+                                 p.ctypes.data if p is not None else None, int(device), C.byref(self._ctx))
+        if rc != 0:
+            self._ctx = C.c_void_p()
+            raise RuntimeError("tb_create failed (%d): %s" % (rc, self._lib.tb_last_error(None).decode()))
+        self.device = int(device)
+        self._n_staged = 0
+
+    # -- lifetime ------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx:
+            self._lib.tb_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError("%s failed (%d): %s" % (what, rc, self._lib.tb_last_error(self._ctx).decode()))
+
+    # -- configuration -------------------------------------------------------------------------
+    def set_rowset(self, slot, train, valid):
+        t = np.ascontiguousarray(np.asarray(train, dtype=np.int32))
+        v = np.ascontiguousarray(np.asarray(valid, dtype=np.int32))
+        self._check(self._lib.tb_set_rowset(self._ctx, int(slot), t.ctypes.data, t.size, v.ctypes.data, v.size),
+                    "tb_set_rowset")
+
+    def set_option(self, name, value):
+        self._check(self._lib.tb_set_option(self._ctx, name.encode(), int(value)), "tb_set_option")
+
+    # -- evaluation ----------------------------------------------------------------------------
+    def stage(self, genomes=None, flat=None, off=None):
+        """Copy a batch to the device.  Pass ``genomes`` (list of index arrays) or pre-packed flat/off."""
+        if genomes is not None:
+            flat, off = pack_genomes(genomes, self.m)
+        flat = np.ascontiguousarray(flat, dtype=np.int32)
+        off = np.ascontiguousarray(off, dtype=np.int64)
+        self._check(self._lib.tb_stage_genomes(self._ctx, flat.ctypes.data, off.ctypes.data, off.size - 1),
+                    "tb_stage_genomes")
+        self._n_staged = off.size - 1
+
+    def evaluate_staged(self, slots=(0,), h2=0.4, mode=MODE_AUTO, out=None, out_device_ptr=None):
+        """Fitness of the staged batch on each row set -> array (P, n_slots), or written to a device pointer."""
+        s = np.ascontiguousarray(np.asarray(slots, dtype=np.int32))
+        if out_device_ptr is not None:
+            self._check(self._lib.tb_eval_staged(self._ctx, s.ctypes.data, s.size, float(h2), int(mode),
+                                                 C.c_void_p(int(out_device_ptr)), 1), "tb_eval_staged")
+            return None
+        if out is None:
+            out = np.empty((self._n_staged, s.size), dtype=np.float64)
+        self._check(self._lib.tb_eval_staged(self._ctx, s.ctypes.data, s.size, float(h2), int(mode),
+                                             out.ctypes.data, 0), "tb_eval_staged")
+        return out
+
+    def evaluate(self, genomes, slots=(0,), h2=0.4, mode=MODE_AUTO):
+        """One generation: host index lists in, host fitness out (P, n_slots)."""
+        flat, off = pack_genomes(genomes, self.m)
+        return self.evaluate_packed(flat, off, slots, h2, mode)
+
+    def evaluate_packed(self, flat, off, slots=(0,), h2=0.4, mode=MODE_AUTO, out=None):
+        s = np.ascontiguousarray(np.asarray(slots, dtype=np.int32))
+        P = off.size - 1
+        if out is None:
+            out = np.empty((P, s.size), dtype=np.float64)
+        self._check(self._lib.tb_eval(self._ctx, s.ctypes.data, s.size, flat.ctypes.data, off.ctypes.data, P,
+                                      float(h2), int(mode), out.ctypes.data), "tb_eval")
+        self._n_staged = P
+        return out
+
+    # -- diagnostics ---------------------------------------------------------------------------
+    def gram_debug(self, indices, rows, impl="tc"):
+        flat, _ = pack_genomes([indices], self.m)
+        out = np.empty((rows, rows), dtype=np.int32)
+        self._check(self._lib.tb_gram_debug(self._ctx, flat.ctypes.data, flat.size, int(rows),
+                                            0 if impl == "tc" else 1, out.ctypes.data), "tb_gram_debug")
+        return out
+
+    def debug_dims(self, job=0):
+        d = np.zeros(4, dtype=np.int32)
+        self._check(self._lib.tb_debug_fetch(self._ctx, DBG_DIMS, job, d.ctypes.data, d.nbytes), "tb_debug_fetch")
+        return dict(rpad=int(d[0]), ntp=int(d[1]), n_v=int(d[2]), kstride=int(d[3]))
+
+    def debug_fetch(self, what, job=0):
+        d = self.debug_dims(job)
+        shape, dt = {
+            DBG_C: ((d["rpad"], d["rpad"]), np.int32),
+            DBG_S: ((d["rpad"],), np.int64),
+            DBG_SQ: ((2,), np.int64),
+            DBG_M: ((d["ntp"] + d["n_v"], d["ntp"]), np.float64),
+            DBG_ALPHA: ((d["ntp"],), np.float64),
+            DBG_PRED: ((d["n_v"],), np.float64),
+        }[what]
+        out = np.empty(shape, dtype=dt)
+        self._check(self._lib.tb_debug_fetch(self._ctx, what, job, out.ctypes.data, out.nbytes), "tb_debug_fetch")
+        return out
+
+    def stage_times(self):
+        ms = np.zeros(len(STAGES), dtype=np.float64)
+        ln = np.zeros(len(STAGES), dtype=np.uint64)
+        self._check(self._lib.tb_stage_times(self._ctx, ms.ctypes.data, ln.ctypes.data), "tb_stage_times")
+        return {s: (float(ms[i]), int(ln[i])) for i, s in enumerate(STAGES)}
+
+    def launch_count(self):
+        return int(self._lib.tb_launch_count(self._ctx))
+
+    def reset_counters(self):
+        self._check(self._lib.tb_reset_counters(self._ctx), "tb_reset_counters")
+
+    def last_wave(self):
+        return int(self._lib.tb_last_wave(self._ctx))

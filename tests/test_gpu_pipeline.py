@@ -1,0 +1,231 @@
+"""GPU parity tests, stage by stage and end to end, through the C-ABI (tblup_b200.engine -> ctypes).
+
+Bars (BASELINE.json north_star): uncentred Gram entries and the integer centring terms bit-exact against the
+oracle; fitness within 1e-6 absolute of the reference values stored in tests/golden/*.npz.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden, unpack
+from oracle import gblup_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+FIT_TOL = 1e-6   # north_star: "per-individual fitness agrees with the reference numpy path within 1e-6 absolute"
+
+
+def _engine(x, y, train, valid, test=None, extra_sets=()):
+    from tblup_b200 import GblupEngine
+    rest = [] if test is None else list(test)
+    perm = np.concatenate([np.asarray(train), np.asarray(valid), np.asarray(rest, dtype=np.int64)]).astype(np.int64)
+    if perm.size != x.shape[0]:
+        missing = np.setdiff1d(np.arange(x.shape[0]), perm)
+        perm = np.concatenate([perm, missing])
+    eng = GblupEngine(x, y, perm=perm)
+    eng.set_rowset(0, train, valid)
+    for slot, (t, v) in enumerate(extra_sets, start=1):
+        eng.set_rowset(slot, t, v)
+    return eng, perm
+
+
+@pytest.fixture(scope="module")
+def mid():
+    g = load_golden("fit_mid")
+    eng, perm = _engine(g["x"], g["y"], g["train"], g["valid"], g["test"])
+    yield g, eng, perm
+    eng.close()
+
+
+@pytest.mark.parametrize("impl", ["simt", "tc"])
+@pytest.mark.parametrize("k", [1, 31, 128, 700, 1500, -900])
+def test_gram_bit_exact(mid, impl, k):
+    g, eng, perm = mid
+    rng = np.random.default_rng(abs(k) + 7)
+    m = g["x"].shape[1]
+    idx = rng.integers(0, m, size=-k) if k < 0 else rng.choice(m, size=k, replace=False)
+    rows = 400
+    got = eng.gram_debug(idx, rows, impl=impl)
+    want = np.tril(O.exact_gram(g["x"], idx, perm[:rows]))
+    assert got.dtype == np.int32
+    assert np.array_equal(got.astype(np.int64), want)
+
+
+def test_gram_partial_rows(mid):
+    """Row counts that are not tile multiples, including a single 128-row tile and an odd count."""
+    g, eng, perm = mid
+    idx = np.arange(0, 1500, 3)
+    for rows in (1, 127, 129, 257, 385):
+        got = eng.gram_debug(idx, rows, impl="tc")
+        assert np.array_equal(got.astype(np.int64), np.tril(O.exact_gram(g["x"], idx, perm[:rows])))
+
+
+@pytest.mark.parametrize("mode", [O.MODE_GBLUP, O.MODE_SNPBLUP])
+def test_stage_by_stage_against_oracle(mid, mode):
+    from tblup_b200 import engine as E
+    g, eng, perm = mid
+    x, y, h2 = g["x"], g["y"], float(g["h2"])
+    tr, va = g["train"], g["valid"]
+    genomes = [gen for gen in unpack(g["genomes_flat"], g["genomes_off"])]
+    job = 3
+    fit_ref, d = O.exact_fitness(genomes[job], tr, va, x, y, h2, mode, detail=True)
+    nt, nv = len(tr), len(va)
+    api_mode = E.MODE_GBLUP if mode == O.MODE_GBLUP else E.MODE_SNPBLUP
+
+    eng.set_option("stop_after", 4)          # after the scale stage: M = [A ; G_vt] before factorisation
+    eng.evaluate(genomes, slots=[0], h2=h2, mode=api_mode)
+    dims = eng.debug_dims(job)
+    C = eng.debug_fetch(E.DBG_C, job)
+    assert np.array_equal(np.tril(C[:nt + nv, :nt + nv]).astype(np.int64)[:, :nt], np.tril(d["C"])[:, :nt])
+    s = eng.debug_fetch(E.DBG_S, job)
+    assert np.array_equal(s[:nt + nv], d["s"])
+    SQ = eng.debug_fetch(E.DBG_SQ, job)
+    assert int(SQ[0]) == d["S"] and int(SQ[1]) == d["Q"]
+    M = eng.debug_fetch(E.DBG_M, job)
+    ntp = dims["ntp"]
+    assert np.array_equal(np.tril(M[:nt, :nt]), np.tril(d["A"]))          # same integer numerators, one division
+    g_vt = O.exact_grm_block(d["C"][nt:, :nt], d["s"][nt:], d["s"][:nt], d["S"], d["Q"], d["N"])
+    assert np.array_equal(M[ntp:ntp + nv, :nt], g_vt)
+    if ntp > nt:
+        assert np.array_equal(np.tril(M[nt:ntp, :ntp]), np.tril(np.eye(ntp)[nt:ntp]))
+
+    eng.set_option("stop_after", -1)
+    fit = eng.evaluate(genomes, slots=[0], h2=h2, mode=api_mode)[:, 0]
+    L = np.tril(eng.debug_fetch(E.DBG_M, job)[:nt, :nt])
+    assert np.allclose(L @ L.T, d["A"], rtol=0, atol=1e-10 * np.abs(d["A"]).max())
+    alpha = eng.debug_fetch(E.DBG_ALPHA, job)[:nt]
+    assert np.allclose(alpha, d["alpha"], rtol=1e-9, atol=1e-12)
+    pred = eng.debug_fetch(E.DBG_PRED, job)
+    assert np.allclose(pred, d["pred"], rtol=1e-9, atol=1e-12)
+    assert abs(fit[job] - fit_ref) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["fit_small", "fit_offset", "fit_mid"])
+def test_fitness_matches_reference(name):
+    """Every branch of blup() on the reference's own numbers: forced gblup, forced snp_blup, the k > n
+    dispatch, the testing split (train+valid -> test) and each cross-validation fold."""
+    from tblup_b200 import engine as E
+    g = load_golden(name)
+    x, y, h2 = g["x"], g["y"], float(g["h2"])
+    tr, va, te = g["train"], g["valid"], g["test"]
+    f_tr = unpack(g["fold_train_flat"], g["fold_train_off"])
+    f_va = unpack(g["fold_valid_flat"], g["fold_valid_off"])
+    sets = [(np.concatenate((tr, va)), te)] + list(zip(f_tr, f_va))
+    eng, _ = _engine(x, y, tr, va, te, extra_sets=sets)
+    try:
+        genomes = unpack(g["genomes_flat"], g["genomes_off"])
+        got_g = eng.evaluate(genomes, slots=[0], h2=h2, mode=E.MODE_GBLUP)[:, 0]
+        got_s = eng.evaluate(genomes, slots=[0], h2=h2, mode=E.MODE_SNPBLUP)[:, 0]
+        got_all = eng.evaluate(genomes, slots=list(range(len(sets) + 1)), h2=h2, mode=E.MODE_AUTO)
+        assert np.abs(got_g - g["ref_gblup"]).max() < FIT_TOL
+        assert np.abs(got_s - g["ref_snp_blup"]).max() < FIT_TOL
+        assert np.abs(got_all[:, 0] - g["ref_blup"]).max() < FIT_TOL
+        assert np.abs(got_all[:, 1] - g["ref_blup_testing"]).max() < FIT_TOL
+        assert np.abs(got_all[:, 2:] - g["ref_blup_folds"]).max() < FIT_TOL
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("name", ["traj_gblup", "traj_snpblup", "traj_intercv", "traj_intracv"])
+def test_trajectory_replay(name):
+    """Fixed-seed DE runs of the reference (its own Population/evolver/selector): every batch it evaluated
+    gets the same fitness (1e-6) and therefore the same parent-vs-child decisions and selected panel."""
+    from tblup_b200 import engine as E
+    g = load_golden(name)
+    x, y, h2 = g["x"], g["y"], float(g["h2"])
+    regressor = str(g["regressor"])
+    tr, va, te = g["train"], g["valid"], g["test"]
+    sets = []
+    if "fold_train_flat" in g:
+        sets = list(zip(unpack(g["fold_train_flat"], g["fold_train_off"]),
+                        unpack(g["fold_valid_flat"], g["fold_valid_off"])))
+    eng, _ = _engine(x, y, tr, va, te, extra_sets=sets)
+    try:
+        genomes = unpack(g["genomes_flat"], g["genomes_off"])
+        pos = 0
+        fpos = 0
+        pop = int(g["pop"])
+        current = np.full(pop, -np.inf)
+        for b, size in enumerate(g["batch_sizes"]):
+            batch = genomes[pos:pos + size]
+            pos += size
+            if regressor == "intracv_blup":
+                got = eng.evaluate(batch, slots=list(range(1, len(sets) + 1)), h2=h2, mode=E.MODE_AUTO).mean(axis=1)
+            elif regressor == "intercv_blup":
+                got = eng.evaluate(batch, slots=[1 + int(g["split_of_batch"][b])], h2=h2, mode=E.MODE_AUTO)[:, 0]
+            else:
+                got = eng.evaluate(batch, slots=[0], h2=h2, mode=E.MODE_AUTO)[:, 0]
+            ref = g["fitness"][fpos:fpos + size]
+            where = g["positions"][fpos:fpos + size]
+            fpos += size
+            assert np.abs(got - ref).max() < FIT_TOL
+            # the selector's decision (tblup/selector.py:28: child replaces parent iff strictly fitter)
+            decide_ref = ref > current[where]
+            decide_got = got > current[where]
+            ties = np.abs(ref - current[where]) < FIT_TOL
+            assert np.array_equal(decide_ref[~ties], decide_got[~ties])
+            current[where] = np.where(decide_ref, ref, current[where])
+            if b < len(g["pop_fitness"]):          # the replayed selection is the reference's own population
+                assert np.allclose(current, g["pop_fitness"][b], rtol=0, atol=1e-12)
+    finally:
+        eng.close()
+
+
+def test_config1_shape_against_oracle():
+    """BASELINE config 1 shape (1000 animals x 10000 markers): random k-subsets on both sides of k = n."""
+    from tblup_b200 import engine as E
+    import random
+    x, y = O.synth_genotypes(1000, 10000, h2=0.4, seed=0)
+    random.seed(0)
+    np.random.seed(0)
+    tr, va, te = O.ref_splits(1000)
+    eng, _ = _engine(x, y, tr, va, te)
+    try:
+        rng = np.random.default_rng(1)
+        genomes = [rng.choice(10000, size=k, replace=False) for k in (100, 999, 1000, 1001, 1500, 1500, 2500, 4000)]
+        got = eng.evaluate(genomes, slots=[0], h2=0.4, mode=E.MODE_AUTO)[:, 0]
+        want = np.array([O.exact_blup(gm, tr, va, x, y, 0.4) for gm in genomes])
+        assert np.abs(got - want).max() < 1e-9
+        xf = x.astype(np.float64)
+        for i in (0, 4):
+            assert abs(got[i] - O.ref_blup(genomes[i].astype(int), tr, va, xf, y, 0.4)) < FIT_TOL
+    finally:
+        eng.close()
+
+
+def test_waves_and_ragged_batches():
+    """The wave scheduler must not change results: same batch with 1, 3 and all individuals per wave."""
+    from tblup_b200 import engine as E
+    g = load_golden("fit_small")
+    eng, _ = _engine(g["x"], g["y"], g["train"], g["valid"], g["test"])
+    try:
+        genomes = unpack(g["genomes_flat"], g["genomes_off"])
+        base = eng.evaluate(genomes, slots=[0], h2=float(g["h2"]), mode=E.MODE_AUTO)
+        for mw in (1, 3, 5):
+            eng.set_option("max_wave", mw)
+            again = eng.evaluate(genomes, slots=[0], h2=float(g["h2"]), mode=E.MODE_AUTO)
+            assert eng.last_wave() == mw
+            assert np.array_equal(base, again)
+    finally:
+        eng.close()
+
+
+def test_error_paths():
+    from tblup_b200 import GblupEngine
+    g = load_golden("fit_small")
+    x = g["x"].copy()
+    with pytest.raises(ValueError):
+        GblupEngine(np.where(x == 2, 3, x), g["y"])
+    eng, _ = _engine(g["x"], g["y"], g["train"], g["valid"], g["test"])
+    try:
+        with pytest.raises(IndexError):
+            eng.evaluate([np.array([0, x.shape[1]])])
+        with pytest.raises(RuntimeError):
+            eng.evaluate([np.array([1, 2, 3])], slots=[5])          # undefined row set
+        with pytest.raises(RuntimeError):
+            eng.evaluate([np.array([], dtype=np.int64)])
+        # negative indices wrap like numpy fancy indexing
+        a = eng.evaluate([np.array([-1, 5, 9])])[0, 0]
+        b = eng.evaluate([np.array([x.shape[1] - 1, 5, 9])])[0, 0]
+        assert a == b
+    finally:
+        eng.close()

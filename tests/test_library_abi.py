@@ -1,0 +1,77 @@
+"""CPU-side checks of the C-ABI boundary: the shared library loads and exports every symbol the header
+declares (no compute calls -- there is no GPU in the build container), and the loader fails loudly."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "tblup_b200.h")
+
+
+def header_symbols():
+    text = open(HEADER).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(tb_[a-z_0-9]+)\s*\(", text)))
+
+
+@pytest.fixture(scope="module")
+def built():
+    import __graft_entry__ as ge
+    ge.build()
+    from tblup_b200 import _lib
+    return _lib
+
+
+def test_header_and_loader_agree(built):
+    assert header_symbols() == sorted(built.SYMBOLS)
+
+
+def test_library_exports_every_symbol(built):
+    lib = ctypes.CDLL(built.LIB_PATH)
+    for name in header_symbols():
+        assert hasattr(lib, name), name
+    assert built.load().tb_abi_version() == 1
+
+
+def test_header_cites_reference_for_each_entry_point():
+    text = open(HEADER).read()
+    assert text.count("evaluator.py") >= 6 and "tblup/utils.py" in text
+
+
+def test_no_cpu_fallback_without_device(built):
+    """Creating a context with no GPU must raise with a clear message, never silently compute on the CPU."""
+    import numpy as np
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from tblup_b200 import GblupEngine
+    x = np.zeros((8, 8), dtype=np.int8)
+    with pytest.raises(RuntimeError, match="no CUDA device|no CPU fallback|CUDA"):
+        GblupEngine(x, np.zeros(8))
+
+
+def test_product_package_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "tblup_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_genome_packing_semantics():
+    import numpy as np
+    from tblup_b200.engine import pack_genomes, as_dosage_int8
+    flat, off = pack_genomes([np.array([3, -1, 3]), [0], np.array([], dtype=int)], 10)
+    assert flat.tolist() == [3, 9, 3, 0] and off.tolist() == [0, 3, 4, 4]
+    with pytest.raises(IndexError):
+        pack_genomes([[10]], 10)
+    with pytest.raises(IndexError):
+        pack_genomes([[-11]], 10)
+    with pytest.raises(ValueError):
+        as_dosage_int8(np.array([[0.5, 1.0]]))
+    with pytest.raises(ValueError):
+        as_dosage_int8(np.array([[0, 3]]))
+    assert as_dosage_int8(np.array([[0.0, 2.0]])).dtype == np.int8
