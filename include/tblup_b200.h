@@ -95,6 +95,13 @@ uint64_t tb_launch_count(const tb_ctx* ctx);
 int tb_reset_counters(tb_ctx* ctx);
 int tb_last_wave(const tb_ctx* ctx);
 
+/* Run the context's work on a caller-owned CUDA stream (e.g. torch's current stream, so the caller's CUDA
+ * events bracket it); NULL restores the context's own stream. */
+int tb_set_stream(tb_ctx* ctx, void* cuda_stream);
+
+/* Peak probes for roofline denominators: which = 0 -> fp64 DMMA (mma.sync m8n8k4) TFLOP/s on this device. */
+int tb_microbench(tb_ctx* ctx, int which, double* out);
+
 #ifdef __cplusplus
 }
 #endif

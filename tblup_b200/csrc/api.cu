@@ -384,7 +384,8 @@ int tb_create(const int8_t* geno, int n, int m, const double* y, const int32_t* 
     c->err = std::string(what) + ": " + cudaGetErrorString(ce);
     return true;
   };
-  if (chk(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking), "cudaStreamCreate")) return bail("");
+  if (chk(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return bail("");
+  c->stream = c->own_stream;
   if (chk(cudaMalloc(&c->d_x, (size_t)m * c->ldn), "cudaMalloc genotypes")) return bail("");
   if (chk(cudaMemsetAsync(c->d_x, 0, (size_t)m * c->ldn, c->stream), "memset")) return bail("");
   if (chk(cudaMalloc(&c->d_colsum_all, (size_t)m * sizeof(int)), "cudaMalloc colsum")) return bail("");
@@ -453,7 +454,7 @@ int tb_destroy(tb_ctx* c) {
   cudaFree(c->d_colsum_all);
   cudaFree(c->d_idx);
   cudaFree(c->ws);
-  if (c->stream) cudaStreamDestroy(c->stream);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
   return 0;
 }
@@ -695,5 +696,24 @@ int tb_reset_counters(tb_ctx* c) {
 }
 
 int tb_last_wave(const tb_ctx* c) { return c ? c->last_wave : 0; }
+
+int tb_set_stream(tb_ctx* c, void* cuda_stream) {
+  if (!c) return -1;
+  TB_CUDA(c, cudaSetDevice(c->device));
+  TB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+  return 0;
+}
+
+int tb_microbench(tb_ctx* c, int which, double* out) {
+  if (!c || !out) return -1;
+  TB_CUDA(c, cudaSetDevice(c->device));
+  if (which == 0) {
+    TB_CUDA(c, tb_microbench_dmma(c->n_sm, c->stream, out));
+    c->launches += 4;
+    return 0;
+  }
+  return fail(c, "tb_microbench: unknown probe");
+}
 
 }  // extern "C"

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #define TB_MAX_SLOTS 64
 #define TB_NB 64          // Cholesky block size (rows/cols per block column)
@@ -51,6 +52,7 @@ struct TbCtx {
   std::vector<int> pos_of;        // original animal index -> universe position
   TbRowSet slots[TB_MAX_SLOTS];
   cudaStream_t stream = nullptr;
+  cudaStream_t own_stream = nullptr;
 
   // staged genomes
   int* d_idx = nullptr;           // flat marker lists
@@ -164,3 +166,6 @@ struct TbSolveJob {
 };
 cudaError_t tb_solve_init();
 cudaError_t tb_launch_solve(const TbSolveJob* d_jobs, int n_jobs, int max_ntp, cudaStream_t st);
+
+// microbench.cu
+cudaError_t tb_microbench_dmma(int n_sm, cudaStream_t st, double* tflops);

@@ -192,5 +192,14 @@ class GblupEngine:
     def reset_counters(self):
         self._check(self._lib.tb_reset_counters(self._ctx), "tb_reset_counters")
 
+    def set_stream(self, cuda_stream_handle):
+        """Run on a caller-owned stream (pass ``torch.cuda.current_stream().cuda_stream``); None restores."""
+        self._check(self._lib.tb_set_stream(self._ctx, C.c_void_p(int(cuda_stream_handle or 0))), "tb_set_stream")
+
+    def microbench(self, which=0):
+        out = C.c_double(0.0)
+        self._check(self._lib.tb_microbench(self._ctx, int(which), C.byref(out)), "tb_microbench")
+        return float(out.value)
+
     def last_wave(self):
         return int(self._lib.tb_last_wave(self._ctx))
