@@ -136,7 +136,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
   }
   const int kstride_max = tb_round_up(kmax, TB_GRAM_BK);
   per_ind += (size_t)rpad * kstride_max + (size_t)rpad * rpad * sizeof(int32_t) +
-             (size_t)n_slots * (rpad + 2) * sizeof(long long) + 4096;
+             (size_t)n_slots * (rpad + 2) * sizeof(long long) + (size_t)n_slots * kstride_max * sizeof(int) + 4096;
 
   size_t free_b = 0, total_b = 0;
   TB_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
@@ -188,6 +188,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     int32_t* d_C = ar.take<int32_t>((size_t)Wc * rpad * rpad);
     long long* d_s = ar.take<long long>((size_t)n_jobs * rpad);
     long long* d_SQ = ar.take<long long>((size_t)n_jobs * 2);
+    int* d_csg = ar.take<int>((size_t)n_jobs * kstride);
     int* d_status = ar.take<int>(n_jobs);
     int* d_kb = ar.take<int>(Wc);
     const int** d_cs = ar.take<const int*>(n_jobs);
@@ -277,7 +278,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     if (c->stop_after == TB_ST_GATHER) continue;
 
     sp = span_begin(c, TB_ST_CENTRE);
-    TB_CUDA(c, tb_launch_centre_terms(d_panel, rpad, kstride, c->d_idx, d_off, w0, Wc, n_slots, d_cs, d_s, d_SQ, st));
+    TB_CUDA(c, tb_launch_centre_terms(d_panel, rpad, kstride, c->d_idx, d_off, w0, Wc, n_slots, d_kb, d_cs, d_csg, d_s, d_SQ, st));
     span_end(c, sp);
     count(c, TB_ST_CENTRE, 2);
     if (c->stop_after == TB_ST_CENTRE) continue;

@@ -130,63 +130,79 @@ __global__ void __launch_bounds__(256, 2) chol_gemm_kernel(const TbCholJob* __re
   }
 }
 
-// One CTA per matrix: factor the 64 x 64 diagonal block in shared memory and invert the factor.
+// One CTA per matrix: factor the 64 x 64 diagonal block and invert the factor.
+// potrf: thread (r = tid / 4, q = tid % 4) keeps row r, columns q, q+4, ... in registers; per column one
+// barrier: the owners publish the raw column through a double-buffered smem vector, every thread rescales it
+// by 1/sqrt(pivot) itself and applies the rank-1 update to its registers.
+// inverse: forward substitution row by row, the dot products of a row split over 4 thread groups.
 __global__ void __launch_bounds__(256) chol_diag_kernel(const TbCholJob* __restrict__ jobs, int j) {
   extern __shared__ double dsm[];
   double (*Ls)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dsm);
   double (*Xs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dsm + NB * (NB + 1));
+  __shared__ double colbuf[2][NB];
+  __shared__ double part[4][NB];
   __shared__ int bad;
   const TbCholJob jb = jobs[blockIdx.x];
   const int ntp = jb.ntp;
   if (j * NB >= ntp) return;
   double* D = jb.M + (size_t)j * NB * ntp + j * NB;
   const int tid = threadIdx.x;
+  const int r = tid >> 2, q = tid & 3;
   if (tid == 0) bad = 0;
-  for (int e = tid; e < NB * NB; e += 256) {
-    const int r = e >> 6, c = e & 63;
-    Ls[r][c] = c <= r ? D[(size_t)r * ntp + c] : 0.0;
+  double a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = q + 4 * i;
+    a[i] = c <= r ? D[(size_t)r * ntp + c] : 0.0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < NB; ++c) {
+    const int qc = c & 3, ic = c >> 2;
+    if (q == qc && r >= c) colbuf[c & 1][r] = a[ic];
+    __syncthreads();
+    const double d = colbuf[c & 1][c];
+    if (!(d > 0.0) && tid == 0) bad = 1;
+    const double inv = 1.0 / sqrt(d);
+    if (r >= c) {
+      const double lr = colbuf[c & 1][r] * inv;
+      if (q == qc) a[ic] = lr;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int cc = q + 4 * i;
+        if (cc > c && cc <= r) a[i] -= lr * (colbuf[c & 1][cc] * inv);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = q + 4 * i;
+    Ls[r][c] = c <= r ? a[i] : 0.0;
     Xs[r][c] = 0.0;
   }
   __syncthreads();
-  for (int c = 0; c < NB; ++c) {
-    if (tid == 0) {
-      const double d = Ls[c][c];
-      if (!(d > 0.0)) bad = 1;
-      Ls[c][c] = sqrt(d);
-    }
-    __syncthreads();
-    const double piv = Ls[c][c];
-    if (tid > c && tid < NB) Ls[tid][c] /= piv;
-    __syncthreads();
-    for (int e = tid; e < NB * NB; e += 256) {
-      const int r = e >> 6, cc = e & 63;
-      if (cc > c && cc <= r) Ls[r][cc] -= Ls[r][c] * Ls[cc][c];
-    }
-    __syncthreads();
-  }
-  // Linv column c by forward substitution (thread c), four interleaved partial sums per row.
-  if (tid < NB) {
-    const int c = tid;
-    Xs[c][c] = 1.0 / Ls[c][c];
-    for (int r = c + 1; r < NB; ++r) {
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      int p = c;
-      for (; p + 3 < r; p += 4) {
-        s0 += Ls[r][p] * Xs[p][c];
-        s1 += Ls[r][p + 1] * Xs[p + 1][c];
-        s2 += Ls[r][p + 2] * Xs[p + 2][c];
-        s3 += Ls[r][p + 3] * Xs[p + 3][c];
+  // X = L^-1, row by row: X[rr][c] = (delta - sum_{p<rr} L[rr][p] X[p][c]) / L[rr][rr]
+  {
+    const int c = tid & 63, h = tid >> 6;
+    for (int rr = 0; rr < NB; ++rr) {
+      double sacc = 0.0;
+      if (c <= rr) {
+        for (int p = c + h; p < rr; p += 4) sacc += Ls[rr][p] * Xs[p][c];   // X[p][c] = 0 for p < c
       }
-      for (; p < r; ++p) s0 += Ls[r][p] * Xs[p][c];
-      Xs[r][c] = -((s0 + s1) + (s2 + s3)) / Ls[r][r];
+      part[h][c] = sacc;
+      __syncthreads();
+      if (h == 0 && c <= rr) {
+        const double tot = (part[0][c] + part[1][c]) + (part[2][c] + part[3][c]);
+        Xs[rr][c] = ((c == rr ? 1.0 : 0.0) - tot) / Ls[rr][rr];
+      }
+      __syncthreads();
     }
   }
-  __syncthreads();
   double* Li = jb.Linv + (size_t)j * NB * NB;
   for (int e = tid; e < NB * NB; e += 256) {
-    const int r = e >> 6, c = e & 63;
-    D[(size_t)r * ntp + c] = Ls[r][c];
-    Li[e] = Xs[r][c];
+    const int rr = e >> 6, c = e & 63;
+    D[(size_t)rr * ntp + c] = Ls[rr][c];
+    Li[e] = Xs[rr][c];
   }
   if (tid == 0 && bad) *jb.status = 1;
 }

@@ -61,46 +61,24 @@ __global__ void __launch_bounds__(256) gather_kernel(const int8_t* __restrict__ 
   }
 }
 
-// s[a] = sum_j panel[a][j] * colsum[idx[j]]  (exact, int64).  One warp per animal row.
-__global__ void __launch_bounds__(256) centre_rows_kernel(const int8_t* __restrict__ panel, int rpad, int kstride,
-                                                          const int* __restrict__ idx,
-                                                          const long long* __restrict__ off, int w0, int n_slots,
-                                                          const int* const* __restrict__ colsum_of,
-                                                          long long* __restrict__ s) {
-  const int job = blockIdx.y;  // w * n_slots + slot
-  const int w = job / n_slots;
-  const int a = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (a >= rpad) return;
-  const long long o0 = off[w0 + w];
-  const int k = (int)(off[w0 + w + 1] - o0);
-  const int* cs = colsum_of[job];
-  const int8_t* row = panel + ((size_t)w * rpad + a) * kstride;
-  long long acc = 0;
-  for (int j = lane * 4; j < k; j += 128) {
-    const uint32_t v = *reinterpret_cast<const uint32_t*>(row + j);  // bytes past k are zero padding
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      if (j + b < k) acc += (long long)((v >> (8 * b)) & 0xff) * (long long)cs[idx[o0 + j + b]];
-    }
-  }
-  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) s[(size_t)job * rpad + a] = acc;
-}
-
-// SQ[job] = { sum_j colsum[idx[j]], sum_j colsum[idx[j]]^2 }.
+// csg[job][j] = colsum_job[idx[j]] (zero padded to kstride) and SQ[job] = { sum_j csg, sum_j csg^2 }.
 __global__ void __launch_bounds__(256) centre_sq_kernel(const int* __restrict__ idx, const long long* __restrict__ off,
-                                                        int w0, int n_slots, const int* const* __restrict__ colsum_of,
-                                                        long long* __restrict__ SQ) {
+                                                        int w0, int n_slots, int kstride,
+                                                        const int* const* __restrict__ colsum_of,
+                                                        int* __restrict__ csg, long long* __restrict__ SQ) {
   __shared__ long long sh[2][8];
   const int job = blockIdx.x, w = job / n_slots;
   const long long o0 = off[w0 + w];
   const int k = (int)(off[w0 + w + 1] - o0);
   const int* cs = colsum_of[job];
+  int* out = csg + (size_t)job * kstride;
   long long S = 0, Q = 0;
-  for (int j = threadIdx.x; j < k; j += blockDim.x) {
-    const long long c = cs[idx[o0 + j]];
+  for (int j = threadIdx.x; j < kstride; j += blockDim.x) {
+    int c = 0;
+    if (j < k) c = cs[idx[o0 + j]];
+    out[j] = c;
     S += c;
-    Q += c * c;
+    Q += (long long)c * c;
   }
   for (int o = 16; o; o >>= 1) {
     S += __shfl_xor_sync(0xffffffffu, S, o);
@@ -122,6 +100,33 @@ __global__ void __launch_bounds__(256) centre_sq_kernel(const int* __restrict__ 
   }
 }
 
+// s[a] = sum_j panel[a][j] * csg[j]  (exact, int64).  One warp per animal row; each lane consumes 16 panel
+// bytes + 16 gathered column sums per iteration (panel streamed from HBM, csg stays in L1/L2).
+__global__ void __launch_bounds__(256) centre_rows_kernel(const int8_t* __restrict__ panel, int rpad, int kstride,
+                                                          const int* __restrict__ kblocks, int n_slots,
+                                                          const int* __restrict__ csg, long long* __restrict__ s) {
+  const int job = blockIdx.y;  // w * n_slots + slot
+  const int w = job / n_slots;
+  const int a = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (a >= rpad) return;
+  const int kbytes = kblocks[w] * TB_GRAM_BK;     // panel and csg are zero beyond k
+  const uint4* row = reinterpret_cast<const uint4*>(panel + ((size_t)w * rpad + a) * kstride);
+  const int4* cg = reinterpret_cast<const int4*>(csg + (size_t)job * kstride);
+  long long acc = 0;
+  for (int j = lane; j < kbytes / 16; j += 32) {
+    const uint4 v = row[j];
+    const int4 c0 = cg[4 * j], c1 = cg[4 * j + 1], c2 = cg[4 * j + 2], c3 = cg[4 * j + 3];
+    int t = 0;
+    t += (int)(v.x & 0xff) * c0.x + (int)((v.x >> 8) & 0xff) * c0.y + (int)((v.x >> 16) & 0xff) * c0.z + (int)(v.x >> 24) * c0.w;
+    t += (int)(v.y & 0xff) * c1.x + (int)((v.y >> 8) & 0xff) * c1.y + (int)((v.y >> 16) & 0xff) * c1.z + (int)(v.y >> 24) * c1.w;
+    t += (int)(v.z & 0xff) * c2.x + (int)((v.z >> 8) & 0xff) * c2.y + (int)((v.z >> 16) & 0xff) * c2.z + (int)(v.z >> 24) * c2.w;
+    t += (int)(v.w & 0xff) * c3.x + (int)((v.w >> 8) & 0xff) * c3.y + (int)((v.w >> 16) & 0xff) * c3.z + (int)(v.w >> 24) * c3.w;
+    acc += t;   // 16 products of (dosage <= 2) x (column sum <= 2n < 2^26) fit an int
+  }
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) s[(size_t)job * rpad + a] = acc;
+}
+
 }  // namespace
 
 cudaError_t tb_launch_gather(const int8_t* d_x, int ldn, const int* d_idx, const long long* d_off, int w0, int W,
@@ -132,13 +137,13 @@ cudaError_t tb_launch_gather(const int8_t* d_x, int ldn, const int* d_idx, const
 }
 
 cudaError_t tb_launch_centre_terms(const int8_t* d_panel, int rpad, int kstride, const int* d_idx,
-                                   const long long* d_off, int w0, int W, int n_slots,
-                                   const int* const* d_colsum_of, long long* d_s, long long* d_SQ,
+                                   const long long* d_off, int w0, int W, int n_slots, const int* d_kblocks,
+                                   const int* const* d_colsum_of, int* d_csg, long long* d_s, long long* d_SQ,
                                    cudaStream_t st) {
-  dim3 grid((rpad + 7) / 8, W * n_slots);
-  centre_rows_kernel<<<grid, 256, 0, st>>>(d_panel, rpad, kstride, d_idx, d_off, w0, n_slots, d_colsum_of, d_s);
+  centre_sq_kernel<<<W * n_slots, 256, 0, st>>>(d_idx, d_off, w0, n_slots, kstride, d_colsum_of, d_csg, d_SQ);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  centre_sq_kernel<<<W * n_slots, 256, 0, st>>>(d_idx, d_off, w0, n_slots, d_colsum_of, d_SQ);
+  dim3 grid((rpad + 7) / 8, W * n_slots);
+  centre_rows_kernel<<<grid, 256, 0, st>>>(d_panel, rpad, kstride, d_kblocks, n_slots, d_csg, d_s);
   return cudaGetLastError();
 }

@@ -12,57 +12,82 @@
 
 namespace {
 
+__device__ __forceinline__ double grm_entry(long long cv, long long s_sum, long long N, long long Q, double den) {
+  const long long num = N * N * cv - N * s_sum + Q;
+  return 2.0 * (double)num / den;
+}
+
+// One thread = one row x 4 consecutive columns; a block covers 16 rows x 128 columns (2 rows per thread).
+// Fast path: the four column animals sit at consecutive, 16-byte aligned universe positions strictly below the
+// row animal's position -> one 16-byte load of C; otherwise element-wise with the (max, min) lookup.
 __global__ void __launch_bounds__(256) scale_kernel(const TbScaleJob* __restrict__ jobs) {
   const TbScaleJob jb = jobs[blockIdx.z];
-  const int ntp = jb.ntp, n_t = jb.n_t, n_v = jb.n_v;
-  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int ntp = jb.ntp, n_t = jb.n_t, n_v = jb.n_v, rpad = jb.rpad;
+  const int r0 = blockIdx.y * 16, c0 = blockIdx.x * 128;
   if (r0 >= ntp + n_v || c0 >= ntp) return;
-  if (r0 < ntp && c0 > r0 + 31) return;            // strictly above the diagonal of A
-  const int c = c0 + (threadIdx.x & 31);
+  if (r0 < ntp && c0 > r0 + 15) return;            // strictly above the diagonal of A
+  const int c = c0 + (threadIdx.x & 31) * 4;
+  if (c >= ntp) return;
   const long long N = jb.N, S = jb.SQ[0], Q = jb.SQ[1];
   const double den = (double)(2 * N * S - Q);
-  const bool c_real = c < n_t;
-  int pc = 0;
-  long long sc = 0;
-  if (c_real) {
-    pc = jb.tpos[c];
-    sc = jb.s[pc];
+  int pc[4];
+  long long sc[4];
+  bool creal[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    creal[i] = c + i < n_t;
+    pc[i] = creal[i] ? jb.tpos[c + i] : 0;
+    sc[i] = creal[i] ? jb.s[pc[i]] : 0;
   }
-  for (int rr = threadIdx.x >> 5; rr < 32; rr += 8) {
-    const int r = r0 + rr;
+  const bool run = creal[3] && pc[1] == pc[0] + 1 && pc[2] == pc[0] + 2 && pc[3] == pc[0] + 3 && (pc[0] & 3) == 0;
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int r = r0 + (threadIdx.x >> 5) + 8 * h;
     if (r >= ntp + n_v) break;
-    double out;
-    if (r < ntp) {
-      if (c > r) continue;
-      if (r >= n_t || !c_real) {
-        out = (r == c) ? 1.0 : 0.0;
-      } else {
-        const int pr = jb.tpos[r];
-        const int hi = pr > pc ? pr : pc, lo = pr > pc ? pc : pr;
-        const long long cv = jb.C[(size_t)hi * jb.rpad + lo];
-        const long long num = N * N * cv - N * (jb.s[pr] + sc) + Q;
-        out = 2.0 * (double)num / den;
-        if (r == c) out += jb.lambda;
-      }
+    const bool in_a = r < ntp;
+    if (in_a && c > r) continue;
+    double out[4];
+    const bool r_real = in_a ? (r < n_t) : true;
+    if (!r_real) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) out[i] = (r == c + i) ? 1.0 : 0.0;
     } else {
-      if (!c_real) {
-        out = 0.0;
+      const int pr = in_a ? jb.tpos[r] : jb.vpos[r - ntp];
+      const long long sr = jb.s[pr];
+      const int32_t* crow = jb.C + (size_t)pr * rpad;
+      if (run && pc[3] < pr) {
+        const int4 cv = *reinterpret_cast<const int4*>(crow + pc[0]);
+        out[0] = grm_entry(cv.x, sr + sc[0], N, Q, den);
+        out[1] = grm_entry(cv.y, sr + sc[1], N, Q, den);
+        out[2] = grm_entry(cv.z, sr + sc[2], N, Q, den);
+        out[3] = grm_entry(cv.w, sr + sc[3], N, Q, den);
       } else {
-        const int pr = jb.vpos[r - ntp];
-        const int hi = pr > pc ? pr : pc, lo = pr > pc ? pc : pr;
-        const long long cv = jb.C[(size_t)hi * jb.rpad + lo];
-        const long long num = N * N * cv - N * (jb.s[pr] + sc) + Q;
-        out = 2.0 * (double)num / den;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (!creal[i]) {
+            out[i] = 0.0;
+          } else {
+            const int hi = pr > pc[i] ? pr : pc[i], lo = pr > pc[i] ? pc[i] : pr;
+            out[i] = grm_entry(jb.C[(size_t)hi * rpad + lo], sr + sc[i], N, Q, den);
+          }
+        }
+      }
+      if (in_a) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (r == c + i) out[i] += jb.lambda;
       }
     }
-    jb.M[(size_t)r * ntp + c] = out;
+    double2* dst = reinterpret_cast<double2*>(jb.M + (size_t)r * ntp + c);
+    dst[0] = make_double2(out[0], out[1]);
+    dst[1] = make_double2(out[2], out[3]);
   }
 }
 
 }  // namespace
 
 cudaError_t tb_launch_scale(const TbScaleJob* d_jobs, int n_jobs, int max_rows, int max_ntp, cudaStream_t st) {
-  dim3 grid((max_ntp + 31) / 32, (max_rows + 31) / 32, n_jobs);
+  dim3 grid((max_ntp + 127) / 128, (max_rows + 15) / 16, n_jobs);
   scale_kernel<<<grid, 256, 0, st>>>(d_jobs);
   return cudaGetLastError();
 }

@@ -114,9 +114,10 @@ cudaError_t tb_launch_colsum(const int8_t* d_x, int ldn, int m, const int* d_pos
 cudaError_t tb_launch_gather(const int8_t* d_x, int ldn, const int* d_idx, const long long* d_off, int w0, int W,
                              int rpad, int kstride, int8_t* d_panel, cudaStream_t st);
 cudaError_t tb_launch_centre_terms(const int8_t* d_panel, int rpad, int kstride, const int* d_idx,
-                                   const long long* d_off, int w0, int W, int n_slots,
+                                   const long long* d_off, int w0, int W, int n_slots, const int* d_kblocks,
                                    const int* const* d_colsum_of, /* [W*n_slots] device ptrs */
-                                   long long* d_s, long long* d_SQ, cudaStream_t st);
+                                   int* d_csg /* [W*n_slots][kstride] scratch */, long long* d_s, long long* d_SQ,
+                                   cudaStream_t st);
 
 // gram_tc.cu / gram_simt.cu
 cudaError_t tb_gram_tc_init();
