@@ -45,6 +45,8 @@ def parse():
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--pop", type=int, default=0, help="override genomes per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--precision", default="mixed", choices=["mixed", "fp64"],
+                    help="mixed: TF32 tensor-core Cholesky preconditioner + fp64 refinement (default); fp64: fp64 Cholesky")
     ap.add_argument("--cpu-sample", type=int, default=0, help="individuals in the CPU sample (default: one per core)")
     return ap.parse_args()
 
@@ -138,11 +140,12 @@ class CpuArm:
 
 
 def chol_update_flops(ntp, nb=64):
-    """Algorithmic flops of the Cholesky update launches of one matrix (lower triangle only):
-    step j contributes 2 * (j nb) * [nb (nb+1)/2 + (ntp - (j+1) nb) nb]."""
+    """Algorithmic flops of the (outer) Cholesky update launches of one matrix, lower triangle only: block column
+    starting at c0 (width w = min(nb, ntp - c0)) contributes 2 * c0 * [w (w+1)/2 + (ntp - c0 - w) w]."""
     tot = 0
-    for j in range(1, ntp // nb):
-        tot += 2 * (j * nb) * (nb * (nb + 1) // 2 + (ntp - (j + 1) * nb) * nb)
+    for c0 in range(nb, ntp, nb):
+        w = min(nb, ntp - c0)
+        tot += 2 * c0 * (w * (w + 1) // 2 + (ntp - c0 - w) * w)
     return tot
 
 
@@ -227,6 +230,7 @@ def main():
             eng.set_rowset(f, tr, va)
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
+    eng.set_precision(args.precision)
 
     n_batches = 2
     batches = [synth.random_genomes(P, m, k, seed=1000 + 17 * rank + b) for b in range(n_batches)]
@@ -276,6 +280,7 @@ def main():
     stage = eng.stage_times()
     eng.set_option("profile", 0)
     wave = eng.last_wave()
+    precision = eng.last_precision()
 
     # -- e2e: host buffers through the public C-ABI call, copies inside the timed region -----------
     for i in range(max(1, min(args.warmup, 2))):
@@ -318,24 +323,36 @@ def main():
         ntp = (n_t + 63) // 64 * 64
         upd_ms, upd_launches = stage["chol_update"]
         n_mats = P * len(slots) * args.steps
-        upd_flops = chol_update_flops(ntp) * n_mats
-        achieved = upd_flops / (upd_ms * 1e-3) / 1e12 if upd_ms > 0 else None
-        gram_ms, gram_launches = stage["gram"]
-        n_v = len(valid) if folds == 1 else len(train) // folds
-        rows_t = len(train)   # Gram covers the union of the fold rows once per individual
-        gram_ops = 2.0 * k * (rows_t * (rows_t + 1) / 2 + (len(valid) * rows_t if folds == 1 else 0)) * P * args.steps
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
         bf16 = peaks.get("bf16_tflops_sustained") or 1400.0
+        if precision == "mixed":
+            upd_flops = chol_update_flops(ntp, 256) * n_mats
+            upd_kernel = "tf32_gemm_kernel (outer left-looking Cholesky update, tcgen05 kind::tf32, M128 x N256)"
+            upd_peak = bf16 / 2
+            upd_peak_src = "0.5 x bf16_tflops_sustained of MEASURED_PEAKS.json (tf32 dense = half the bf16 rate)"
+        else:
+            upd_flops = chol_update_flops(ntp, 64) * n_mats
+            upd_kernel = "chol_gemm_kernel<0> (left-looking Cholesky update, fp64 DMMA)"
+            upd_peak = dmma_peak
+            upd_peak_src = ("fp64 mma.sync issue-rate probe run in this process (MEASURED_PEAKS.json has no fp64 "
+                            "entry; B200 nominal fp64 is 37 TFLOP/s)")
+        achieved = upd_flops / (upd_ms * 1e-3) / 1e12 if upd_ms > 0 else None
+        gram_ms, gram_launches = stage["gram"]
+        n_v = len(valid) if folds == 1 else len(train) // folds
+        rows_t = len(train)   # Gram covers the union of the fold rows once per individual
+        gram_ops = 2.0 * k * (rows_t * (rows_t + 1) / 2 + (len(valid) * rows_t if folds == 1 else 0)) * P * args.steps
         line = {
             "metric": METRIC, "value": evals / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "s8 Gram (s32 accumulate) + f64 Cholesky/solve", "data": "synthetic",
+            "vs_baseline": None,
+            "dtype": ("s8 Gram (s32) + tf32 Cholesky preconditioner + f64 refinement/solve" if precision == "mixed"
+                      else "s8 Gram (s32 accumulate) + f64 Cholesky/solve"), "data": "synthetic",
             "config": {"workload": args.workload, "animals": n, "markers": m, "k": k, "pop_per_gpu": P, "folds": folds,
-                       "h2": H2, "n_train": int(n_t), "n_valid": int(n_v), "individuals_per_wave": wave,
+                       "h2": H2, "n_train": int(n_t), "n_valid": int(n_v), "individuals_per_wave": wave, "precision": precision,
                        "l2": "inputs larger than L2 (each step streams >20 GB of per-genome panels and matrices)",
                        "parallelism": "replicated genotypes, population sharded, NCCL all-gather of fitness"},
             "e2e": {"value": evals / (ms_e2e * 1e-3), "unit": UNIT,
@@ -343,11 +360,10 @@ def main():
                     "d2h_bytes_per_step": int(P * len(slots) * 8), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": "chol_gemm_kernel<0> (left-looking Cholesky update, fp64 DMMA)",
-                         "achieved": achieved, "peak": dmma_peak, "unit": "TFLOP/s",
-                         "frac": (achieved / dmma_peak) if achieved and dmma_peak else None, "traffic": None,
-                         "peak_source": "fp64 mma.sync issue-rate probe run in this process (MEASURED_PEAKS.json has "
-                                        "no fp64 entry; B200 nominal fp64 is 37 TFLOP/s)",
+            "roofline": {"bound": "tensor", "kernel": upd_kernel,
+                         "achieved": achieved, "peak": upd_peak, "unit": "TFLOP/s",
+                         "frac": (achieved / upd_peak) if achieved and upd_peak else None, "traffic": None,
+                         "peak_source": upd_peak_src,
                          "launches": int(upd_launches), "avg_launch_ms": upd_ms / max(1, upd_launches),
                          "share_of_step": upd_ms / ms},
             "roofline_gram": {"bound": "tensor", "kernel": "gram_tc_kernel (tcgen05 kind::i8)",

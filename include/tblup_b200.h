@@ -42,7 +42,9 @@ enum {
   TB_DBG_M = 3,     /* double [(ntp+n_v)*ntp]  [A ; G_vt] (A holds L after the factorisation)        */
   TB_DBG_ALPHA = 4, /* double [ntp]                                                                  */
   TB_DBG_PRED = 5,  /* double [n_v]                                                                  */
-  TB_DBG_DIMS = 6   /* int32  [4]              rpad, ntp, n_v, kstride                               */
+  TB_DBG_DIMS = 6,  /* int32  [4]              rpad, ntp, n_v, kstride                               */
+  TB_DBG_L32 = 7,   /* float  [ntp*ntp]        TF32 Cholesky factor (mixed precision mode only)      */
+  TB_DBG_SWEEPS = 8 /* int32  [1]              refinement sweeps the solve needed (mixed mode)       */
 };
 
 int tb_abi_version(void);
@@ -85,7 +87,9 @@ int tb_gram_debug(tb_ctx* ctx, const int32_t* idx, int k, int rows, int impl, in
 int tb_debug_fetch(tb_ctx* ctx, int what, int job, void* out, size_t nbytes);
 
 /* options: "profile" (0/1: per-stage CUDA-event timing), "stop_after" (stage index, -1 = run all),
- * "workspace_mb" (cap for the wave workspace, 0 = auto), "max_wave" (cap individuals per wave, 0 = auto) */
+ * "workspace_mb" (cap for the wave workspace, 0 = auto), "max_wave" (cap individuals per wave, 0 = auto),
+ * "precision" (0 = mixed: TF32 tensor-core Cholesky as preconditioner + fp64 refinement against the exact
+ * integer operator [default]; 1 = fp64 Cholesky throughout) */
 int tb_set_option(tb_ctx* ctx, const char* name, long long value);
 
 /* Accumulated per-stage device milliseconds (valid with profile=1) and kernel launches since the last
@@ -94,6 +98,8 @@ int tb_stage_times(tb_ctx* ctx, double* ms_out, uint64_t* launches_out);
 uint64_t tb_launch_count(const tb_ctx* ctx);
 int tb_reset_counters(tb_ctx* ctx);
 int tb_last_wave(const tb_ctx* ctx);
+/* precision mode the last evaluation ran in: 0 = mixed, 1 = fp64 */
+int tb_last_precision(const tb_ctx* ctx);
 
 /* Run the context's work on a caller-owned CUDA stream (e.g. torch's current stream, so the caller's CUDA
  * events bracket it); NULL restores the context's own stream. */

@@ -30,6 +30,7 @@ SYMBOLS = {
     "tb_launch_count": (C.c_uint64, [C.c_void_p]),
     "tb_reset_counters": (C.c_int, [C.c_void_p]),
     "tb_last_wave": (C.c_int, [C.c_void_p]),
+    "tb_last_precision": (C.c_int, [C.c_void_p]),
     "tb_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tb_microbench": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
 }

@@ -97,6 +97,21 @@ int ensure_ws(TbCtx* c, size_t bytes) {
   return 0;
 }
 
+struct MarkCtx {
+  TbCtx* c;
+  size_t open;
+  int n_update = 0;
+};
+void mark_cb(void* p, int which, int end) {
+  MarkCtx* m = static_cast<MarkCtx*>(p);
+  if (!end) {
+    m->open = span_begin(m->c, which == 0 ? TB_ST_CHOL_UPDATE : TB_ST_CHOL_PANEL);
+    if (which == 0) m->n_update++;
+  } else {
+    span_end(m->c, m->open);
+  }
+}
+
 struct SlotView {
   const TbRowSet* rs;
   size_t m_elems, linv_elems;
@@ -127,6 +142,15 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     per_ind += (sv[s].m_elems + sv[s].linv_elems + rs->ntp + rs->n_v) * sizeof(double) + 1024;
   }
   has_train.resize(rpad / TB_GRAM_BM, 0);
+  bool mixed = c->precision == 0 && tb_solve_mixed_fits(max_ntp);
+  for (int s = 0; s < n_slots; ++s) mixed = mixed && sv[s].rs->ntp == max_ntp;
+  c->last_mixed = mixed ? 1 : 0;
+  if (mixed) {
+    per_ind = 0;
+    for (int s = 0; s < n_slots; ++s)
+      per_ind += (size_t)max_ntp * max_ntp * sizeof(float) + (size_t)max_ntp * TB_NB * sizeof(float) +
+                 (size_t)(max_ntp + sv[s].rs->n_v) * sizeof(double) + 1024;
+  }
   const int P = c->P;
   int kmax = 0;
   for (int i = 0; i < P; ++i) {
@@ -141,7 +165,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
   size_t free_b = 0, total_b = 0;
   TB_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
   size_t budget = c->ws_limit ? c->ws_limit : (size_t)((double)(free_b + c->ws_bytes) * 0.80);
-  const size_t fixed = (size_t)128 * kstride_max + (size_t)P * n_slots * 256 + (1 << 20);
+  const size_t fixed = (size_t)128 * kstride_max + (size_t)P * n_slots * 512 + (size_t)128 * max_ntp * sizeof(float) + (1 << 20);
   if (budget < fixed + per_ind) budget = fixed + per_ind;
   long long Wll = (long long)((budget - fixed) / per_ind);
   int W = (int)std::min<long long>(Wll, P);
@@ -168,6 +192,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
   std::vector<TbScaleJob> h_scale;
   std::vector<TbCholJob> h_chol;
   std::vector<TbSolveJob> h_solve;
+  std::vector<TbSolveMixedJob> h_msolve;
   std::vector<const int*> h_cs;
   std::vector<int> h_kb;
 
@@ -195,11 +220,23 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     TbScaleJob* d_scale = ar.take<TbScaleJob>(n_jobs);
     TbCholJob* d_chol = ar.take<TbCholJob>(n_jobs);
     TbSolveJob* d_solve = ar.take<TbSolveJob>(n_jobs);
+    TbSolveMixedJob* d_msolve = ar.take<TbSolveMixedJob>(n_jobs);
+    int* d_sweeps = ar.take<int>(n_jobs);
+    float* d_L32 = nullptr;
+    float* d_Linv32 = nullptr;
+    if (mixed) {
+      d_L32 = ar.take<float>(((size_t)n_jobs * max_ntp + 128) * max_ntp);
+      d_Linv32 = ar.take<float>((size_t)n_jobs * max_ntp * TB_NB);
+    }
 
     h_scale.resize(n_jobs);
     h_chol.resize(n_jobs);
     h_solve.resize(n_jobs);
+    h_msolve.resize(n_jobs);
     h_cs.resize(n_jobs);
+    c->dbg.L32 = d_L32;
+    c->dbg.sweeps = d_sweeps;
+    c->dbg.ntp_all = max_ntp;
     c->dbg.W = Wc;
     c->dbg.n_slots = n_slots;
     c->dbg.rpad = rpad;
@@ -218,8 +255,8 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
       for (int s = 0; s < n_slots; ++s) {
         const int job = w * n_slots + s;
         const TbRowSet* rs = sv[s].rs;
-        double* Mj = ar.take<double>(sv[s].m_elems);
-        double* Lj = ar.take<double>(sv[s].linv_elems);
+        double* Mj = mixed ? nullptr : ar.take<double>(sv[s].m_elems);
+        double* Lj = mixed ? nullptr : ar.take<double>(sv[s].linv_elems);
         double* aj = ar.take<double>(rs->ntp);
         double* pj = ar.take<double>(rs->n_v);
         h_cs[job] = gblup ? c->d_colsum_all : rs->d_colsum_train;
@@ -253,6 +290,27 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
         oj.n_t = rs->n_t;
         oj.n_v = rs->n_v;
         oj.ntp = rs->ntp;
+        TbSolveMixedJob& mj = h_msolve[job];
+        mj.L32 = d_L32 ? d_L32 + (size_t)job * max_ntp * max_ntp : nullptr;
+        mj.Linv32 = d_Linv32 ? d_Linv32 + (size_t)job * max_ntp * TB_NB : nullptr;
+        mj.C = sj.C;
+        mj.s = sj.s;
+        mj.SQ = sj.SQ;
+        mj.tpos = rs->d_tpos;
+        mj.vpos = rs->d_vpos;
+        mj.y_t = oj.y_t;
+        mj.y_v = oj.y_v;
+        mj.status = d_status + job;
+        mj.alpha = aj;
+        mj.pred = pj;
+        mj.fitness = oj.fitness;
+        mj.sweeps = d_sweeps + job;
+        mj.N = sj.N;
+        mj.n_t = rs->n_t;
+        mj.n_v = rs->n_v;
+        mj.ntp = rs->ntp;
+        mj.rpad = rpad;
+        mj.lambda = lambda;
         c->dbg.M[job] = Mj;
         c->dbg.alpha[job] = aj;
         c->dbg.pred[job] = pj;
@@ -268,6 +326,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     TB_CUDA(c, cudaMemcpyAsync(d_scale, h_scale.data(), n_jobs * sizeof(TbScaleJob), cudaMemcpyHostToDevice, st));
     TB_CUDA(c, cudaMemcpyAsync(d_chol, h_chol.data(), n_jobs * sizeof(TbCholJob), cudaMemcpyHostToDevice, st));
     TB_CUDA(c, cudaMemcpyAsync(d_solve, h_solve.data(), n_jobs * sizeof(TbSolveJob), cudaMemcpyHostToDevice, st));
+    TB_CUDA(c, cudaMemcpyAsync(d_msolve, h_msolve.data(), n_jobs * sizeof(TbSolveMixedJob), cudaMemcpyHostToDevice, st));
     TB_CUDA(c, cudaMemsetAsync(d_status, 0, n_jobs * sizeof(int), st));
     span_end(c, sp);
 
@@ -292,6 +351,31 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     span_end(c, sp);
     count(c, TB_ST_GRAM, 1);
     if (c->stop_after == TB_ST_GRAM) continue;
+
+    if (mixed) {
+      sp = span_begin(c, TB_ST_SCALE);
+      TB_CUDA(c, tb_launch_scale32(d_scale, n_jobs, max_ntp, d_L32, st));
+      span_end(c, sp);
+      count(c, TB_ST_SCALE, 1);
+      if (c->stop_after == TB_ST_SCALE) continue;
+      {
+        int nl[2] = {0, 0};
+        std::string e;
+        MarkCtx mc{c, 0};
+        cudaError_t ce = tb_chol_tc_factor(d_L32, d_Linv32, d_status, n_jobs, max_ntp, c->n_sm, st, nl, &e,
+                                           c->profile ? &mark_cb : nullptr, &mc);
+        if (ce != cudaSuccess)
+          return fail(c, "tensor-core Cholesky: " + (e.empty() ? std::string(cudaGetErrorString(ce)) : e), -2);
+        count(c, TB_ST_CHOL_UPDATE, mc.n_update);
+        count(c, TB_ST_CHOL_PANEL, nl[0] + nl[1] - mc.n_update);
+      }
+      if (c->stop_after == TB_ST_CHOL_UPDATE || c->stop_after == TB_ST_CHOL_PANEL) continue;
+      sp = span_begin(c, TB_ST_SOLVE);
+      TB_CUDA(c, tb_launch_solve_mixed(d_msolve, n_jobs, max_ntp, st));
+      span_end(c, sp);
+      count(c, TB_ST_SOLVE, 1);
+      continue;
+    }
 
     sp = span_begin(c, TB_ST_SCALE);
     TB_CUDA(c, tb_launch_scale(d_scale, n_jobs, max_rows, max_ntp, st));
@@ -439,7 +523,8 @@ int tb_create(const int8_t* geno, int n, int m, const double* y, const int32_t* 
     if (b2) return bail("");
   }
   if (chk(tb_gram_tc_init(), "gram kernel init") || chk(tb_chol_init(), "cholesky kernel init") ||
-      chk(tb_solve_init(), "solve kernel init"))
+      chk(tb_solve_init(), "solve kernel init") ||
+      chk(tb_chol_tc_init(), "tensor-core cholesky init") || chk(tb_solve_mixed_init(), "mixed solve init"))
     return bail("");
   *out = c;
   return 0;
@@ -650,7 +735,13 @@ int tb_debug_fetch(tb_ctx* c, int what, int job, void* out, size_t nbytes) {
     case TB_DBG_C: src = d.C + (size_t)(job / d.n_slots) * d.rpad * d.rpad; need = (size_t)d.rpad * d.rpad * 4; break;
     case TB_DBG_S: src = d.s + (size_t)job * d.rpad; need = (size_t)d.rpad * 8; break;
     case TB_DBG_SQ: src = d.SQ + (size_t)job * 2; need = 16; break;
-    case TB_DBG_M: src = d.M[job]; need = (size_t)(d.ntp[job] + d.n_v[job]) * d.ntp[job] * 8; break;
+    case 7:
+      if (!d.L32) return fail(c, "tb_debug_fetch: no fp32 factor (fp64 precision mode)");
+      src = d.L32 + (size_t)job * d.ntp_all * d.ntp_all; need = (size_t)d.ntp_all * d.ntp_all * 4; break;
+    case 8: src = d.sweeps + job; need = 4; break;
+    case TB_DBG_M:
+      if (!d.M[job]) return fail(c, "tb_debug_fetch: [A ; G_vt] is not formed in mixed precision mode");
+      src = d.M[job]; need = (size_t)(d.ntp[job] + d.n_v[job]) * d.ntp[job] * 8; break;
     case TB_DBG_ALPHA: src = d.alpha[job]; need = (size_t)d.ntp[job] * 8; break;
     case TB_DBG_PRED: src = d.pred[job]; need = (size_t)d.n_v[job] * 8; break;
     case TB_DBG_DIMS:
@@ -671,6 +762,7 @@ int tb_set_option(tb_ctx* c, const char* name, long long value) {
   else if (s == "stop_after") c->stop_after = (int)value;
   else if (s == "workspace_mb") c->ws_limit = value > 0 ? (size_t)value << 20 : 0;
   else if (s == "max_wave") c->max_wave = (int)value;
+  else if (s == "precision") c->precision = value != 0;
   else return fail(c, "tb_set_option: unknown option '" + s + "'");
   return 0;
 }
@@ -697,6 +789,7 @@ int tb_reset_counters(tb_ctx* c) {
 }
 
 int tb_last_wave(const tb_ctx* c) { return c ? c->last_wave : 0; }
+int tb_last_precision(const tb_ctx* c) { return c ? (c->last_mixed ? 0 : 1) : -1; }
 
 int tb_set_stream(tb_ctx* c, void* cuda_stream) {
   if (!c) return -1;

@@ -1,0 +1,394 @@
+// Mixed-precision batched Cholesky on the 5th-generation tensor cores.
+//
+// The factorisation of A = G_tt + lambda I only has to be good enough to precondition: solve.cu refines the
+// solution against the exact integer cross-products in fp64 until the correction vanishes (cond(A) <= ~150,
+// so a TF32 factor contracts the error by > 100x per sweep).  That moves the n^3/3 flops of
+// tblup/evaluator.py:282 from the FP64 pipe (37 TFLOP/s) to tcgen05.mma.kind::tf32 (~1.1 PFLOP/s nominal).
+//
+// Storage: one fp32 matrix per (individual, row set), L32[job][ntp][ntp] (lower triangle meaningful), plus the
+// fp32 inverses of the 64 x 64 diagonal blocks.  Two-level left-looking schedule, all jobs in lock-step:
+//   outer block column J (256 wide):  T[:, J] -= L[:, 0:J] L[J, 0:J]^T          tf32_gemm  N = 256, K = 256 J
+//   inner block column i (64 wide):   T[:, i] -= L[:, J0:i] L[i, J0:i]^T        tf32_gemm  N = 64,  K <= 192
+//                                     L[i][i] = chol(T[i][i]), Linv_i           chol_diag32_kernel (fp64 math)
+//                                     L[:, i] = T[:, i] Linv_i^T                tf32_gemm  N = 64,  K = 64
+// The wide outer update keeps DRAM traffic at n^3/(6*256) words per matrix (a 64-wide left-looking sweep would be
+// HBM-bound) and gives the MMA its most efficient shape (M128 x N256); the narrow inner steps touch only the
+// 256-wide panel.
+//
+// tf32_gemm_kernel is the Gram kernel's structure (gram_tc.cu) with fp32 operands: persistent CTAs, warp 0 = TMA
+// producer (SWIZZLE_128B boxes of 32 floats x 64 rows, 4-stage ring), warp 1 = single-thread MMA issuer
+// (tcgen05.mma.cta_group::1.kind::tf32, M = 128, N = 64..256, K = 8 per instruction, fp32 accumulators in TMEM,
+// double-buffered), warps 2-5 = epilogue (tcgen05.ld -> read-modify-write of the fp32 tile in global memory).
+#include "tb_internal.h"
+#include "tb_ptx.cuh"
+
+namespace {
+
+using namespace tbptx;
+
+constexpr int NB = TB_NB;            // 64
+constexpr int TBM = 128;             // tile rows
+constexpr int TBK = 32;              // floats per k-block (one 128-byte swizzle span)
+constexpr int BOX_ROWS = 64;         // TMA box: 32 floats x 64 rows = 8 KiB
+constexpr int BOX_BYTES = BOX_ROWS * TBK * 4;
+constexpr int MAX_N = 256;
+constexpr int TSTAGES = 4;
+constexpr int TA_BYTES = TBM * TBK * 4;          // 16 KiB
+constexpr int TB_BYTES_MAX = MAX_N * TBK * 4;    // 32 KiB
+constexpr int TSTAGE_BYTES = TA_BYTES + TB_BYTES_MAX;
+constexpr int TACC = 2;
+constexpr int T_THREADS = 192;
+constexpr int T_SMEM = TSTAGES * TSTAGE_BYTES + 1024 + 256;
+
+struct GemmParams {
+  int n_jobs;
+  int ntp;           // rows (= columns) of every job's matrix; also rows per job in tensor map A
+  int row0;          // first output row
+  int n_mtiles;      // ceil((ntp - row0) / 128)
+  int a_col0;        // K range of the A operand: columns [a_col0, a_col0 + K)
+  int K;             // multiple of 32
+  int b_row0;        // first row of the B operand inside its job
+  int b_col0;        // first column of the B operand
+  int b_rows_per_job;
+  int c_col0;        // first output column (in L32)
+  int N;             // output columns: 64, 128, 192 or 256
+  int mode;          // 0: C -= A B^T   1: C = A B^T rounded to TF32 (final L entries)
+  float* L32;
+};
+
+struct TBarriers {
+  uint64_t full[TSTAGES];
+  uint64_t empty[TSTAGES];
+  uint64_t acc_full[TACC];
+  uint64_t acc_empty[TACC];
+  uint32_t tmem_base;
+};
+
+__host__ __device__ constexpr uint32_t umma_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+         (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+__device__ __forceinline__ float round_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(T_THREADS, 1)
+tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  TBarriers* bars = reinterpret_cast<TBarriers*>(smem + TSTAGES * TSTAGE_BYTES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_items = p.n_jobs * p.n_mtiles;
+  const int nkb = p.K / TBK;
+  const int n_bbox = p.N / BOX_ROWS;
+  const uint32_t stage_tx = TA_BYTES + n_bbox * BOX_BYTES;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tmap_a);
+    prefetch_tensormap(&tmap_b);
+    for (int s = 0; s < TSTAGES; ++s) {
+      mbar_init(&bars->full[s], 1);
+      mbar_init(&bars->empty[s], 1);
+    }
+    for (int s = 0; s < TACC; ++s) {
+      mbar_init(&bars->acc_full[s], 1);
+      mbar_init(&bars->acc_empty[s], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<TACC * MAX_N>(&bars->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = bars->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int job = item / p.n_mtiles, mt = item - job * p.n_mtiles;
+        const int row_a = job * p.ntp + p.row0 + mt * TBM;
+        const int row_b = job * p.b_rows_per_job + p.b_row0;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&bars->empty[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * TSTAGE_BYTES;
+          mbar_arrive_expect_tx(&bars->full[stage], stage_tx);
+          tma_load_2d(sa, &tmap_a, &bars->full[stage], p.a_col0 + kb * TBK, row_a);
+          tma_load_2d(sa + BOX_BYTES, &tmap_a, &bars->full[stage], p.a_col0 + kb * TBK, row_a + BOX_ROWS);
+          for (int b = 0; b < n_bbox; ++b)
+            tma_load_2d(sa + TA_BYTES + b * BOX_BYTES, &tmap_b, &bars->full[stage], p.b_col0 + kb * TBK,
+                        row_b + b * BOX_ROWS);
+          if (++stage == TSTAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_tf32(TBM, p.N);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * MAX_N;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&bars->full[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * TSTAGE_BYTES);
+          const uint64_t adesc = umma_desc_k_sw128(sa);
+          const uint64_t bdesc = umma_desc_k_sw128(sa + TA_BYTES);
+#pragma unroll
+          for (int k = 0; k < TBK / 8; ++k) umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          umma_commit(&bars->empty[stage]);
+          if (++stage == TSTAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        umma_commit(&bars->acc_full[acc]);
+        if (++acc == TACC) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int job = item / p.n_mtiles, mt = item - job * p.n_mtiles;
+      const int r = p.row0 + mt * TBM + q * 32 + lane;          // row inside the job's matrix
+      const int r_hi = p.row0 + mt * TBM + TBM - 1;
+      mbar_wait(&bars->acc_full[acc], acc_phase);
+      tc_fence_after();
+      float* crow = p.L32 + ((size_t)job * p.ntp + (r < p.ntp ? r : 0)) * p.ntp + p.c_col0;
+#pragma unroll 1
+      for (int c = 0; c < p.N / 32; ++c) {
+        if (p.c_col0 + c * 32 > r_hi) continue;                  // strictly above the diagonal: never read
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * MAX_N + c * 32, v);
+        tmem_ld_wait();
+        if (r < p.ntp) {
+          float4* dst = reinterpret_cast<float4*>(crow + c * 32);
+          if (p.mode == 0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 o = dst[i];
+              o.x -= __uint_as_float(v[4 * i]);
+              o.y -= __uint_as_float(v[4 * i + 1]);
+              o.z -= __uint_as_float(v[4 * i + 2]);
+              o.w -= __uint_as_float(v[4 * i + 3]);
+              dst[i] = o;
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              dst[i] = make_float4(round_tf32(__uint_as_float(v[4 * i])), round_tf32(__uint_as_float(v[4 * i + 1])),
+                                   round_tf32(__uint_as_float(v[4 * i + 2])), round_tf32(__uint_as_float(v[4 * i + 3])));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+      if (++acc == TACC) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<TACC * MAX_N>(tmem_base);
+  }
+}
+
+// Diagonal block of the fp32 matrix: same register-resident potrf + inverse as chol_diag_kernel (fp64 math),
+// fp32 storage.  The factor is rounded to TF32 on the way out so that the tensor-core operand truncation is a
+// no-op and the triangular solves in solve.cu use exactly the operator the factorisation built.
+__global__ void __launch_bounds__(256) chol_diag32_kernel(float* __restrict__ L32, float* __restrict__ Linv32,
+                                                          int* __restrict__ status, int ntp, int jb) {
+  extern __shared__ double dsm[];
+  double (*Ls)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dsm);
+  double (*Xs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dsm + NB * (NB + 1));
+  __shared__ double colbuf[2][NB];
+  __shared__ double part[4][NB];
+  __shared__ int bad;
+  const int job = blockIdx.x;
+  float* D = L32 + ((size_t)job * ntp + (size_t)jb * NB) * ntp + jb * NB;
+  const int tid = threadIdx.x;
+  const int r = tid >> 2, q = tid & 3;
+  if (tid == 0) bad = 0;
+  double a[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = q + 4 * i;
+    a[i] = c <= r ? (double)D[(size_t)r * ntp + c] : 0.0;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int c = 0; c < NB; ++c) {
+    const int qc = c & 3, ic = c >> 2;
+    if (q == qc && r >= c) colbuf[c & 1][r] = a[ic];
+    __syncthreads();
+    const double d = colbuf[c & 1][c];
+    if (!(d > 0.0) && tid == 0) bad = 1;
+    const double inv = 1.0 / sqrt(d);
+    if (r >= c) {
+      const double lr = colbuf[c & 1][r] * inv;
+      if (q == qc) a[ic] = lr;
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int cc = q + 4 * i;
+        if (cc > c && cc <= r) a[i] -= lr * (colbuf[c & 1][cc] * inv);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const int c = q + 4 * i;
+    Ls[r][c] = c <= r ? (double)round_tf32((float)a[i]) : 0.0;   // the stored (rounded) factor is what gets inverted
+    Xs[r][c] = 0.0;
+  }
+  __syncthreads();
+  {
+    const int c = tid & 63, h = tid >> 6;
+    for (int rr = 0; rr < NB; ++rr) {
+      double sacc = 0.0;
+      if (c <= rr) {
+        for (int pp = c + h; pp < rr; pp += 4) sacc += Ls[rr][pp] * Xs[pp][c];
+      }
+      part[h][c] = sacc;
+      __syncthreads();
+      if (h == 0 && c <= rr) {
+        const double tot = (part[0][c] + part[1][c]) + (part[2][c] + part[3][c]);
+        Xs[rr][c] = ((c == rr ? 1.0 : 0.0) - tot) / Ls[rr][rr];
+      }
+      __syncthreads();
+    }
+  }
+  float* Li = Linv32 + ((size_t)job * ntp + (size_t)jb * NB) * NB;
+  for (int e = tid; e < NB * NB; e += 256) {
+    const int rr = e >> 6, c = e & 63;
+    D[(size_t)rr * ntp + c] = (float)Ls[rr][c];
+    Li[e] = round_tf32((float)Xs[rr][c]);
+  }
+  if (tid == 0 && bad) status[job] = 1;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode32 = nullptr;
+constexpr int DIAG32_SMEM = 2 * NB * (NB + 1) * (int)sizeof(double);
+
+cudaError_t encode_f32(CUtensorMap* tm, const float* base, size_t cols, size_t rows, std::string* err) {
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(float)};
+  const cuuint32_t box[2] = {(cuuint32_t)TBK, (cuuint32_t)BOX_ROWS};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode32(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) *err = "cuTensorMapEncodeTiled(f32) failed with CUresult " + std::to_string((int)r);
+    return cudaErrorInvalidValue;
+  }
+  return cudaSuccess;
+}
+
+}  // namespace
+
+cudaError_t tb_chol_tc_init() {
+  if (!g_encode32) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+    if (e != cudaSuccess) return e;
+    if (!fn || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
+    g_encode32 = reinterpret_cast<EncodeTiledFn>(fn);
+  }
+  cudaError_t e = cudaFuncSetAttribute(chol_diag32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG32_SMEM);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(tf32_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
+}
+
+// Factor every job's fp32 matrix in place.  L32: [n_jobs * ntp + 128 slack rows][ntp]; Linv32: [n_jobs * ntp][64].
+// launches[0] / launches[1] receive the number of GEMM / diagonal-block kernel launches.
+cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, int* status, int n_jobs, int ntp, int n_sm, cudaStream_t st,
+                              int* launches, std::string* err,
+                              void (*mark)(void*, int, int), void* mark_ctx) {
+  CUtensorMap tm_l, tm_inv;
+  cudaError_t e = encode_f32(&tm_l, L32, (size_t)ntp, (size_t)n_jobs * ntp + 128, err);
+  if (e != cudaSuccess) return e;
+  e = encode_f32(&tm_inv, Linv32, (size_t)NB, (size_t)n_jobs * ntp, err);
+  if (e != cudaSuccess) return e;
+  auto gemm = [&](const CUtensorMap& tb, GemmParams p) -> cudaError_t {
+    p.n_jobs = n_jobs;
+    p.ntp = ntp;
+    p.L32 = L32;
+    p.n_mtiles = (ntp - p.row0 + TBM - 1) / TBM;
+    if (p.n_mtiles <= 0 || p.K <= 0) return cudaSuccess;
+    const int items = n_jobs * p.n_mtiles;
+    const int grid = items < n_sm ? items : n_sm;
+    tf32_gemm_kernel<<<grid, T_THREADS, T_SMEM, st>>>(tm_l, tb, p);
+    launches[0]++;
+    return cudaGetLastError();
+  };
+  const int OB = 256;
+  for (int c0 = 0; c0 < ntp; c0 += OB) {
+    const int w = (ntp - c0) < OB ? (ntp - c0) : OB;
+    if (c0 > 0) {
+      if (mark) mark(mark_ctx, 0, 0);
+      GemmParams p{};
+      p.row0 = c0; p.a_col0 = 0; p.K = c0; p.b_row0 = c0; p.b_col0 = 0; p.b_rows_per_job = ntp; p.c_col0 = c0;
+      p.N = w; p.mode = 0;
+      if ((e = gemm(tm_l, p)) != cudaSuccess) return e;
+      if (mark) mark(mark_ctx, 0, 1);
+    }
+    if (mark) mark(mark_ctx, 1, 0);
+    for (int cc = c0; cc < c0 + w; cc += NB) {
+      if (cc > c0) {
+        GemmParams p{};
+        p.row0 = cc; p.a_col0 = c0; p.K = cc - c0; p.b_row0 = cc; p.b_col0 = c0; p.b_rows_per_job = ntp; p.c_col0 = cc;
+        p.N = NB; p.mode = 0;
+        if ((e = gemm(tm_l, p)) != cudaSuccess) return e;
+      }
+      chol_diag32_kernel<<<n_jobs, 256, DIAG32_SMEM, st>>>(L32, Linv32, status, ntp, cc / NB);
+      launches[1]++;
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      if (cc + NB < ntp) {
+        GemmParams p{};
+        p.row0 = cc + NB; p.a_col0 = cc; p.K = NB; p.b_row0 = cc; p.b_col0 = 0; p.b_rows_per_job = ntp; p.c_col0 = cc;
+        p.N = NB; p.mode = 1;
+        if ((e = gemm(tm_inv, p)) != cudaSuccess) return e;
+      }
+    }
+    if (mark) mark(mark_ctx, 1, 1);
+  }
+  return cudaSuccess;
+}

@@ -76,12 +76,15 @@ struct TbCtx {
   int profile = 0;                // 1: bracket every stage with events (serialises nothing: one stream)
   int stop_after = -1;            // debug: stop the pipeline after this stage
   int max_wave = 0;
+  int precision = 0;              // 0: mixed (TF32 tensor-core Cholesky + fp64 refinement) when possible, 1: fp64
+  int last_mixed = 0;
   int n_sm = 148;
   // layout of the last wave (for tb_debug_fetch)
   struct DbgLayout {
     int W = 0, n_slots = 0, rpad = 0, kstride = 0;
     int32_t* C = nullptr; long long* s = nullptr; long long* SQ = nullptr;
     std::vector<double*> M, alpha, pred;
+    float* L32 = nullptr; int* sweeps = nullptr; int ntp_all = 0;
     std::vector<int> ntp, n_v;
   } dbg;
   double stage_ms[TB_ST_COUNT] = {};
@@ -167,6 +170,34 @@ struct TbSolveJob {
 };
 cudaError_t tb_solve_init();
 cudaError_t tb_launch_solve(const TbSolveJob* d_jobs, int n_jobs, int max_ntp, cudaStream_t st);
+
+// solve_mixed.cu / chol_tc.cu (mixed-precision path)
+struct TbSolveMixedJob {
+  const float* L32;        // [ntp][ntp] TF32 Cholesky factor (lower)
+  const float* Linv32;     // [ntp][64] inverses of its diagonal blocks
+  const int32_t* C;        // [rpad][rpad] integer cross-products
+  const long long* s;      // [rpad]
+  const long long* SQ;     // {S, Q}
+  const int* tpos;
+  const int* vpos;
+  const double* y_t;       // [ntp]
+  const double* y_v;       // [n_v]
+  const int* status;
+  double* alpha;           // [ntp]
+  double* pred;            // [n_v]
+  double* fitness;
+  int* sweeps;             // refinement sweeps used (diagnostics)
+  long long N;
+  int n_t, n_v, ntp, rpad;
+  double lambda;
+};
+cudaError_t tb_solve_mixed_init();
+bool tb_solve_mixed_fits(int ntp);
+cudaError_t tb_launch_solve_mixed(const TbSolveMixedJob* d_jobs, int n_jobs, int ntp, cudaStream_t st);
+cudaError_t tb_launch_scale32(const TbScaleJob* d_jobs, int n_jobs, int ntp, float* L32, cudaStream_t st);
+cudaError_t tb_chol_tc_init();
+cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, int* status, int n_jobs, int ntp, int n_sm, cudaStream_t st,
+                              int* launches, std::string* err, void (*mark)(void*, int, int), void* mark_ctx);
 
 // microbench.cu
 cudaError_t tb_microbench_dmma(int n_sm, cudaStream_t st, double* tflops);

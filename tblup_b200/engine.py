@@ -14,7 +14,8 @@ from . import _lib
 
 MODE_AUTO, MODE_GBLUP, MODE_SNPBLUP = 0, 1, 2
 STAGES = ["h2d", "gather", "centre", "gram", "scale", "chol_update", "chol_panel", "solve", "d2h"]
-DBG_C, DBG_S, DBG_SQ, DBG_M, DBG_ALPHA, DBG_PRED, DBG_DIMS = range(7)
+DBG_C, DBG_S, DBG_SQ, DBG_M, DBG_ALPHA, DBG_PRED, DBG_DIMS, DBG_L32, DBG_SWEEPS = range(9)
+PRECISION_MIXED, PRECISION_FP64 = 0, 1
 
 
 def as_dosage_int8(geno):
@@ -175,6 +176,8 @@ class GblupEngine:
             DBG_M: ((d["ntp"] + d["n_v"], d["ntp"]), np.float64),
             DBG_ALPHA: ((d["ntp"],), np.float64),
             DBG_PRED: ((d["n_v"],), np.float64),
+            DBG_L32: ((d["ntp"], d["ntp"]), np.float32),
+            DBG_SWEEPS: ((1,), np.int32),
         }[what]
         out = np.empty(shape, dtype=dt)
         self._check(self._lib.tb_debug_fetch(self._ctx, what, job, out.ctypes.data, out.nbytes), "tb_debug_fetch")
@@ -200,6 +203,14 @@ class GblupEngine:
         out = C.c_double(0.0)
         self._check(self._lib.tb_microbench(self._ctx, int(which), C.byref(out)), "tb_microbench")
         return float(out.value)
+
+    def set_precision(self, mode):
+        """'mixed' (default): TF32 tensor-core Cholesky as preconditioner + fp64 refinement against the exact integer
+        operator; 'fp64': fp64 Cholesky throughout."""
+        self.set_option("precision", {"mixed": PRECISION_MIXED, "fp64": PRECISION_FP64}[mode])
+
+    def last_precision(self):
+        return {0: "mixed", 1: "fp64"}[int(self._lib.tb_last_precision(self._ctx))]
 
     def last_wave(self):
         return int(self._lib.tb_last_wave(self._ctx))

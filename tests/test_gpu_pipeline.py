@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 FIT_TOL = 1e-6   # north_star: "per-individual fitness agrees with the reference numpy path within 1e-6 absolute"
 
 
-def _engine(x, y, train, valid, test=None, extra_sets=()):
+def _engine(x, y, train, valid, test=None, extra_sets=(), precision="mixed"):
     from tblup_b200 import GblupEngine
     rest = [] if test is None else list(test)
     perm = np.concatenate([np.asarray(train), np.asarray(valid), np.asarray(rest, dtype=np.int64)]).astype(np.int64)
@@ -22,6 +22,7 @@ def _engine(x, y, train, valid, test=None, extra_sets=()):
         missing = np.setdiff1d(np.arange(x.shape[0]), perm)
         perm = np.concatenate([perm, missing])
     eng = GblupEngine(x, y, perm=perm)
+    eng.set_precision(precision)
     eng.set_rowset(0, train, valid)
     for slot, (t, v) in enumerate(extra_sets, start=1):
         eng.set_rowset(slot, t, v)
@@ -31,7 +32,7 @@ def _engine(x, y, train, valid, test=None, extra_sets=()):
 @pytest.fixture(scope="module")
 def mid():
     g = load_golden("fit_mid")
-    eng, perm = _engine(g["x"], g["y"], g["train"], g["valid"], g["test"])
+    eng, perm = _engine(g["x"], g["y"], g["train"], g["valid"], g["test"], precision="fp64")
     yield g, eng, perm
     eng.close()
 
@@ -99,8 +100,9 @@ def test_stage_by_stage_against_oracle(mid, mode):
     assert abs(fit[job] - fit_ref) < 1e-12
 
 
+@pytest.mark.parametrize("precision", ["fp64", "mixed"])
 @pytest.mark.parametrize("name", ["fit_small", "fit_offset", "fit_mid"])
-def test_fitness_matches_reference(name):
+def test_fitness_matches_reference(name, precision):
     """Every branch of blup() on the reference's own numbers: forced gblup, forced snp_blup, the k > n
     dispatch, the testing split (train+valid -> test) and each cross-validation fold."""
     from tblup_b200 import engine as E
@@ -110,10 +112,11 @@ def test_fitness_matches_reference(name):
     f_tr = unpack(g["fold_train_flat"], g["fold_train_off"])
     f_va = unpack(g["fold_valid_flat"], g["fold_valid_off"])
     sets = [(np.concatenate((tr, va)), te)] + list(zip(f_tr, f_va))
-    eng, _ = _engine(x, y, tr, va, te, extra_sets=sets)
+    eng, _ = _engine(x, y, tr, va, te, extra_sets=sets, precision=precision)
     try:
         genomes = unpack(g["genomes_flat"], g["genomes_off"])
         got_g = eng.evaluate(genomes, slots=[0], h2=h2, mode=E.MODE_GBLUP)[:, 0]
+        assert eng.last_precision() == precision
         got_s = eng.evaluate(genomes, slots=[0], h2=h2, mode=E.MODE_SNPBLUP)[:, 0]
         got_all = eng.evaluate(genomes, slots=list(range(len(sets) + 1)), h2=h2, mode=E.MODE_AUTO)
         assert np.abs(got_g - g["ref_gblup"]).max() < FIT_TOL
@@ -125,8 +128,9 @@ def test_fitness_matches_reference(name):
         eng.close()
 
 
+@pytest.mark.parametrize("precision", ["fp64", "mixed"])
 @pytest.mark.parametrize("name", ["traj_gblup", "traj_snpblup", "traj_intercv", "traj_intracv"])
-def test_trajectory_replay(name):
+def test_trajectory_replay(name, precision):
     """Fixed-seed DE runs of the reference (its own Population/evolver/selector): every batch it evaluated
     gets the same fitness (1e-6) and therefore the same parent-vs-child decisions and selected panel."""
     from tblup_b200 import engine as E
@@ -138,7 +142,7 @@ def test_trajectory_replay(name):
     if "fold_train_flat" in g:
         sets = list(zip(unpack(g["fold_train_flat"], g["fold_train_off"]),
                         unpack(g["fold_valid_flat"], g["fold_valid_off"])))
-    eng, _ = _engine(x, y, tr, va, te, extra_sets=sets)
+    eng, _ = _engine(x, y, tr, va, te, extra_sets=sets, precision=precision)
     try:
         genomes = unpack(g["genomes_flat"], g["genomes_off"])
         pos = 0
@@ -170,6 +174,34 @@ def test_trajectory_replay(name):
         eng.close()
 
 
+def test_mixed_precision_factor_and_refinement():
+    """The TF32 tensor-core factor is only a preconditioner: L L^T matches A to TF32 accuracy, and the fp64
+    refinement against the exact integer operator lands on the oracle's alpha / predictions / fitness."""
+    from tblup_b200 import engine as E
+    g = load_golden("fit_mid")
+    x, y, h2 = g["x"], g["y"], float(g["h2"])
+    tr, va = g["train"], g["valid"]
+    eng, _ = _engine(x, y, tr, va, g["test"], precision="mixed")
+    try:
+        genomes = unpack(g["genomes_flat"], g["genomes_off"])
+        fit = eng.evaluate(genomes, slots=[0], h2=h2, mode=E.MODE_GBLUP)[:, 0]
+        assert eng.last_precision() == "mixed"
+        nt = len(tr)
+        for job in (0, 3, 5):
+            ref, d = O.exact_fitness(genomes[job], tr, va, x, y, h2, O.MODE_GBLUP, detail=True)
+            L = np.tril(eng.debug_fetch(E.DBG_L32, job)[:nt, :nt]).astype(np.float64)
+            rel = np.abs(np.tril(L @ L.T - d["A"])).max() / np.abs(d["A"]).max()
+            assert rel < 5e-3, rel                       # TF32: 10 mantissa bits
+            assert rel > 1e-7                            # ... and it really is the low-precision factor
+            sweeps = int(eng.debug_fetch(E.DBG_SWEEPS, job)[0])
+            assert 1 <= sweeps <= 6, sweeps
+            assert np.allclose(eng.debug_fetch(E.DBG_ALPHA, job)[:nt], d["alpha"], rtol=1e-8, atol=1e-11)
+            assert np.allclose(eng.debug_fetch(E.DBG_PRED, job), d["pred"], rtol=1e-8, atol=1e-11)
+            assert abs(fit[job] - ref) < 1e-10
+    finally:
+        eng.close()
+
+
 def test_config1_shape_against_oracle():
     """BASELINE config 1 shape (1000 animals x 10000 markers): random k-subsets on both sides of k = n."""
     from tblup_b200 import engine as E
@@ -182,9 +214,12 @@ def test_config1_shape_against_oracle():
     try:
         rng = np.random.default_rng(1)
         genomes = [rng.choice(10000, size=k, replace=False) for k in (100, 999, 1000, 1001, 1500, 1500, 2500, 4000)]
-        got = eng.evaluate(genomes, slots=[0], h2=0.4, mode=E.MODE_AUTO)[:, 0]
         want = np.array([O.exact_blup(gm, tr, va, x, y, 0.4) for gm in genomes])
-        assert np.abs(got - want).max() < 1e-9
+        for precision in ("fp64", "mixed"):
+            eng.set_precision(precision)
+            got = eng.evaluate(genomes, slots=[0], h2=0.4, mode=E.MODE_AUTO)[:, 0]
+            assert eng.last_precision() == precision
+            assert np.abs(got - want).max() < 1e-9, precision
         xf = x.astype(np.float64)
         for i in (0, 4):
             assert abs(got[i] - O.ref_blup(genomes[i].astype(int), tr, va, xf, y, 0.4)) < FIT_TOL
