@@ -145,6 +145,8 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
   bool mixed = c->precision == 0 && tb_solve_mixed_fits(max_ntp);
   for (int s = 0; s < n_slots; ++s) mixed = mixed && sv[s].rs->ntp == max_ntp;
   c->last_mixed = mixed ? 1 : 0;
+  bool contig_all = true;
+  for (int s = 0; s < n_slots; ++s) contig_all = contig_all && sv[s].rs->contiguous && sv[s].rs->n_t % 4 == 0;
   if (mixed) {
     per_ind = 0;
     for (int s = 0; s < n_slots; ++s)
@@ -371,7 +373,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
       }
       if (c->stop_after == TB_ST_CHOL_UPDATE || c->stop_after == TB_ST_CHOL_PANEL) continue;
       sp = span_begin(c, TB_ST_SOLVE);
-      TB_CUDA(c, tb_launch_solve_mixed(d_msolve, n_jobs, max_ntp, st));
+      TB_CUDA(c, tb_launch_solve_mixed(d_msolve, n_jobs, max_ntp, contig_all ? 1 : 0, st));
       span_end(c, sp);
       count(c, TB_ST_SOLVE, 1);
       continue;
@@ -572,6 +574,8 @@ int tb_set_rowset(tb_ctx* c, int slot, const int32_t* train, int n_t, const int3
   r.rpad = tb_round_up(r.rows, TB_GRAM_BM);
   r.has_train.assign(r.rpad / TB_GRAM_BM, 0);
   for (int i = 0; i < n_t; ++i) r.has_train[tpos[i] / TB_GRAM_BM] = 1;
+  r.contiguous = true;
+  for (int i = 0; i < n_t; ++i) r.contiguous = r.contiguous && tpos[i] == i;
   std::vector<double> yt(r.ntp, 0.0), ytc(r.ntp, 0.0), yv(n_v);
   double mean = 0.0;
   for (int i = 0; i < n_t; ++i) {

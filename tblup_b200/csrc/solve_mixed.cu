@@ -16,7 +16,8 @@ namespace {
 
 constexpr int NB = TB_NB;
 constexpr int ST = 512;
-constexpr int MAX_SWEEPS = 8;
+constexpr int MAX_SWEEPS = 6;
+constexpr double REL_TOL = 1e-9;     // stop when the correction is below 1e-9 of the solution (fitness bar: 1e-6)
 
 __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -45,39 +46,53 @@ __device__ double block_max(double v, double* red) {
   return t;
 }
 
-// work <- (L L^T)^-1 work, in place.
+__device__ __forceinline__ double dot4(const float4 l, const double* z) {
+  const double2 z0 = *reinterpret_cast<const double2*>(z), z1 = *reinterpret_cast<const double2*>(z + 2);
+  return (double)l.x * z0.x + (double)l.y * z0.y + (double)l.z * z1.x + (double)l.w * z1.y;
+}
+__device__ __forceinline__ double dot4i(const int4 c, const double* z) {
+  const double2 z0 = *reinterpret_cast<const double2*>(z), z1 = *reinterpret_cast<const double2*>(z + 2);
+  return (double)c.x * z0.x + (double)c.y * z0.y + (double)c.z * z1.x + (double)c.w * z1.y;
+}
+
+// work <- (L L^T)^-1 work, in place.  All global loads are 16 bytes with four independent loads in flight per
+// thread (the kernel is bound by how many bytes one CTA keeps in flight, not by arithmetic).
 __device__ void apply_minv(const float* __restrict__ L, const float* __restrict__ Linv, int ntp, double* work,
                            double* rvec, double* part) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nb = ntp / NB;
   for (int b = 0; b < nb; ++b) {                      // forward: L z = work
     const int kc = b * NB;
-    for (int i = warp; i < NB; i += ST / 32) {
-      const float4* row = reinterpret_cast<const float4*>(L + (size_t)(kc + i) * ntp);
-      double s0 = 0.0, s1 = 0.0;
-      int c = lane;
-      for (; c + 32 < kc / 4; c += 64) {
-        const float4 l0 = row[c], l1 = row[c + 32];
-        const double* z0 = work + 4 * c;
-        const double* z1 = work + 4 * (c + 32);
-        s0 += (double)l0.x * z0[0] + (double)l0.y * z0[1] + (double)l0.z * z0[2] + (double)l0.w * z0[3];
-        s1 += (double)l1.x * z1[0] + (double)l1.y * z1[1] + (double)l1.z * z1[2] + (double)l1.w * z1[3];
+    {
+      // each warp owns rows kc + 4 warp .. + 3 and streams them together (z is read from smem once for all four)
+      const float4* r0 = reinterpret_cast<const float4*>(L + (size_t)(kc + 4 * warp) * ntp);
+      const size_t rs = ntp / 4;
+      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+      for (int c = lane; c < kc / 4; c += 32) {
+        const float4 l0 = r0[c], l1 = r0[rs + c], l2 = r0[2 * rs + c], l3 = r0[3 * rs + c];
+        const double* z = work + 4 * c;
+        s0 += dot4(l0, z);
+        s1 += dot4(l1, z);
+        s2 += dot4(l2, z);
+        s3 += dot4(l3, z);
       }
-      for (; c < kc / 4; c += 32) {
-        const float4 l0 = row[c];
-        const double* z0 = work + 4 * c;
-        s0 += (double)l0.x * z0[0] + (double)l0.y * z0[1] + (double)l0.z * z0[2] + (double)l0.w * z0[3];
+      s0 = warp_sum(s0);
+      s1 = warp_sum(s1);
+      s2 = warp_sum(s2);
+      s3 = warp_sum(s3);
+      if (lane == 0) {
+        rvec[4 * warp + 0] = work[kc + 4 * warp + 0] - s0;
+        rvec[4 * warp + 1] = work[kc + 4 * warp + 1] - s1;
+        rvec[4 * warp + 2] = work[kc + 4 * warp + 2] - s2;
+        rvec[4 * warp + 3] = work[kc + 4 * warp + 3] - s3;
       }
-      const double s = warp_sum(s0 + s1);
-      if (lane == 0) rvec[i] = work[kc + i] - s;
     }
     __syncthreads();
     {
       const int i = tid >> 3, sub = tid & 7;
-      const float* li = Linv + ((size_t)kc + i) * NB + sub * 8;
-      double s = 0.0;
-#pragma unroll
-      for (int pp = 0; pp < 8; ++pp) s += (double)li[pp] * rvec[sub * 8 + pp];
+      const float4* li = reinterpret_cast<const float4*>(Linv + ((size_t)kc + i) * NB + sub * 8);
+      const double s_ = dot4(li[0], rvec + sub * 8) + dot4(li[1], rvec + sub * 8 + 4);
+      double s = s_;
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
       s += __shfl_xor_sync(0xffffffffu, s, 4);
@@ -88,23 +103,48 @@ __device__ void apply_minv(const float* __restrict__ L, const float* __restrict_
   for (int b = nb - 1; b >= 0; --b) {                 // backward: L^T d = z
     const int kc = b * NB;
     {
-      const int c = tid & 63, grp = tid >> 6;
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      int i = kc + NB + grp;
-      for (; i + 24 < ntp; i += 32) {
-        s0 += (double)L[(size_t)i * ntp + kc + c] * work[i];
-        s1 += (double)L[(size_t)(i + 8) * ntp + kc + c] * work[i + 8];
-        s2 += (double)L[(size_t)(i + 16) * ntp + kc + c] * work[i + 16];
-        s3 += (double)L[(size_t)(i + 24) * ntp + kc + c] * work[i + 24];
+      // thread = 4 consecutive columns (one float4) x one of 32 row groups
+      const int cq = tid & 15, rg = tid >> 4;
+      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+      const float* base = L + kc + 4 * cq;
+      int i = kc + NB + rg;
+      for (; i + 96 < ntp; i += 128) {
+        const float4 l0 = *reinterpret_cast<const float4*>(base + (size_t)i * ntp);
+        const float4 l1 = *reinterpret_cast<const float4*>(base + (size_t)(i + 32) * ntp);
+        const float4 l2 = *reinterpret_cast<const float4*>(base + (size_t)(i + 64) * ntp);
+        const float4 l3 = *reinterpret_cast<const float4*>(base + (size_t)(i + 96) * ntp);
+        const double w0 = work[i], w1 = work[i + 32], w2 = work[i + 64], w3 = work[i + 96];
+        a0 += (double)l0.x * w0 + (double)l1.x * w1 + (double)l2.x * w2 + (double)l3.x * w3;
+        a1 += (double)l0.y * w0 + (double)l1.y * w1 + (double)l2.y * w2 + (double)l3.y * w3;
+        a2 += (double)l0.z * w0 + (double)l1.z * w1 + (double)l2.z * w2 + (double)l3.z * w3;
+        a3 += (double)l0.w * w0 + (double)l1.w * w1 + (double)l2.w * w2 + (double)l3.w * w3;
       }
-      for (; i < ntp; i += 8) s0 += (double)L[(size_t)i * ntp + kc + c] * work[i];
-      part[grp * NB + c] = (s0 + s1) + (s2 + s3);
+      for (; i < ntp; i += 32) {
+        const float4 l0 = *reinterpret_cast<const float4*>(base + (size_t)i * ntp);
+        const double w0 = work[i];
+        a0 += (double)l0.x * w0;
+        a1 += (double)l0.y * w0;
+        a2 += (double)l0.z * w0;
+        a3 += (double)l0.w * w0;
+      }
+      // the two row groups of a warp (lanes l and l ^ 16) are combined by shuffle, then one smem row per warp
+      a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, 16);
+      a3 += __shfl_xor_sync(0xffffffffu, a3, 16);
+      if (lane < 16) {
+        double* pr = part + warp * NB + 4 * cq;
+        pr[0] = a0;
+        pr[1] = a1;
+        pr[2] = a2;
+        pr[3] = a3;
+      }
     }
     __syncthreads();
     if (tid < NB) {
       double s = 0.0;
 #pragma unroll
-      for (int gI = 0; gI < 8; ++gI) s += part[gI * NB + tid];
+      for (int gI = 0; gI < ST / 32; ++gI) s += part[gI * NB + tid];
       rvec[tid] = work[kc + tid] - s;
     }
     __syncthreads();
@@ -130,46 +170,85 @@ __device__ void apply_minv(const float* __restrict__ L, const float* __restrict_
   }
 }
 
-__global__ void __launch_bounds__(ST) solve_mixed_kernel(const TbSolveMixedJob* __restrict__ jobs) {
-  extern __shared__ double msm[];
-  const TbSolveMixedJob jb = jobs[blockIdx.x];
-  const int ntp = jb.ntp, n_t = jb.n_t, n_v = jb.n_v, rpad = jb.rpad;
-  double* alpha = msm;               // [ntp]
-  double* work = alpha + ntp;        // [ntp]
-  double* sT = work + ntp;           // [ntp] s at the training positions
-  double* rvec = sT + ntp;           // [NB]
-  double* part = rvec + NB;          // [8][NB]
-  double* red = part + 8 * NB;       // [ST/32]
-  int* tp = reinterpret_cast<int*>(red + ST / 32);   // [ntp]
+// (C alpha)_a over the training animals into work[a]; CONTIG: training animal b sits at universe position b.
+template <bool CONTIG>
+__device__ void sym_matvec(const int32_t* __restrict__ C, int rpad, int n_t, const int* tp, const double* alpha,
+                           double* work, double* part2) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const double Nd = (double)jb.N, Sd = (double)jb.SQ[0], Qd = (double)jb.SQ[1];
-  const double coef = 2.0 / (2.0 * Nd * Sd - Qd);
-  const int32_t* C = jb.C;
-
-  for (int a = tid; a < ntp; a += ST) {
-    const bool real = a < n_t;
-    const int pa = real ? jb.tpos[a] : 0;
-    tp[a] = pa;
-    sT[a] = real ? (double)jb.s[pa] : 0.0;
-    work[a] = jb.y_t[a];
-  }
-  __syncthreads();
-  apply_minv(jb.L32, jb.Linv32, ntp, work, rvec, part);
-  for (int a = tid; a < ntp; a += ST) alpha[a] = work[a];
-  __syncthreads();
-
-  int sweeps = 0;
-  double sa = 0.0, ssa = 0.0;
-  for (;;) {
-    double l0 = 0.0, l1 = 0.0;
-    for (int a = tid; a < n_t; a += ST) {
-      l0 += alpha[a];
-      l1 += sT[a] * alpha[a];
+  if (CONTIG) {
+    // rows: (C alpha)_a += sum_{b <= a} C[a][b] alpha_b, 16-byte loads, four in flight
+    for (int a = warp; a < n_t; a += ST / 32) {
+      const int4* row = reinterpret_cast<const int4*>(C + (size_t)a * rpad);
+      const int n4 = a / 4 + 1;                     // int4 groups that contain a column <= a
+      double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+      int c = lane;
+      for (; c + 96 < n4 - 1; c += 128) {           // groups strictly before the one holding the diagonal
+        const int4 v0 = row[c], v1 = row[c + 32], v2 = row[c + 64], v3 = row[c + 96];
+        d0 += dot4i(v0, alpha + 4 * c);
+        d1 += dot4i(v1, alpha + 4 * (c + 32));
+        d2 += dot4i(v2, alpha + 4 * (c + 64));
+        d3 += dot4i(v3, alpha + 4 * (c + 96));
+      }
+      for (; c < n4; c += 32) {
+        const int4 v = row[c];
+        const int b = 4 * c;
+        d0 += (double)v.x * alpha[b];
+        if (b + 1 <= a) d1 += (double)v.y * alpha[b + 1];
+        if (b + 2 <= a) d2 += (double)v.z * alpha[b + 2];
+        if (b + 3 <= a) d3 += (double)v.w * alpha[b + 3];
+      }
+      const double d = warp_sum((d0 + d1) + (d2 + d3));
+      if (lane == 0) work[a] = d;
     }
-    sa = block_sum(l0, red);
-    ssa = block_sum(l1, red);
-    if (sweeps == MAX_SWEEPS) break;
-    // ---- r = y - A alpha : rows (b <= a) ...
+    __syncthreads();
+    // columns: (C alpha)_a += sum_{b > a} C[b][a] alpha_b; thread = 4 consecutive columns x one of 4 row groups
+    const int cg = tid & 127, rg = tid >> 7;
+    for (int a0 = 0; a0 < n_t; a0 += 512) {
+      const int ca = a0 + 4 * cg;
+      double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
+      if (ca < n_t) {
+        const int32_t* colp = C + ca;
+        int b = a0 + 1 + rg;
+        const int b_tri = min(n_t, a0 + 516);        // rows that may still cross the diagonal of this column block
+        for (; b < b_tri; b += 4) {
+          const int4 v = *reinterpret_cast<const int4*>(colp + (size_t)b * rpad);
+          const double w = alpha[b];
+          if (b > ca) e0 += (double)v.x * w;
+          if (b > ca + 1) e1 += (double)v.y * w;
+          if (b > ca + 2) e2 += (double)v.z * w;
+          if (b > ca + 3) e3 += (double)v.w * w;
+        }
+        for (; b + 12 < n_t; b += 16) {
+          const int4 v0 = *reinterpret_cast<const int4*>(colp + (size_t)b * rpad);
+          const int4 v1 = *reinterpret_cast<const int4*>(colp + (size_t)(b + 4) * rpad);
+          const int4 v2 = *reinterpret_cast<const int4*>(colp + (size_t)(b + 8) * rpad);
+          const int4 v3 = *reinterpret_cast<const int4*>(colp + (size_t)(b + 12) * rpad);
+          const double w0 = alpha[b], w1 = alpha[b + 4], w2 = alpha[b + 8], w3 = alpha[b + 12];
+          e0 += (double)v0.x * w0 + (double)v1.x * w1 + (double)v2.x * w2 + (double)v3.x * w3;
+          e1 += (double)v0.y * w0 + (double)v1.y * w1 + (double)v2.y * w2 + (double)v3.y * w3;
+          e2 += (double)v0.z * w0 + (double)v1.z * w1 + (double)v2.z * w2 + (double)v3.z * w3;
+          e3 += (double)v0.w * w0 + (double)v1.w * w1 + (double)v2.w * w2 + (double)v3.w * w3;
+        }
+        for (; b < n_t; b += 4) {
+          const int4 v = *reinterpret_cast<const int4*>(colp + (size_t)b * rpad);
+          const double w = alpha[b];
+          e0 += (double)v.x * w;
+          e1 += (double)v.y * w;
+          e2 += (double)v.z * w;
+          e3 += (double)v.w * w;
+        }
+      }
+      double* pr = part2 + rg * 512 + 4 * cg;
+      pr[0] = e0;
+      pr[1] = e1;
+      pr[2] = e2;
+      pr[3] = e3;
+      __syncthreads();
+      const int a = a0 + tid;
+      if (a < n_t) work[a] += (part2[tid] + part2[512 + tid]) + (part2[1024 + tid] + part2[1536 + tid]);
+      __syncthreads();
+    }
+  } else {
     for (int a = warp; a < n_t; a += ST / 32) {
       const int pa = tp[a];
       double d0 = 0.0, d1 = 0.0;
@@ -189,7 +268,6 @@ __global__ void __launch_bounds__(ST) solve_mixed_kernel(const TbSolveMixedJob* 
       if (lane == 0) work[a] = d;
     }
     __syncthreads();
-    // ---- ... and columns (b > a): consecutive threads own consecutive columns, rows are streamed
     for (int a0 = 0; a0 < n_t; a0 += ST) {
       const int a = a0 + tid;
       if (a < n_t) {
@@ -211,12 +289,60 @@ __global__ void __launch_bounds__(ST) solve_mixed_kernel(const TbSolveMixedJob* 
           const int p0 = tp[b];
           d0 += (double)C[(size_t)(pa > p0 ? pa : p0) * rpad + (pa > p0 ? p0 : pa)] * alpha[b];
         }
-        const double ca = work[a] + (d0 + d1) + (d2 + d3);
-        const double Aa = jb.lambda * alpha[a] + coef * (Nd * Nd * ca - Nd * sT[a] * sa - Nd * ssa + Qd * sa);
-        work[a] = jb.y_t[a] - Aa;
+        work[a] += (d0 + d1) + (d2 + d3);
       }
     }
-    for (int a = n_t + tid; a < ntp; a += ST) work[a] = 0.0;
+    __syncthreads();
+  }
+}
+
+template <bool CONTIG>
+__global__ void __launch_bounds__(ST) solve_mixed_kernel(const TbSolveMixedJob* __restrict__ jobs) {
+  extern __shared__ double msm[];
+  const TbSolveMixedJob jb = jobs[blockIdx.x];
+  const int ntp = jb.ntp, n_t = jb.n_t, n_v = jb.n_v, rpad = jb.rpad;
+  double* alpha = msm;               // [ntp]
+  double* work = alpha + ntp;        // [ntp]
+  double* rvec = work + ntp;         // [NB]
+  double* part = rvec + NB;          // [ST/32][NB]
+  double* part2 = part + (ST / 32) * NB;   // [4][512]
+  double* red = part2 + 4 * 512;     // [ST/32]
+  int* tp = reinterpret_cast<int*>(red + ST / 32);   // [ntp]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const double Nd = (double)jb.N, Sd = (double)jb.SQ[0], Qd = (double)jb.SQ[1];
+  const double coef = 2.0 / (2.0 * Nd * Sd - Qd);
+  const int32_t* C = jb.C;
+
+  for (int a = tid; a < ntp; a += ST) {
+    tp[a] = a < n_t ? jb.tpos[a] : 0;
+    work[a] = jb.y_t[a];
+  }
+  __syncthreads();
+  apply_minv(jb.L32, jb.Linv32, ntp, work, rvec, part);
+  for (int a = tid; a < ntp; a += ST) alpha[a] = work[a];
+  __syncthreads();
+
+  int sweeps = 0;
+  double sa = 0.0, ssa = 0.0, prev_dmax = 1e300;
+  for (;;) {
+    double l0 = 0.0, l1 = 0.0;
+    for (int a = tid; a < n_t; a += ST) {
+      l0 += alpha[a];
+      l1 += (double)jb.s[tp[a]] * alpha[a];
+    }
+    sa = block_sum(l0, red);
+    ssa = block_sum(l1, red);
+    if (sweeps == MAX_SWEEPS) break;
+    sym_matvec<CONTIG>(C, rpad, n_t, tp, alpha, work, part2);      // work[a] = (C alpha)_a, a < n_t
+    for (int a = tid; a < ntp; a += ST) {
+      double rr = 0.0;
+      if (a < n_t) {
+        const double Aa = jb.lambda * alpha[a] +
+                          coef * (Nd * Nd * work[a] - Nd * (double)jb.s[tp[a]] * sa - Nd * ssa + Qd * sa);
+        rr = jb.y_t[a] - Aa;
+      }
+      work[a] = rr;
+    }
     __syncthreads();
     apply_minv(jb.L32, jb.Linv32, ntp, work, rvec, part);
     double dmax = 0.0, amax = 0.0;
@@ -230,12 +356,14 @@ __global__ void __launch_bounds__(ST) solve_mixed_kernel(const TbSolveMixedJob* 
     dmax = block_max(dmax, red);
     amax = block_max(amax, red);
     ++sweeps;
-    if (!(dmax > 1e-11 * amax)) {
-      // converged: one more pass through the loop head refreshes sa / ssa for the prediction, then leave
+    const bool converged = !(dmax > REL_TOL * amax);
+    const bool stalled = dmax > 0.5 * prev_dmax;       // rounding floor of the residual reached
+    prev_dmax = dmax;
+    if (converged || stalled) {
       double m0 = 0.0, m1 = 0.0;
       for (int a = tid; a < n_t; a += ST) {
         m0 += alpha[a];
-        m1 += sT[a] * alpha[a];
+        m1 += (double)jb.s[tp[a]] * alpha[a];
       }
       sa = block_sum(m0, red);
       ssa = block_sum(m1, red);
@@ -248,20 +376,35 @@ __global__ void __launch_bounds__(ST) solve_mixed_kernel(const TbSolveMixedJob* 
   // ---- predictions on the validation animals
   for (int v = warp; v < n_v; v += ST / 32) {
     const int pv = jb.vpos[v];
-    double d0 = 0.0, d1 = 0.0;
-    int b = lane;
-    for (; b + 32 < n_t; b += 64) {
-      const int p0 = tp[b], p1 = tp[b + 32];
-      const int c0 = C[(size_t)(pv > p0 ? pv : p0) * rpad + (pv > p0 ? p0 : pv)];
-      const int c1 = C[(size_t)(pv > p1 ? pv : p1) * rpad + (pv > p1 ? p1 : pv)];
-      d0 += (double)c0 * alpha[b];
-      d1 += (double)c1 * alpha[b + 32];
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+    if (CONTIG && pv >= n_t) {
+      const int4* row = reinterpret_cast<const int4*>(C + (size_t)pv * rpad);
+      const int n4 = n_t / 4;
+      int c = lane;
+      for (; c + 96 < n4; c += 128) {
+        const int4 v0 = row[c], v1 = row[c + 32], v2 = row[c + 64], v3 = row[c + 96];
+        d0 += dot4i(v0, alpha + 4 * c);
+        d1 += dot4i(v1, alpha + 4 * (c + 32));
+        d2 += dot4i(v2, alpha + 4 * (c + 64));
+        d3 += dot4i(v3, alpha + 4 * (c + 96));
+      }
+      for (; c < n4; c += 32) d0 += dot4i(row[c], alpha + 4 * c);
+      for (int b = 4 * n4 + lane; b < n_t; b += 32) d1 += (double)C[(size_t)pv * rpad + b] * alpha[b];
+    } else {
+      int b = lane;
+      for (; b + 32 < n_t; b += 64) {
+        const int p0 = tp[b], p1 = tp[b + 32];
+        const int c0 = C[(size_t)(pv > p0 ? pv : p0) * rpad + (pv > p0 ? p0 : pv)];
+        const int c1 = C[(size_t)(pv > p1 ? pv : p1) * rpad + (pv > p1 ? p1 : pv)];
+        d0 += (double)c0 * alpha[b];
+        d1 += (double)c1 * alpha[b + 32];
+      }
+      for (; b < n_t; b += 32) {
+        const int p0 = tp[b];
+        d0 += (double)C[(size_t)(pv > p0 ? pv : p0) * rpad + (pv > p0 ? p0 : pv)] * alpha[b];
+      }
     }
-    for (; b < n_t; b += 32) {
-      const int p0 = tp[b];
-      d0 += (double)C[(size_t)(pv > p0 ? pv : p0) * rpad + (pv > p0 ? p0 : pv)] * alpha[b];
-    }
-    const double d = warp_sum(d0 + d1);
+    const double d = warp_sum((d0 + d1) + (d2 + d3));
     if (lane == 0) jb.pred[v] = coef * (Nd * Nd * d - Nd * (double)jb.s[pv] * sa - Nd * ssa + Qd * sa);
   }
   __syncthreads();
@@ -360,20 +503,30 @@ int g_solve_mixed_smem_max = 0;
 }  // namespace
 
 static inline int solve_mixed_smem_bytes(int ntp) {
-  return (3 * ntp + NB + 8 * NB + ST / 32) * (int)sizeof(double) + ntp * (int)sizeof(int);
+  return (2 * ntp + NB + (ST / 32) * NB + 4 * 512 + ST / 32) * (int)sizeof(double) + ntp * (int)sizeof(int);
 }
 
 cudaError_t tb_solve_mixed_init() {
   g_solve_mixed_smem_max = 220 * 1024;
-  return cudaFuncSetAttribute(solve_mixed_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_solve_mixed_smem_max);
+  cudaError_t e = cudaFuncSetAttribute(solve_mixed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       g_solve_mixed_smem_max);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(solve_mixed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              g_solve_mixed_smem_max);
 }
 
 bool tb_solve_mixed_fits(int ntp) { return solve_mixed_smem_bytes(ntp) <= 220 * 1024; }
 
-cudaError_t tb_launch_solve_mixed(const TbSolveMixedJob* d_jobs, int n_jobs, int ntp, cudaStream_t st) {
+// contiguous != 0: every job's training animal b sits at universe position b and n_t is a multiple of 4
+// (vectorised symmetric mat-vec); otherwise positions are looked up per element.
+cudaError_t tb_launch_solve_mixed(const TbSolveMixedJob* d_jobs, int n_jobs, int ntp, int contiguous,
+                                  cudaStream_t st) {
   const int smem = solve_mixed_smem_bytes(ntp);
   if (smem > g_solve_mixed_smem_max) return cudaErrorInvalidConfiguration;
-  solve_mixed_kernel<<<n_jobs, ST, smem, st>>>(d_jobs);
+  if (contiguous)
+    solve_mixed_kernel<true><<<n_jobs, ST, smem, st>>>(d_jobs);
+  else
+    solve_mixed_kernel<false><<<n_jobs, ST, smem, st>>>(d_jobs);
   return cudaGetLastError();
 }
 

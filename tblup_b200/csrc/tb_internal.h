@@ -41,6 +41,7 @@ struct TbRowSet {
   double* d_yt_ctr = nullptr;   // [ntp] y_t minus its mean
   double* d_yv = nullptr;       // [n_v]
   std::vector<unsigned char> has_train;   // per 128-row universe block: contains a training animal
+  bool contiguous = false;      // training animal b sits at universe position b
 };
 
 struct TbCtx {
@@ -193,7 +194,8 @@ struct TbSolveMixedJob {
 };
 cudaError_t tb_solve_mixed_init();
 bool tb_solve_mixed_fits(int ntp);
-cudaError_t tb_launch_solve_mixed(const TbSolveMixedJob* d_jobs, int n_jobs, int ntp, cudaStream_t st);
+cudaError_t tb_launch_solve_mixed(const TbSolveMixedJob* d_jobs, int n_jobs, int ntp, int contiguous,
+                                  cudaStream_t st);
 cudaError_t tb_launch_scale32(const TbScaleJob* d_jobs, int n_jobs, int ntp, float* L32, cudaStream_t st);
 cudaError_t tb_chol_tc_init();
 cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, int* status, int n_jobs, int ntp, int n_sm, cudaStream_t st,
