@@ -5,7 +5,8 @@
 //   (A alpha)_a = lambda alpha_a + (2/den) [ N^2 (C alpha)_a - N s_a (sum alpha) - N (s . alpha) + Q (sum alpha) ]
 //
 // with C, s, S, Q the integers of scale.cu / DESIGN.md §1 and den = 2 N S - Q.  Iteration:
-//   alpha <- M^-1 y;  repeat { r = y - A alpha;  d = M^-1 r;  alpha += d } until max|d| <= 1e-11 max|alpha|
+//   alpha <- M^-1 y;  repeat { r = y - A alpha;  d = M^-1 r;  alpha += d } until the predicted remaining error
+//   max|d| * (observed contraction) <= 1e-9 max|alpha|   (typically 2 sweeps; at most 6)
 // where M^-1 = (L L^T)^-1 by blocked substitution (fp32 factor, fp64 accumulation).  Then
 //   pred_v = (G_vt alpha)_v from the integer rows of the validation animals, fitness = |pearson(y_v, pred_v)|.
 // Same reference lines as solve.cu (tblup/evaluator.py:282-286, :311-314).  One CTA per (individual, row set);
@@ -17,7 +18,8 @@ namespace {
 constexpr int NB = TB_NB;
 constexpr int ST = 512;
 constexpr int MAX_SWEEPS = 6;
-constexpr double REL_TOL = 1e-9;     // stop when the correction is below 1e-9 of the solution (fitness bar: 1e-6)
+constexpr double REL_TOL = 1e-9;     // stop when the PREDICTED remaining error is below 1e-9 of the solution
+                                     // (fitness bar of BASELINE.json: 1e-6 absolute)
 
 __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -356,8 +358,12 @@ __global__ void __launch_bounds__(ST) solve_mixed_kernel(const TbSolveMixedJob* 
     dmax = block_max(dmax, red);
     amax = block_max(amax, red);
     ++sweeps;
-    const bool converged = !(dmax > REL_TOL * amax);
-    const bool stalled = dmax > 0.5 * prev_dmax;       // rounding floor of the residual reached
+    // the correction just applied was the previous error; the error now left is about dmax * rho with
+    // rho = dmax / prev_dmax the observed contraction (first sweep: assume rho <= 0.05, the TF32 factor
+    // contracts by 1e-2 .. 1e-3 for cond(A) up to a few hundred)
+    const double rho = sweeps == 1 ? 0.05 : fmin(1.0, dmax / prev_dmax);
+    const bool converged = !(dmax * rho > REL_TOL * amax);
+    const bool stalled = sweeps > 1 && dmax > 0.5 * prev_dmax;   // rounding floor of the residual reached
     prev_dmax = dmax;
     if (converged || stalled) {
       double m0 = 0.0, m1 = 0.0;
