@@ -195,9 +195,11 @@ def test_mixed_precision_factor_and_refinement():
             assert rel > 1e-7                            # ... and it really is the low-precision factor
             sweeps = int(eng.debug_fetch(E.DBG_SWEEPS, job)[0])
             assert 1 <= sweeps <= 6, sweeps
-            assert np.allclose(eng.debug_fetch(E.DBG_ALPHA, job)[:nt], d["alpha"], rtol=1e-8, atol=1e-11)
-            assert np.allclose(eng.debug_fetch(E.DBG_PRED, job), d["pred"], rtol=1e-8, atol=1e-11)
-            assert abs(fit[job] - ref) < 1e-10
+            # refinement stops once the predicted remaining error is below 1e-8 of max|alpha|
+            amax = np.abs(d["alpha"]).max()
+            assert np.abs(eng.debug_fetch(E.DBG_ALPHA, job)[:nt] - d["alpha"]).max() < 2e-8 * amax
+            assert np.abs(eng.debug_fetch(E.DBG_PRED, job) - d["pred"]).max() < 2e-8 * np.abs(d["pred"]).max() + 1e-9
+            assert abs(fit[job] - ref) < 1e-7
     finally:
         eng.close()
 
@@ -219,7 +221,7 @@ def test_config1_shape_against_oracle():
             eng.set_precision(precision)
             got = eng.evaluate(genomes, slots=[0], h2=0.4, mode=E.MODE_AUTO)[:, 0]
             assert eng.last_precision() == precision
-            assert np.abs(got - want).max() < 1e-9, precision
+            assert np.abs(got - want).max() < (1e-9 if precision == "fp64" else 1e-7), precision
         xf = x.astype(np.float64)
         for i in (0, 4):
             assert abs(got[i] - O.ref_blup(genomes[i].astype(int), tr, va, xf, y, 0.4)) < FIT_TOL
