@@ -281,6 +281,10 @@ def main():
     eng.set_option("profile", 0)
     wave = eng.last_wave()
     precision = eng.last_precision()
+    mean_sweeps = None
+    if precision == "mixed":
+        last = (P - 1) % wave + 1            # jobs in the last wave (the one the debug view points at)
+        mean_sweeps = float(np.mean([eng.debug_fetch(E.DBG_SWEEPS, j)[0] for j in range(min(last * len(slots), 64))]))
 
     # -- e2e: host buffers through the public C-ABI call, copies inside the timed region -----------
     for i in range(max(1, min(args.warmup, 2))):
@@ -345,6 +349,32 @@ def main():
         n_v = len(valid) if folds == 1 else len(train) // folds
         rows_t = len(train)   # Gram covers the union of the fold rows once per individual
         gram_ops = 2.0 * k * (rows_t * (rows_t + 1) / 2 + (len(valid) * rows_t if folds == 1 else 0)) * P * args.steps
+        hbm = peaks.get("hbm_gbs") or 6650.0
+        rl_update = {"bound": "tensor", "kernel": upd_kernel, "achieved": achieved, "peak": upd_peak, "unit": "TFLOP/s",
+                     "frac": (achieved / upd_peak) if achieved and upd_peak else None, "traffic": None,
+                     "peak_source": upd_peak_src, "launches": int(upd_launches),
+                     "avg_launch_ms": upd_ms / max(1, upd_launches), "share_of_step": upd_ms / ms}
+        solve_ms, solve_launches = stage["solve"]
+        tri_bytes = n_t * (n_t + 1) / 2 * 4          # lower triangle of the fp32 factor == of the int32 cross-products
+        if precision == "mixed":
+            # per matrix: (1 + sweeps) preconditioner applications (factor read forwards and backwards), `sweeps`
+            # symmetric mat-vecs on the integer cross-products (lower triangle read by rows and by columns), one
+            # pass over the validation rows
+            per_mat = (1 + mean_sweeps) * 2 * tri_bytes + mean_sweeps * 2 * tri_bytes + n_v * n_t * 4
+            solve_kernel = ("solve_mixed_kernel (blocked substitution with the TF32 factor + fp64 refinement on the "
+                            "integer cross-products + predictions + Pearson)")
+        else:
+            per_mat = 2 * n_t * (n_t + 1) / 2 * 8 + n_v * n_t * 8
+            solve_kernel = "solve_kernel (fp64 blocked substitution + predictions + Pearson)"
+        solve_gbs = per_mat * n_mats / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else None
+        rl_solve = {"bound": "hbm", "kernel": solve_kernel, "achieved": solve_gbs, "peak": hbm, "unit": "GB/s",
+                    "frac": (solve_gbs / hbm) if solve_gbs else None, "traffic": None,
+                    "peak_source": "hbm_gbs of MEASURED_PEAKS.json" if peaks.get("hbm_gbs") else "fallback 6650 GB/s",
+                    "algorithmic_bytes_per_matrix": per_mat, "mean_refinement_sweeps": mean_sweeps,
+                    "launches": int(solve_launches), "avg_launch_ms": solve_ms / max(1, solve_launches),
+                    "share_of_step": solve_ms / ms}
+        dominant = rl_solve if solve_ms > upd_ms else rl_update
+        other = rl_update if dominant is rl_solve else rl_solve
         line = {
             "metric": METRIC, "value": evals / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -360,12 +390,8 @@ def main():
                     "d2h_bytes_per_step": int(P * len(slots) * 8), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "tensor", "kernel": upd_kernel,
-                         "achieved": achieved, "peak": upd_peak, "unit": "TFLOP/s",
-                         "frac": (achieved / upd_peak) if achieved and upd_peak else None, "traffic": None,
-                         "peak_source": upd_peak_src,
-                         "launches": int(upd_launches), "avg_launch_ms": upd_ms / max(1, upd_launches),
-                         "share_of_step": upd_ms / ms},
+            "roofline": dominant,
+            "roofline_" + ("cholesky_update" if other is rl_update else "solve"): other,
             "roofline_gram": {"bound": "tensor", "kernel": "gram_tc_kernel (tcgen05 kind::i8)",
                               "achieved": gram_ops / (gram_ms * 1e-3) / 1e12 if gram_ms > 0 else None,
                               "peak": 2 * bf16, "unit": "TOP/s",
