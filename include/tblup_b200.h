@@ -108,6 +108,25 @@ int tb_set_stream(tb_ctx* ctx, void* cuda_stream);
 /* Peak probes for roofline denominators: which = 0 -> fp64 DMMA (mma.sync m8n8k4) TFLOP/s on this device. */
 int tb_microbench(tb_ctx* ctx, int which, double* out);
 
+/* ---- on-device differential evolution on random-key individuals (tblup/evolver.py:63-157 DE/rand/1 with binary
+ * crossover, tblup/individual.py:132-167 random-key decode, tblup/selector.py:18-34 greedy selection) ----------
+ * The P x m key matrix stays in HBM; a generation is evolve -> decode -> evaluate -> select without a host
+ * round-trip of genomes.
+ * tb_de_init: keys_host [P][m] (the reference's np.random.uniform(size=m) per individual) or NULL to draw them on
+ * the device from `seed`.  tb_de_evaluate: fitness of the current population (generation 0,
+ * tblup/population.py:47).  tb_de_step: one generation; abc [P][3] parent indices and fixed [P] forced crossover
+ * positions, mask [P][m] (1 = take the mutant) may be given by the host (replaying the reference's own draws) or
+ * be NULL (device draws from `seed`); F is the mutation intensity the caller chose for this generation
+ * (evolver.py:147-151), take_out [P] (nullable) receives which children replaced their parent.
+ * tb_de_get: what = 0 population fitness [P] f64, 1 last offspring fitness [P] f64, 2 population keys [P][m] f64,
+ * 3 last offspring keys, 4 decoded genome of individual `which` [length] i32 (ascending index order),
+ * 5 genomes of the last evaluated batch [P][length] i32. */
+int tb_de_init(tb_ctx* ctx, int P, int length, const double* keys_host, uint64_t seed);
+int tb_de_evaluate(tb_ctx* ctx, const int32_t* slots, int n_slots, double h2, int mode_rule);
+int tb_de_step(tb_ctx* ctx, const int32_t* slots, int n_slots, double h2, int mode_rule, double F, double CR, int clip,
+               const int32_t* abc, const int32_t* fixed, const uint8_t* mask, uint64_t seed, int32_t* take_out);
+int tb_de_get(tb_ctx* ctx, int what, int which, void* out, size_t nbytes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -31,6 +31,11 @@ SYMBOLS = {
     "tb_reset_counters": (C.c_int, [C.c_void_p]),
     "tb_last_wave": (C.c_int, [C.c_void_p]),
     "tb_last_precision": (C.c_int, [C.c_void_p]),
+    "tb_de_init": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_uint64]),
+    "tb_de_evaluate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int]),
+    "tb_de_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int,
+                             C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "tb_de_get": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "tb_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tb_microbench": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
 }

@@ -414,6 +414,11 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
 
 }  // namespace
 
+int tb_internal_eval_device(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_rule, double* d_fit) {
+  return eval_core(c, slots, n_slots, h2, mode_rule, d_fit);
+}
+void tb_internal_collect_spans(TbCtx* c) { spans_collect(c); }
+
 extern "C" {
 
 int tb_abi_version(void) { return TB_ABI_VERSION; }
@@ -537,6 +542,7 @@ int tb_destroy(tb_ctx* c) {
   cudaSetDevice(c->device);
   if (c->stream) cudaStreamSynchronize(c->stream);
   for (auto& r : c->slots) free_rowset(r);
+  tb_de_release(c);
   for (auto ev : c->ev_pool) cudaEventDestroy(ev);
   cudaFree(c->d_x);
   cudaFree(c->d_colsum_all);

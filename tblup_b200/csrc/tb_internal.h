@@ -88,6 +88,14 @@ struct TbCtx {
     float* L32 = nullptr; int* sweeps = nullptr; int ntp_all = 0;
     std::vector<int> ntp, n_v;
   } dbg;
+  // on-device differential evolution (de.cu)
+  struct DeState {
+    int P = 0, k = 0;
+    double *keys = nullptr, *child = nullptr, *fit = nullptr, *child_fit = nullptr, *raw_fit = nullptr;
+    size_t raw_cap = 0;
+    int *abc = nullptr, *fixed = nullptr, *take = nullptr;
+    unsigned char* mask = nullptr;
+  } de;
   double stage_ms[TB_ST_COUNT] = {};
   unsigned long long stage_launches[TB_ST_COUNT] = {};
   unsigned long long launches = 0;
@@ -203,3 +211,9 @@ cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, int* status, int n_jobs
 
 // microbench.cu
 cudaError_t tb_microbench_dmma(int n_sm, cudaStream_t st, double* tflops);
+
+// api.cu internals used by de.cu: evaluate the genomes already staged on the device (c->d_idx, c->h_off, c->P)
+// into a device buffer [P * n_slots] (asynchronous on c->stream), and fold the profiling spans after a sync.
+int tb_internal_eval_device(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_rule, double* d_fit);
+void tb_internal_collect_spans(TbCtx* c);
+void tb_de_release(TbCtx* c);

@@ -1,0 +1,90 @@
+"""On-device differential evolution (DE/rand/1, binary crossover) over random-key individuals.
+
+Host handle for the ``tb_de_*`` entry points: the P x m key matrix, the decoded genomes, the fitness vector and the
+greedy selection all stay on the GPU; per generation the host passes a handful of scalars (and, optionally, the
+random draws -- which is how the parity tests replay the reference's own Mersenne-Twister stream).
+Mirrors tblup/evolver.py:86-157 (DERandOneEvolver), tblup/individual.py:132-167 (RandomKeyIndividual) and
+tblup/selector.py:18-34 for the default configuration of the reference (``--de_strategy de_rand_1``).
+"""
+import ctypes as C
+
+import numpy as np
+
+from .engine import MODE_AUTO
+
+
+def mutation_intensity(generation, configured):
+    """F used in ``generation``: 5 on every fifth generation, else the configured value (tblup/evolver.py:147-151)."""
+    return 5.0 if generation % 5 == 0 else float(configured)
+
+
+class DeviceDE:
+    def __init__(self, engine, population_size, length, keys=None, seed=0):
+        self.eng = engine
+        self.P, self.k, self.m = int(population_size), int(length), engine.m
+        kp = None
+        if keys is not None:
+            keys = np.ascontiguousarray(np.asarray(keys, dtype=np.float64))
+            if keys.shape != (self.P, self.m):
+                raise ValueError("keys must have shape (population, markers)")
+            kp = keys.ctypes.data
+        engine._check(engine._lib.tb_de_init(engine._ctx, self.P, self.k, kp, int(seed)), "tb_de_init")
+        self.generation = 0
+
+    def evaluate(self, slots=(0,), h2=0.4, mode=MODE_AUTO):
+        """Fitness of the current population (generation 0, tblup/population.py:47)."""
+        s = np.ascontiguousarray(np.asarray(slots, dtype=np.int32))
+        self.eng._check(self.eng._lib.tb_de_evaluate(self.eng._ctx, s.ctypes.data, s.size, float(h2), int(mode)),
+                        "tb_de_evaluate")
+        return self.fitness()
+
+    def step(self, F, CR, slots=(0,), h2=0.4, mode=MODE_AUTO, clip=False, abc=None, fixed=None, mask=None, seed=0):
+        """One generation: evolve -> decode -> evaluate -> select.  Returns the boolean 'child replaced parent' vector."""
+        s = np.ascontiguousarray(np.asarray(slots, dtype=np.int32))
+        pa = pf = pm = None
+        if abc is not None:
+            abc = np.ascontiguousarray(np.asarray(abc, dtype=np.int32).reshape(self.P, 3))
+            fixed = np.ascontiguousarray(np.asarray(fixed, dtype=np.int32).reshape(self.P))
+            pa, pf = abc.ctypes.data, fixed.ctypes.data
+        if mask is not None:
+            mask = np.ascontiguousarray(np.asarray(mask).astype(np.uint8).reshape(self.P, self.m))
+            pm = mask.ctypes.data
+        take = np.zeros(self.P, dtype=np.int32)
+        self.eng._check(self.eng._lib.tb_de_step(self.eng._ctx, s.ctypes.data, s.size, float(h2), int(mode), float(F),
+                                                 float(CR), int(bool(clip)), pa, pf, pm, int(seed), take.ctypes.data),
+                        "tb_de_step")
+        self.generation += 1
+        return take.astype(bool)
+
+    def run(self, generations, mutation=0.5, CR=0.8, slots=(0,), h2=0.4, mode=MODE_AUTO, clip=False, seed=0):
+        """``generations`` device-driven generations with the reference's F schedule; returns best fitness per generation."""
+        best = []
+        for _ in range(generations):
+            gen = self.generation + 1
+            self.step(mutation_intensity(gen, mutation), CR, slots, h2, mode, clip, seed=seed * 1000003 + gen)
+            best.append(float(np.nanmax(self.fitness())))
+        return best
+
+    def _get(self, what, shape, dtype, which=0):
+        out = np.empty(shape, dtype=dtype)
+        self.eng._check(self.eng._lib.tb_de_get(self.eng._ctx, what, int(which), out.ctypes.data, out.nbytes), "tb_de_get")
+        return out
+
+    def fitness(self):
+        return self._get(0, (self.P,), np.float64)
+
+    def child_fitness(self):
+        return self._get(1, (self.P,), np.float64)
+
+    def keys(self):
+        return self._get(2, (self.P, self.m), np.float64)
+
+    def child_keys(self):
+        return self._get(3, (self.P, self.m), np.float64)
+
+    def genome(self, i):
+        """Decoded genome of individual ``i`` (the set of its ``length`` largest keys, ascending marker index)."""
+        return self._get(4, (self.k,), np.int32, which=i)
+
+    def last_genomes(self):
+        return self._get(5, (self.P, self.k), np.int32)
