@@ -370,7 +370,7 @@ def main():
             # per matrix: (1 + sweeps) preconditioner applications (factor read forwards and backwards), `sweeps`
             # symmetric mat-vecs on the integer cross-products (lower triangle read by rows and by columns), one
             # pass over the validation rows
-            per_mat = (1 + mean_sweeps) * 2 * tri_bytes + mean_sweeps * 2 * tri_bytes + n_v * n_t * 4
+            per_mat = (1 + mean_sweeps) * 2 * (tri_bytes / 2) + mean_sweeps * 2 * tri_bytes + n_v * n_t * 4   # fp16 factor
             solve_kernel = ("solve_mixed_kernel (blocked substitution with the TF32 factor + fp64 refinement on the "
                             "integer cross-products + predictions + Pearson)")
         else:

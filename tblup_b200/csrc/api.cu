@@ -150,7 +150,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
   if (mixed) {
     per_ind = 0;
     for (int s = 0; s < n_slots; ++s)
-      per_ind += (size_t)max_ntp * max_ntp * sizeof(float) + (size_t)max_ntp * TB_NB * sizeof(float) +
+      per_ind += (size_t)max_ntp * max_ntp * (sizeof(float) + 2) + (size_t)max_ntp * TB_NB * sizeof(float) +
                  (size_t)(max_ntp + sv[s].rs->n_v) * sizeof(double) + 1024;
   }
   const int P = c->P;
@@ -226,9 +226,11 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     int* d_sweeps = ar.take<int>(n_jobs);
     float* d_L32 = nullptr;
     float* d_Linv32 = nullptr;
+    unsigned short* d_L16 = nullptr;
     if (mixed) {
       d_L32 = ar.take<float>(((size_t)n_jobs * max_ntp + 128) * max_ntp);
       d_Linv32 = ar.take<float>((size_t)n_jobs * max_ntp * TB_NB);
+      d_L16 = ar.take<unsigned short>((size_t)n_jobs * max_ntp * max_ntp);
     }
 
     h_scale.resize(n_jobs);
@@ -294,6 +296,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
         oj.ntp = rs->ntp;
         TbSolveMixedJob& mj = h_msolve[job];
         mj.L32 = d_L32 ? d_L32 + (size_t)job * max_ntp * max_ntp : nullptr;
+        mj.L16 = d_L16 ? d_L16 + (size_t)job * max_ntp * max_ntp : nullptr;
         mj.Linv32 = d_Linv32 ? d_Linv32 + (size_t)job * max_ntp * TB_NB : nullptr;
         mj.C = sj.C;
         mj.s = sj.s;
@@ -364,7 +367,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
         int nl[2] = {0, 0};
         std::string e;
         MarkCtx mc{c, 0};
-        cudaError_t ce = tb_chol_tc_factor(d_L32, d_Linv32, d_status, n_jobs, max_ntp, c->n_sm, st, nl, &e,
+        cudaError_t ce = tb_chol_tc_factor(d_L32, d_Linv32, d_L16, d_status, n_jobs, max_ntp, c->n_sm, st, nl, &e,
                                            c->profile ? &mark_cb : nullptr, &mc);
         if (ce != cudaSuccess)
           return fail(c, "tensor-core Cholesky: " + (e.empty() ? std::string(cudaGetErrorString(ce)) : e), -2);

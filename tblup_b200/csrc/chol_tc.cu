@@ -21,6 +21,7 @@
 // double-buffered), warps 2-5 = epilogue (tcgen05.ld -> read-modify-write of the fp32 tile in global memory).
 #include "tb_internal.h"
 #include "tb_ptx.cuh"
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -54,6 +55,7 @@ struct GemmParams {
   int N;             // output columns: 64, 128, 192 or 256
   int mode;          // 0: C -= A B^T   1: C = A B^T rounded to TF32 (final L entries)
   float* L32;
+  __half* L16;       // optional half-precision copy of the final factor entries (read by the solve)
 };
 
 struct TBarriers {
@@ -202,10 +204,21 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               dst[i] = o;
             }
           } else {
+            float o[32];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
-              dst[i] = make_float4(round_tf32(__uint_as_float(v[4 * i])), round_tf32(__uint_as_float(v[4 * i + 1])),
-                                   round_tf32(__uint_as_float(v[4 * i + 2])), round_tf32(__uint_as_float(v[4 * i + 3])));
+            for (int i = 0; i < 32; ++i) o[i] = round_tf32(__uint_as_float(v[i]));
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            if (p.L16) {
+              uint4* h = reinterpret_cast<uint4*>(p.L16 + ((size_t)job * p.ntp + r) * p.ntp + p.c_col0 + c * 32);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const __half2 h0 = __floats2half2_rn(o[8 * i], o[8 * i + 1]), h1 = __floats2half2_rn(o[8 * i + 2], o[8 * i + 3]);
+                const __half2 h2 = __floats2half2_rn(o[8 * i + 4], o[8 * i + 5]), h3 = __floats2half2_rn(o[8 * i + 6], o[8 * i + 7]);
+                h[i] = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                                  *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+              }
+            }
           }
         }
       }
@@ -231,7 +244,8 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 // fp32 storage.  The factor is rounded to TF32 on the way out so that the tensor-core operand truncation is a
 // no-op and the triangular solves in solve.cu use exactly the operator the factorisation built.
 __global__ void __launch_bounds__(256) chol_diag32_kernel(float* __restrict__ L32, float* __restrict__ Linv32,
-                                                          int* __restrict__ status, int ntp, int jb) {
+                                                          __half* __restrict__ L16, int* __restrict__ status, int ntp,
+                                                          int jb) {
   extern __shared__ double dsm[];
   double (*Ls)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dsm);
   double (*Xs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dsm + NB * (NB + 1));
@@ -295,6 +309,7 @@ __global__ void __launch_bounds__(256) chol_diag32_kernel(float* __restrict__ L3
   for (int e = tid; e < NB * NB; e += 256) {
     const int rr = e >> 6, c = e & 63;
     D[(size_t)rr * ntp + c] = (float)Ls[rr][c];
+    if (L16) L16[((size_t)job * ntp + (size_t)jb * NB + rr) * ntp + jb * NB + c] = __float2half_rn((float)Ls[rr][c]);
     Li[e] = round_tf32((float)Xs[rr][c]);
   }
   if (tid == 0 && bad) status[job] = 1;
@@ -338,8 +353,10 @@ cudaError_t tb_chol_tc_init() {
 }
 
 // Factor every job's fp32 matrix in place.  L32: [n_jobs * ntp + 128 slack rows][ntp]; Linv32: [n_jobs * ntp][64].
+// L16 (optional): [n_jobs * ntp][ntp] halves, receives a half-precision copy of the factor.
 // launches[0] / launches[1] receive the number of GEMM / diagonal-block kernel launches.
-cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, int* status, int n_jobs, int ntp, int n_sm, cudaStream_t st,
+cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, int* status, int n_jobs, int ntp, int n_sm,
+                              cudaStream_t st,
                               int* launches, std::string* err,
                               void (*mark)(void*, int, int), void* mark_ctx) {
   CUtensorMap tm_l, tm_inv;
@@ -351,6 +368,7 @@ cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, int* status, int n_jobs
     p.n_jobs = n_jobs;
     p.ntp = ntp;
     p.L32 = L32;
+    p.L16 = static_cast<__half*>(L16);
     p.n_mtiles = (ntp - p.row0 + TBM - 1) / TBM;
     if (p.n_mtiles <= 0 || p.K <= 0) return cudaSuccess;
     const int items = n_jobs * p.n_mtiles;
@@ -378,7 +396,7 @@ cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, int* status, int n_jobs
         p.N = NB; p.mode = 0;
         if ((e = gemm(tm_l, p)) != cudaSuccess) return e;
       }
-      chol_diag32_kernel<<<n_jobs, 256, DIAG32_SMEM, st>>>(L32, Linv32, status, ntp, cc / NB);
+      chol_diag32_kernel<<<n_jobs, 256, DIAG32_SMEM, st>>>(L32, Linv32, static_cast<__half*>(L16), status, ntp, cc / NB);
       launches[1]++;
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
       if (cc + NB < ntp) {

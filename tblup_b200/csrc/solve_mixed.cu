@@ -12,6 +12,7 @@
 // Same reference lines as solve.cu (tblup/evaluator.py:282-286, :311-314).  One CTA per (individual, row set);
 // HBM-bound: per sweep the factor is streamed twice (fp32) and the lower triangle of C twice (int32).
 #include "tb_internal.h"
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -57,9 +58,21 @@ __device__ __forceinline__ double dot4i(const int4 c, const double* z) {
   return (double)c.x * z0.x + (double)c.y * z0.y + (double)c.z * z1.x + (double)c.w * z1.y;
 }
 
-// work <- (L L^T)^-1 work, in place.  All global loads are 16 bytes with four independent loads in flight per
-// thread (the kernel is bound by how many bytes one CTA keeps in flight, not by arithmetic).
-__device__ void apply_minv(const float* __restrict__ L, const float* __restrict__ Linv, int ntp, double* work,
+__device__ __forceinline__ double dot8h(const uint4 l, const double* z) {
+  const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&l.x));
+  const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
+  const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&l.z));
+  const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&l.w));
+  const double2 z0 = *reinterpret_cast<const double2*>(z), z1 = *reinterpret_cast<const double2*>(z + 2);
+  const double2 z2 = *reinterpret_cast<const double2*>(z + 4), z3 = *reinterpret_cast<const double2*>(z + 6);
+  return ((double)f0.x * z0.x + (double)f0.y * z0.y) + ((double)f1.x * z1.x + (double)f1.y * z1.y) +
+         ((double)f2.x * z2.x + (double)f2.y * z2.y) + ((double)f3.x * z3.x + (double)f3.y * z3.y);
+}
+
+// work <- (L L^T)^-1 work, in place.  L is the fp16 copy of the TF32 factor (identical 10-bit mantissa, half the
+// bytes of fp32).  All global loads are 16 bytes with four independent loads in flight per thread (the kernel is
+// bound by how many bytes one CTA keeps in flight, not by arithmetic); accumulation in fp64.
+__device__ void apply_minv(const __half* __restrict__ L, const float* __restrict__ Linv, int ntp, double* work,
                            double* rvec, double* part) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nb = ntp / NB;
@@ -67,16 +80,16 @@ __device__ void apply_minv(const float* __restrict__ L, const float* __restrict_
     const int kc = b * NB;
     {
       // each warp owns rows kc + 4 warp .. + 3 and streams them together (z is read from smem once for all four)
-      const float4* r0 = reinterpret_cast<const float4*>(L + (size_t)(kc + 4 * warp) * ntp);
-      const size_t rs = ntp / 4;
+      const uint4* r0 = reinterpret_cast<const uint4*>(L + (size_t)(kc + 4 * warp) * ntp);
+      const size_t rs = ntp / 8;
       double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      for (int c = lane; c < kc / 4; c += 32) {
-        const float4 l0 = r0[c], l1 = r0[rs + c], l2 = r0[2 * rs + c], l3 = r0[3 * rs + c];
-        const double* z = work + 4 * c;
-        s0 += dot4(l0, z);
-        s1 += dot4(l1, z);
-        s2 += dot4(l2, z);
-        s3 += dot4(l3, z);
+      for (int c = lane; c < kc / 8; c += 32) {
+        const uint4 l0 = r0[c], l1 = r0[rs + c], l2 = r0[2 * rs + c], l3 = r0[3 * rs + c];
+        const double* z = work + 8 * c;
+        s0 += dot8h(l0, z);
+        s1 += dot8h(l1, z);
+        s2 += dot8h(l2, z);
+        s3 += dot8h(l3, z);
       }
       s0 = warp_sum(s0);
       s1 = warp_sum(s1);
@@ -105,41 +118,48 @@ __device__ void apply_minv(const float* __restrict__ L, const float* __restrict_
   for (int b = nb - 1; b >= 0; --b) {                 // backward: L^T d = z
     const int kc = b * NB;
     {
-      // thread = 4 consecutive columns (one float4) x one of 32 row groups
-      const int cq = tid & 15, rg = tid >> 4;
-      double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-      const float* base = L + kc + 4 * cq;
+      // thread = 8 consecutive columns (one 16-byte load) x one of 64 row groups
+      const int cq = tid & 7, rg = tid >> 3;
+      double a[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] = 0.0;
+      const __half* base = L + kc + 8 * cq;
+      auto acc8 = [&](const uint4 l, const double w) {
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&l.x));
+        const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
+        const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&l.z));
+        const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&l.w));
+        a[0] += (double)f0.x * w;
+        a[1] += (double)f0.y * w;
+        a[2] += (double)f1.x * w;
+        a[3] += (double)f1.y * w;
+        a[4] += (double)f2.x * w;
+        a[5] += (double)f2.y * w;
+        a[6] += (double)f3.x * w;
+        a[7] += (double)f3.y * w;
+      };
       int i = kc + NB + rg;
-      for (; i + 96 < ntp; i += 128) {
-        const float4 l0 = *reinterpret_cast<const float4*>(base + (size_t)i * ntp);
-        const float4 l1 = *reinterpret_cast<const float4*>(base + (size_t)(i + 32) * ntp);
-        const float4 l2 = *reinterpret_cast<const float4*>(base + (size_t)(i + 64) * ntp);
-        const float4 l3 = *reinterpret_cast<const float4*>(base + (size_t)(i + 96) * ntp);
-        const double w0 = work[i], w1 = work[i + 32], w2 = work[i + 64], w3 = work[i + 96];
-        a0 += (double)l0.x * w0 + (double)l1.x * w1 + (double)l2.x * w2 + (double)l3.x * w3;
-        a1 += (double)l0.y * w0 + (double)l1.y * w1 + (double)l2.y * w2 + (double)l3.y * w3;
-        a2 += (double)l0.z * w0 + (double)l1.z * w1 + (double)l2.z * w2 + (double)l3.z * w3;
-        a3 += (double)l0.w * w0 + (double)l1.w * w1 + (double)l2.w * w2 + (double)l3.w * w3;
+      for (; i + 192 < ntp; i += 256) {
+        const uint4 l0 = *reinterpret_cast<const uint4*>(base + (size_t)i * ntp);
+        const uint4 l1 = *reinterpret_cast<const uint4*>(base + (size_t)(i + 64) * ntp);
+        const uint4 l2 = *reinterpret_cast<const uint4*>(base + (size_t)(i + 128) * ntp);
+        const uint4 l3 = *reinterpret_cast<const uint4*>(base + (size_t)(i + 192) * ntp);
+        acc8(l0, work[i]);
+        acc8(l1, work[i + 64]);
+        acc8(l2, work[i + 128]);
+        acc8(l3, work[i + 192]);
       }
-      for (; i < ntp; i += 32) {
-        const float4 l0 = *reinterpret_cast<const float4*>(base + (size_t)i * ntp);
-        const double w0 = work[i];
-        a0 += (double)l0.x * w0;
-        a1 += (double)l0.y * w0;
-        a2 += (double)l0.z * w0;
-        a3 += (double)l0.w * w0;
+      for (; i < ntp; i += 64) acc8(*reinterpret_cast<const uint4*>(base + (size_t)i * ntp), work[i]);
+      // the four row groups of a warp (lanes differing in bits 3, 4) are combined by shuffle, one smem row per warp
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        a[e] += __shfl_xor_sync(0xffffffffu, a[e], 8);
+        a[e] += __shfl_xor_sync(0xffffffffu, a[e], 16);
       }
-      // the two row groups of a warp (lanes l and l ^ 16) are combined by shuffle, then one smem row per warp
-      a0 += __shfl_xor_sync(0xffffffffu, a0, 16);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, 16);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, 16);
-      a3 += __shfl_xor_sync(0xffffffffu, a3, 16);
-      if (lane < 16) {
-        double* pr = part + warp * NB + 4 * cq;
-        pr[0] = a0;
-        pr[1] = a1;
-        pr[2] = a2;
-        pr[3] = a3;
+      if (lane < 8) {
+        double* pr = part + warp * NB + 8 * cq;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) pr[e] = a[e];
       }
     }
     __syncthreads();
@@ -320,7 +340,7 @@ __global__ void __launch_bounds__(ST) solve_mixed_kernel(const TbSolveMixedJob* 
     work[a] = jb.y_t[a];
   }
   __syncthreads();
-  apply_minv(jb.L32, jb.Linv32, ntp, work, rvec, part);
+  apply_minv(static_cast<const __half*>(jb.L16), jb.Linv32, ntp, work, rvec, part);
   for (int a = tid; a < ntp; a += ST) alpha[a] = work[a];
   __syncthreads();
 
@@ -346,7 +366,7 @@ __global__ void __launch_bounds__(ST) solve_mixed_kernel(const TbSolveMixedJob* 
       work[a] = rr;
     }
     __syncthreads();
-    apply_minv(jb.L32, jb.Linv32, ntp, work, rvec, part);
+    apply_minv(static_cast<const __half*>(jb.L16), jb.Linv32, ntp, work, rvec, part);
     double dmax = 0.0, amax = 0.0;
     for (int a = tid; a < ntp; a += ST) {
       const double d = work[a];
@@ -454,7 +474,7 @@ __global__ void __launch_bounds__(256) scale32_kernel(const TbScaleJob* __restri
   const int c = c0 + (threadIdx.x & 31) * 4;
   if (c >= ntp) return;
   const long long N = jb.N, S = jb.SQ[0], Q = jb.SQ[1];
-  const double den = (double)(2 * N * S - Q);
+  const double inv_den2 = 2.0 / (double)(2 * N * S - Q);
   int pc[4];
   long long sc[4];
   bool creal[4];
@@ -493,8 +513,10 @@ __global__ void __launch_bounds__(256) scale32_kernel(const TbScaleJob* __restri
       for (int i = 0; i < 4; ++i) {
         double g = 0.0;
         if (creal[i]) {
+          // fp32 output: one exact int64 numerator, one fp64 multiply by 2/den (no fp64 division needed here --
+          // the result is rounded to fp32 anyway; the exact operator lives in solve_mixed_kernel)
           const long long num = N * N * (long long)cv[i] - N * (sr + sc[i]) + Q;
-          g = 2.0 * (double)num / den;
+          g = (double)num * inv_den2;
           if (r == c + i) g += jb.lambda;
         }
         out[i] = (float)g;

@@ -183,6 +183,7 @@ cudaError_t tb_launch_solve(const TbSolveJob* d_jobs, int n_jobs, int max_ntp, c
 // solve_mixed.cu / chol_tc.cu (mixed-precision path)
 struct TbSolveMixedJob {
   const float* L32;        // [ntp][ntp] TF32 Cholesky factor (lower)
+  const void* L16;         // [ntp][ntp] the same factor in fp16 (same 10-bit mantissa): what the solve streams
   const float* Linv32;     // [ntp][64] inverses of its diagonal blocks
   const int32_t* C;        // [rpad][rpad] integer cross-products
   const long long* s;      // [rpad]
@@ -206,7 +207,8 @@ cudaError_t tb_launch_solve_mixed(const TbSolveMixedJob* d_jobs, int n_jobs, int
                                   cudaStream_t st);
 cudaError_t tb_launch_scale32(const TbScaleJob* d_jobs, int n_jobs, int ntp, float* L32, cudaStream_t st);
 cudaError_t tb_chol_tc_init();
-cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, int* status, int n_jobs, int ntp, int n_sm, cudaStream_t st,
+cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, int* status, int n_jobs, int ntp, int n_sm,
+                              cudaStream_t st,
                               int* launches, std::string* err, void (*mark)(void*, int, int), void* mark_ctx);
 
 // microbench.cu
