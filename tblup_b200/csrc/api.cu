@@ -253,21 +253,31 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     c->dbg.pred.assign(n_jobs, nullptr);
     c->dbg.ntp.assign(n_jobs, 0);
     c->dbg.n_v.assign(n_jobs, 0);
+    // the centring terms depend on the row set only through the frequency animals: when every genome of the wave
+    // takes the gblup branch (all-animal frequencies) one set of terms per genome serves all its row sets
+    bool wave_all_gblup = true;
+    for (int w = 0; w < Wc; ++w) {
+      const int k = (int)(c->h_off[w0 + w + 1] - c->h_off[w0 + w]);
+      wave_all_gblup = wave_all_gblup && (mode_rule == TB_MODE_GBLUP || (mode_rule == TB_MODE_AUTO && k > c->n));
+    }
+    const int centre_slots = wave_all_gblup ? 1 : n_slots;
+    c->dbg.centre_shared = wave_all_gblup ? 1 : 0;
     for (int w = 0; w < Wc; ++w) {
       const int k = (int)(c->h_off[w0 + w + 1] - c->h_off[w0 + w]);
       const bool gblup = mode_rule == TB_MODE_GBLUP || (mode_rule == TB_MODE_AUTO && k > c->n);
       for (int s = 0; s < n_slots; ++s) {
         const int job = w * n_slots + s;
+        const int cjob = wave_all_gblup ? w : job;      // index of this job's centring terms
         const TbRowSet* rs = sv[s].rs;
         double* Mj = mixed ? nullptr : ar.take<double>(sv[s].m_elems);
         double* Lj = mixed ? nullptr : ar.take<double>(sv[s].linv_elems);
         double* aj = ar.take<double>(rs->ntp);
         double* pj = ar.take<double>(rs->n_v);
-        h_cs[job] = gblup ? c->d_colsum_all : rs->d_colsum_train;
+        h_cs[cjob] = gblup ? c->d_colsum_all : rs->d_colsum_train;
         TbScaleJob& sj = h_scale[job];
         sj.C = d_C + (size_t)w * rpad * rpad;
-        sj.s = d_s + (size_t)job * rpad;
-        sj.SQ = d_SQ + (size_t)job * 2;
+        sj.s = d_s + (size_t)cjob * rpad;
+        sj.SQ = d_SQ + (size_t)cjob * 2;
         sj.tpos = rs->d_tpos;
         sj.vpos = rs->d_vpos;
         sj.M = Mj;
@@ -342,7 +352,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     if (c->stop_after == TB_ST_GATHER) continue;
 
     sp = span_begin(c, TB_ST_CENTRE);
-    TB_CUDA(c, tb_launch_centre_terms(d_panel, rpad, kstride, c->d_idx, d_off, w0, Wc, n_slots, d_kb, d_cs, d_csg, d_s, d_SQ, st));
+    TB_CUDA(c, tb_launch_centre_terms(d_panel, rpad, kstride, c->d_idx, d_off, w0, Wc, centre_slots, d_kb, d_cs, d_csg, d_s, d_SQ, st));
     span_end(c, sp);
     count(c, TB_ST_CENTRE, 2);
     if (c->stop_after == TB_ST_CENTRE) continue;
@@ -746,8 +756,8 @@ int tb_debug_fetch(tb_ctx* c, int what, int job, void* out, size_t nbytes) {
   int dims[4] = {d.rpad, d.ntp[job], d.n_v[job], d.kstride};
   switch (what) {
     case TB_DBG_C: src = d.C + (size_t)(job / d.n_slots) * d.rpad * d.rpad; need = (size_t)d.rpad * d.rpad * 4; break;
-    case TB_DBG_S: src = d.s + (size_t)job * d.rpad; need = (size_t)d.rpad * 8; break;
-    case TB_DBG_SQ: src = d.SQ + (size_t)job * 2; need = 16; break;
+    case TB_DBG_S: src = d.s + (size_t)(d.centre_shared ? job / d.n_slots : job) * d.rpad; need = (size_t)d.rpad * 8; break;
+    case TB_DBG_SQ: src = d.SQ + (size_t)(d.centre_shared ? job / d.n_slots : job) * 2; need = 16; break;
     case 7:
       if (!d.L32) return fail(c, "tb_debug_fetch: no fp32 factor (fp64 precision mode)");
       src = d.L32 + (size_t)job * d.ntp_all * d.ntp_all; need = (size_t)d.ntp_all * d.ntp_all * 4; break;

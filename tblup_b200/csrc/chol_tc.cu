@@ -240,28 +240,29 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
-// Diagonal block of the fp32 matrix: same register-resident potrf + inverse as chol_diag_kernel (fp64 math),
-// fp32 storage.  The factor is rounded to TF32 on the way out so that the tensor-core operand truncation is a
-// no-op and the triangular solves in solve.cu use exactly the operator the factorisation built.
+// Diagonal block of the fp32 matrix: register-resident potrf + inverse (same scheme as chol_diag_kernel) in fp32
+// arithmetic -- the factor is rounded to TF32 (10 mantissa bits) on the way out, so fp32 (24 bits) math is ample,
+// and it halves the shared memory (more CTAs per SM) and avoids the long-latency fp64 sqrt/divide.  The rounded
+// factor is the one that gets inverted and stored, so the tensor-core operand truncation is a no-op and the
+// triangular solves in solve_mixed.cu use exactly the operator the factorisation built.
 __global__ void __launch_bounds__(256) chol_diag32_kernel(float* __restrict__ L32, float* __restrict__ Linv32,
                                                           __half* __restrict__ L16, int* __restrict__ status, int ntp,
                                                           int jb) {
-  extern __shared__ double dsm[];
-  double (*Ls)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dsm);
-  double (*Xs)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dsm + NB * (NB + 1));
-  __shared__ double colbuf[2][NB];
-  __shared__ double part[4][NB];
+  __shared__ float Ls[NB][NB + 1];
+  __shared__ float Xs[NB][NB + 1];
+  __shared__ float colbuf[2][NB];
+  __shared__ float part[4][NB];
   __shared__ int bad;
   const int job = blockIdx.x;
   float* D = L32 + ((size_t)job * ntp + (size_t)jb * NB) * ntp + jb * NB;
   const int tid = threadIdx.x;
   const int r = tid >> 2, q = tid & 3;
   if (tid == 0) bad = 0;
-  double a[16];
+  float a[16];
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int c = q + 4 * i;
-    a[i] = c <= r ? (double)D[(size_t)r * ntp + c] : 0.0;
+    a[i] = c <= r ? D[(size_t)r * ntp + c] : 0.f;
   }
   __syncthreads();
 #pragma unroll
@@ -269,38 +270,38 @@ __global__ void __launch_bounds__(256) chol_diag32_kernel(float* __restrict__ L3
     const int qc = c & 3, ic = c >> 2;
     if (q == qc && r >= c) colbuf[c & 1][r] = a[ic];
     __syncthreads();
-    const double d = colbuf[c & 1][c];
-    if (!(d > 0.0) && tid == 0) bad = 1;
-    const double inv = 1.0 / sqrt(d);
+    const float d = colbuf[c & 1][c];
+    if (!(d > 0.f) && tid == 0) bad = 1;
+    const float inv = rsqrtf(d);
     if (r >= c) {
-      const double lr = colbuf[c & 1][r] * inv;
+      const float lr = colbuf[c & 1][r] * inv;
       if (q == qc) a[ic] = lr;
 #pragma unroll
       for (int i = 0; i < 16; ++i) {
         const int cc = q + 4 * i;
-        if (cc > c && cc <= r) a[i] -= lr * (colbuf[c & 1][cc] * inv);
+        if (cc > c && cc <= r) a[i] = fmaf(-lr, colbuf[c & 1][cc] * inv, a[i]);
       }
     }
   }
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
     const int c = q + 4 * i;
-    Ls[r][c] = c <= r ? (double)round_tf32((float)a[i]) : 0.0;   // the stored (rounded) factor is what gets inverted
-    Xs[r][c] = 0.0;
+    Ls[r][c] = c <= r ? round_tf32(a[i]) : 0.f;
+    Xs[r][c] = 0.f;
   }
   __syncthreads();
   {
     const int c = tid & 63, h = tid >> 6;
     for (int rr = 0; rr < NB; ++rr) {
-      double sacc = 0.0;
+      float sacc = 0.f;
       if (c <= rr) {
-        for (int pp = c + h; pp < rr; pp += 4) sacc += Ls[rr][pp] * Xs[pp][c];
+        for (int pp = c + h; pp < rr; pp += 4) sacc = fmaf(Ls[rr][pp], Xs[pp][c], sacc);
       }
       part[h][c] = sacc;
       __syncthreads();
       if (h == 0 && c <= rr) {
-        const double tot = (part[0][c] + part[1][c]) + (part[2][c] + part[3][c]);
-        Xs[rr][c] = ((c == rr ? 1.0 : 0.0) - tot) / Ls[rr][rr];
+        const float tot = (part[0][c] + part[1][c]) + (part[2][c] + part[3][c]);
+        Xs[rr][c] = ((c == rr ? 1.f : 0.f) - tot) / Ls[rr][rr];
       }
       __syncthreads();
     }
@@ -308,9 +309,9 @@ __global__ void __launch_bounds__(256) chol_diag32_kernel(float* __restrict__ L3
   float* Li = Linv32 + ((size_t)job * ntp + (size_t)jb * NB) * NB;
   for (int e = tid; e < NB * NB; e += 256) {
     const int rr = e >> 6, c = e & 63;
-    D[(size_t)rr * ntp + c] = (float)Ls[rr][c];
-    if (L16) L16[((size_t)job * ntp + (size_t)jb * NB + rr) * ntp + jb * NB + c] = __float2half_rn((float)Ls[rr][c]);
-    Li[e] = round_tf32((float)Xs[rr][c]);
+    D[(size_t)rr * ntp + c] = Ls[rr][c];
+    if (L16) L16[((size_t)job * ntp + (size_t)jb * NB + rr) * ntp + jb * NB + c] = __float2half_rn(Ls[rr][c]);
+    Li[e] = round_tf32(Xs[rr][c]);
   }
   if (tid == 0 && bad) status[job] = 1;
 }
@@ -319,7 +320,7 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode32 = nullptr;
-constexpr int DIAG32_SMEM = 2 * NB * (NB + 1) * (int)sizeof(double);
+constexpr int DIAG32_SMEM = 0;
 
 cudaError_t encode_f32(CUtensorMap* tm, const float* base, size_t cols, size_t rows, std::string* err) {
   const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -347,8 +348,6 @@ cudaError_t tb_chol_tc_init() {
     if (!fn || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
     g_encode32 = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  cudaError_t e = cudaFuncSetAttribute(chol_diag32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DIAG32_SMEM);
-  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(tf32_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
 }
 

@@ -82,7 +82,7 @@ struct TbCtx {
   int n_sm = 148;
   // layout of the last wave (for tb_debug_fetch)
   struct DbgLayout {
-    int W = 0, n_slots = 0, rpad = 0, kstride = 0;
+    int W = 0, n_slots = 0, rpad = 0, kstride = 0, centre_shared = 0;
     int32_t* C = nullptr; long long* s = nullptr; long long* SQ = nullptr;
     std::vector<double*> M, alpha, pred;
     float* L32 = nullptr; int* sweeps = nullptr; int ntp_all = 0;
