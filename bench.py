@@ -28,6 +28,8 @@ WORKLOADS = {
     "c2_5000x50000_k5001_pop1000": dict(n=5000, m=50000, k=5001, pop=1000, folds=1),
     "c1_1000x10000_k1500_pop50": dict(n=1000, m=10000, k=1500, pop=50, folds=1),
     "c3_5000x50000_k5001_pop1000_10fold": dict(n=5000, m=50000, k=5001, pop=1000, folds=10),
+    # config 4 (large-n regime): full shape, population cut to what one short step needs; no CPU arm (minutes/genome)
+    "c4_20000x500000_k50000_pop32": dict(n=20000, m=500000, k=50000, pop=32, folds=1, fast_synth=True, no_cpu=True),
     "tiny": dict(n=300, m=2000, k=400, pop=16, folds=1),
 }
 DEFAULT_WORKLOAD = "c2_5000x50000_k5001_pop1000"
@@ -212,7 +214,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    x, y = synth.synth_dataset(n, m, h2=H2, seed=0)
+    x, y = (synth.synth_dataset_fast if wl.get("fast_synth") else synth.synth_dataset)(n, m, h2=H2, seed=0)
     train, valid, test = synth.split_indices(n, seed=0)
     slots = [0]
     eng = GblupEngine(x, y, perm=np.concatenate([train, valid, test]), device=local_rank)
@@ -314,7 +316,7 @@ def main():
         ms, ms_e2e = float(t[0]), float(t[1])
 
     cpu_baseline = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not wl.get("no_cpu"):
         sample = args.cpu_sample or cores
         arm = CpuArm(x, y, train, valid, cores)
         try:

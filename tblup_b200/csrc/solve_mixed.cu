@@ -19,6 +19,7 @@ namespace {
 constexpr int NB = TB_NB;
 constexpr int ST = 512;
 constexpr int MAX_SWEEPS = 6;
+constexpr int MIXED_SMEM_NTP = 4096;  // up to this many (padded) training animals alpha stays in shared memory
 constexpr double REL_TOL = 1e-8;     // stop when the PREDICTED remaining error is below 1e-8 of the solution
                                      // (fitness bar of BASELINE.json: 1e-6 absolute)
 
@@ -323,20 +324,24 @@ __global__ void __launch_bounds__(ST) solve_mixed_kernel(const TbSolveMixedJob* 
   extern __shared__ double msm[];
   const TbSolveMixedJob jb = jobs[blockIdx.x];
   const int ntp = jb.ntp, n_t = jb.n_t, n_v = jb.n_v, rpad = jb.rpad;
-  double* alpha = msm;               // [ntp]
-  double* work = alpha + ntp;        // [ntp]
+  // small matrices keep alpha and the position table in shared memory; beyond MIXED_SMEM_NTP rows alpha lives in
+  // the job's global output vector and the positions are read from the row set (both stay L1/L2 resident)
+  const bool big = ntp > MIXED_SMEM_NTP;
+  double* work = msm;                // [ntp]
   double* rvec = work + ntp;         // [NB]
   double* part = rvec + NB;          // [ST/32][NB]
   double* part2 = part + (ST / 32) * NB;   // [4][512]
   double* red = part2 + 4 * 512;     // [ST/32]
-  int* tp = reinterpret_cast<int*>(red + ST / 32);   // [ntp]
+  double* alpha = big ? jb.alpha : red + ST / 32;                                              // [ntp]
+  const int* tp = big ? jb.tpos : reinterpret_cast<const int*>(red + ST / 32 + ntp);          // [n_t]
+  int* tp_w = big ? nullptr : reinterpret_cast<int*>(red + ST / 32 + ntp);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const double Nd = (double)jb.N, Sd = (double)jb.SQ[0], Qd = (double)jb.SQ[1];
   const double coef = 2.0 / (2.0 * Nd * Sd - Qd);
   const int32_t* C = jb.C;
 
   for (int a = tid; a < ntp; a += ST) {
-    tp[a] = a < n_t ? jb.tpos[a] : 0;
+    if (tp_w) tp_w[a] = a < n_t ? jb.tpos[a] : 0;
     work[a] = jb.y_t[a];
   }
   __syncthreads();
@@ -396,7 +401,8 @@ __global__ void __launch_bounds__(ST) solve_mixed_kernel(const TbSolveMixedJob* 
       break;
     }
   }
-  for (int a = tid; a < ntp; a += ST) jb.alpha[a] = alpha[a];
+  if (!big)
+    for (int a = tid; a < ntp; a += ST) jb.alpha[a] = alpha[a];
   if (tid == 0 && jb.sweeps) *jb.sweeps = sweeps;
 
   // ---- predictions on the validation animals
@@ -531,7 +537,8 @@ int g_solve_mixed_smem_max = 0;
 }  // namespace
 
 static inline int solve_mixed_smem_bytes(int ntp) {
-  return (2 * ntp + NB + (ST / 32) * NB + 4 * 512 + ST / 32) * (int)sizeof(double) + ntp * (int)sizeof(int);
+  const int fixed = (ntp + NB + (ST / 32) * NB + 4 * 512 + ST / 32) * (int)sizeof(double);
+  return ntp > MIXED_SMEM_NTP ? fixed : fixed + ntp * (int)(sizeof(double) + sizeof(int));
 }
 
 cudaError_t tb_solve_mixed_init() {
