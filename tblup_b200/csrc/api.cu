@@ -70,19 +70,27 @@ inline void count(TbCtx* c, int stage, int n) {
   c->launches += n;
 }
 
-// all tiles (128 x 256) that intersect the lower triangle of [0, rpad)^2 and touch a training row or column
+// all tiles (128 x 256) that intersect the lower triangle of [0, rpad)^2 and touch a training row or column.
+// Order matters for L2 reuse when one genome's panel is larger than L2 (config 4: 800 MB): the persistent CTAs
+// take consecutive list entries, so the list walks super-blocks of 12 x 6 tiles (1 536 x 1 536 entries): the ~148
+// tiles in flight then share 12 A row-blocks and 6 B row-blocks instead of streaming one long tile row.
 void build_tiles(int rpad, const std::vector<unsigned char>& has_train, std::vector<int>& tiles) {
   tiles.clear();
   const int nI = rpad / TB_GRAM_BM, nJ = (rpad + TB_GRAM_BN - 1) / TB_GRAM_BN;
-  for (int I = 0; I < nI; ++I) {
-    for (int J = 0; J < nJ; ++J) {
-      if (J * TB_GRAM_BN > I * TB_GRAM_BM + TB_GRAM_BM - 1) continue;
-      bool need = has_train.empty() || has_train[I];
-      for (int h = 0; h < 2 && !need; ++h) {
-        int blk = 2 * J + h;
-        if (blk < nI && has_train[blk]) need = true;
+  const int SBI = 12, SBJ = 6;
+  for (int I0 = 0; I0 < nI; I0 += SBI) {
+    for (int J0 = 0; J0 < nJ; J0 += SBJ) {
+      for (int I = I0; I < std::min(nI, I0 + SBI); ++I) {
+        for (int J = J0; J < std::min(nJ, J0 + SBJ); ++J) {
+          if (J * TB_GRAM_BN > I * TB_GRAM_BM + TB_GRAM_BM - 1) continue;
+          bool need = has_train.empty() || has_train[I];
+          for (int h = 0; h < 2 && !need; ++h) {
+            int blk = 2 * J + h;
+            if (blk < nI && has_train[blk]) need = true;
+          }
+          if (need) tiles.push_back((I << 16) | J);
+        }
       }
-      if (need) tiles.push_back((I << 16) | J);
     }
   }
 }
