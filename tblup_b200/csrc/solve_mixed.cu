@@ -319,22 +319,31 @@ __device__ void sym_matvec(const int32_t* __restrict__ C, int rpad, int n_t, con
   }
 }
 
-template <bool CONTIG>
+template <bool CONTIG, bool BIG>
 __global__ void __launch_bounds__(ST) solve_mixed_kernel(const TbSolveMixedJob* __restrict__ jobs) {
   extern __shared__ double msm[];
   const TbSolveMixedJob jb = jobs[blockIdx.x];
   const int ntp = jb.ntp, n_t = jb.n_t, n_v = jb.n_v, rpad = jb.rpad;
   // small matrices keep alpha and the position table in shared memory; beyond MIXED_SMEM_NTP rows alpha lives in
   // the job's global output vector and the positions are read from the row set (both stay L1/L2 resident)
-  const bool big = ntp > MIXED_SMEM_NTP;
+  // (BIG is a template parameter so that each instantiation knows the address space of alpha / tp statically)
+  constexpr bool big = BIG;
   double* work = msm;                // [ntp]
   double* rvec = work + ntp;         // [NB]
   double* part = rvec + NB;          // [ST/32][NB]
   double* part2 = part + (ST / 32) * NB;   // [4][512]
   double* red = part2 + 4 * 512;     // [ST/32]
-  double* alpha = big ? jb.alpha : red + ST / 32;                                              // [ntp]
-  const int* tp = big ? jb.tpos : reinterpret_cast<const int*>(red + ST / 32 + ntp);          // [n_t]
-  int* tp_w = big ? nullptr : reinterpret_cast<int*>(red + ST / 32 + ntp);
+  double* alpha;                     // [ntp]
+  const int* tp;                     // [n_t]
+  int* tp_w = nullptr;
+  if constexpr (BIG) {
+    alpha = jb.alpha;
+    tp = jb.tpos;
+  } else {
+    alpha = red + ST / 32;
+    tp_w = reinterpret_cast<int*>(red + ST / 32 + ntp);
+    tp = tp_w;
+  }
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const double Nd = (double)jb.N, Sd = (double)jb.SQ[0], Qd = (double)jb.SQ[1];
   const double coef = 2.0 / (2.0 * Nd * Sd - Qd);
@@ -543,11 +552,15 @@ static inline int solve_mixed_smem_bytes(int ntp) {
 
 cudaError_t tb_solve_mixed_init() {
   g_solve_mixed_smem_max = 220 * 1024;
-  cudaError_t e = cudaFuncSetAttribute(solve_mixed_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       g_solve_mixed_smem_max);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(solve_mixed_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              g_solve_mixed_smem_max);
+  cudaError_t e = cudaSuccess;
+  auto set = [&](const void* fn) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, g_solve_mixed_smem_max);
+  };
+  set((const void*)solve_mixed_kernel<true, false>);
+  set((const void*)solve_mixed_kernel<false, false>);
+  set((const void*)solve_mixed_kernel<true, true>);
+  set((const void*)solve_mixed_kernel<false, true>);
+  return e;
 }
 
 bool tb_solve_mixed_fits(int ntp) { return solve_mixed_smem_bytes(ntp) <= 220 * 1024; }
@@ -558,10 +571,11 @@ cudaError_t tb_launch_solve_mixed(const TbSolveMixedJob* d_jobs, int n_jobs, int
                                   cudaStream_t st) {
   const int smem = solve_mixed_smem_bytes(ntp);
   if (smem > g_solve_mixed_smem_max) return cudaErrorInvalidConfiguration;
-  if (contiguous)
-    solve_mixed_kernel<true><<<n_jobs, ST, smem, st>>>(d_jobs);
-  else
-    solve_mixed_kernel<false><<<n_jobs, ST, smem, st>>>(d_jobs);
+  const bool big = ntp > MIXED_SMEM_NTP;
+  if (contiguous && !big) solve_mixed_kernel<true, false><<<n_jobs, ST, smem, st>>>(d_jobs);
+  else if (!contiguous && !big) solve_mixed_kernel<false, false><<<n_jobs, ST, smem, st>>>(d_jobs);
+  else if (contiguous) solve_mixed_kernel<true, true><<<n_jobs, ST, smem, st>>>(d_jobs);
+  else solve_mixed_kernel<false, true><<<n_jobs, ST, smem, st>>>(d_jobs);
   return cudaGetLastError();
 }
 
