@@ -365,13 +365,16 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     const bool fork_centre = !c->profile && c->stop_after < 0;
     if (fork_centre) {
       TB_CUDA(c, cudaEventRecord(c->ev_fork, st));
+      TB_CUDA(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+      TB_CUDA(c, tb_launch_centre_terms(d_panel, rpad, kstride, c->d_idx, d_off, w0, Wc, centre_slots, d_kb, d_cs, d_csg, d_s, d_SQ, c->aux_stream));
+      TB_CUDA(c, cudaEventRecord(c->ev_join, c->aux_stream));
     } else {
       sp = span_begin(c, TB_ST_CENTRE);
       TB_CUDA(c, tb_launch_centre_terms(d_panel, rpad, kstride, c->d_idx, d_off, w0, Wc, centre_slots, d_kb, d_cs, d_csg, d_s, d_SQ, st));
       span_end(c, sp);
-      if (c->stop_after == TB_ST_CENTRE) continue;
     }
     count(c, TB_ST_CENTRE, 2);
+    if (c->stop_after == TB_ST_CENTRE) continue;
 
     sp = span_begin(c, TB_ST_GRAM);
     {
@@ -381,14 +384,6 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     }
     span_end(c, sp);
     count(c, TB_ST_GRAM, 1);
-    if (fork_centre) {
-      // issued AFTER the Gram launch: the persistent Gram CTAs (one per SM, 192 threads) take their slots first and
-      // the centring CTAs fill the thread slots that remain (issued first, they would occupy every thread slot and
-      // the Gram kernel would simply wait for them)
-      TB_CUDA(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
-      TB_CUDA(c, tb_launch_centre_terms(d_panel, rpad, kstride, c->d_idx, d_off, w0, Wc, centre_slots, d_kb, d_cs, d_csg, d_s, d_SQ, c->aux_stream));
-      TB_CUDA(c, cudaEventRecord(c->ev_join, c->aux_stream));
-    }
     if (fork_centre) TB_CUDA(c, cudaStreamWaitEvent(st, c->ev_join, 0));
     if (c->stop_after == TB_ST_GRAM) continue;
 
