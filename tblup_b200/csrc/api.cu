@@ -359,20 +359,9 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     count(c, TB_ST_GATHER, 1);
     if (c->stop_after == TB_ST_GATHER) continue;
 
-    // The centring terms and the Gram both depend only on the gathered panel: the (HBM-bound) centring kernels run on
-    // a side stream beside the (tensor-bound) Gram kernel and are joined before the scale stage.  With per-stage
-    // profiling or a debug stop they run in line so that the stage timers stay disjoint.
-    const bool fork_centre = !c->profile && c->stop_after < 0;
-    if (fork_centre) {
-      TB_CUDA(c, cudaEventRecord(c->ev_fork, st));
-      TB_CUDA(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
-      TB_CUDA(c, tb_launch_centre_terms(d_panel, rpad, kstride, c->d_idx, d_off, w0, Wc, centre_slots, d_kb, d_cs, d_csg, d_s, d_SQ, c->aux_stream));
-      TB_CUDA(c, cudaEventRecord(c->ev_join, c->aux_stream));
-    } else {
-      sp = span_begin(c, TB_ST_CENTRE);
-      TB_CUDA(c, tb_launch_centre_terms(d_panel, rpad, kstride, c->d_idx, d_off, w0, Wc, centre_slots, d_kb, d_cs, d_csg, d_s, d_SQ, st));
-      span_end(c, sp);
-    }
+    sp = span_begin(c, TB_ST_CENTRE);
+    TB_CUDA(c, tb_launch_centre_terms(d_panel, rpad, kstride, c->d_idx, d_off, w0, Wc, centre_slots, d_kb, d_cs, d_csg, d_s, d_SQ, st));
+    span_end(c, sp);
     count(c, TB_ST_CENTRE, 2);
     if (c->stop_after == TB_ST_CENTRE) continue;
 
@@ -384,7 +373,6 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     }
     span_end(c, sp);
     count(c, TB_ST_GRAM, 1);
-    if (fork_centre) TB_CUDA(c, cudaStreamWaitEvent(st, c->ev_join, 0));
     if (c->stop_after == TB_ST_GRAM) continue;
 
     if (mixed) {
@@ -511,10 +499,6 @@ int tb_create(const int8_t* geno, int n, int m, const double* y, const int32_t* 
   };
   if (chk(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return bail("");
   c->stream = c->own_stream;
-  if (chk(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return bail("");
-  if (chk(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming), "cudaEventCreate") ||
-      chk(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming), "cudaEventCreate"))
-    return bail("");
   if (chk(cudaMalloc(&c->d_x, (size_t)m * c->ldn), "cudaMalloc genotypes")) return bail("");
   if (chk(cudaMemsetAsync(c->d_x, 0, (size_t)m * c->ldn, c->stream), "memset")) return bail("");
   if (chk(cudaMalloc(&c->d_colsum_all, (size_t)m * sizeof(int)), "cudaMalloc colsum")) return bail("");
@@ -586,9 +570,6 @@ int tb_destroy(tb_ctx* c) {
   cudaFree(c->d_idx);
   cudaFree(c->ws);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
-  if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
-  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
-  if (c->ev_join) cudaEventDestroy(c->ev_join);
   delete c;
   return 0;
 }

@@ -54,8 +54,6 @@ struct TbCtx {
   TbRowSet slots[TB_MAX_SLOTS];
   cudaStream_t stream = nullptr;
   cudaStream_t own_stream = nullptr;
-  cudaStream_t aux_stream = nullptr;   // side stream: centring terms run beside the Gram kernel
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 
   // staged genomes
   int* d_idx = nullptr;           // flat marker lists
