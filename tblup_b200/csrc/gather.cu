@@ -113,16 +113,25 @@ __global__ void __launch_bounds__(256) centre_rows_kernel(const int8_t* __restri
   const uint4* row = reinterpret_cast<const uint4*>(panel + ((size_t)w * rpad + a) * kstride);
   const int4* cg = reinterpret_cast<const int4*>(csg + (size_t)job * kstride);
   long long acc = 0;
-  for (int j = lane; j < kbytes / 16; j += 32) {
-    const uint4 v = row[j];
-    const int4 c0 = cg[4 * j], c1 = cg[4 * j + 1], c2 = cg[4 * j + 2], c3 = cg[4 * j + 3];
+  auto dot16 = [&](const uint4 v, const int4* g) -> int {
+    const int4 c0 = g[0], c1 = g[1], c2 = g[2], c3 = g[3];
     int t = 0;
     t += (int)(v.x & 0xff) * c0.x + (int)((v.x >> 8) & 0xff) * c0.y + (int)((v.x >> 16) & 0xff) * c0.z + (int)(v.x >> 24) * c0.w;
     t += (int)(v.y & 0xff) * c1.x + (int)((v.y >> 8) & 0xff) * c1.y + (int)((v.y >> 16) & 0xff) * c1.z + (int)(v.y >> 24) * c1.w;
     t += (int)(v.z & 0xff) * c2.x + (int)((v.z >> 8) & 0xff) * c2.y + (int)((v.z >> 16) & 0xff) * c2.z + (int)(v.z >> 24) * c2.w;
     t += (int)(v.w & 0xff) * c3.x + (int)((v.w >> 8) & 0xff) * c3.y + (int)((v.w >> 16) & 0xff) * c3.z + (int)(v.w >> 24) * c3.w;
-    acc += t;   // 16 products of (dosage <= 2) x (column sum <= 2n < 2^26) fit an int
+    return t;   // 16 products of (dosage <= 2) x (column sum <= 2n < 2^26) fit an int
+  };
+  const int n16 = kbytes / 16;
+  int j = lane;
+  for (; j + 96 < n16; j += 128) {       // four 16-byte panel loads in flight per lane
+    const uint4 v0 = row[j], v1 = row[j + 32], v2 = row[j + 64], v3 = row[j + 96];
+    acc += dot16(v0, cg + 4 * j);
+    acc += dot16(v1, cg + 4 * (j + 32));
+    acc += dot16(v2, cg + 4 * (j + 64));
+    acc += dot16(v3, cg + 4 * (j + 96));
   }
+  for (; j < n16; j += 32) acc += dot16(row[j], cg + 4 * j);
   for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
   if (lane == 0) s[(size_t)job * rpad + a] = acc;
 }

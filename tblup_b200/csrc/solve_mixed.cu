@@ -320,7 +320,7 @@ __device__ void sym_matvec(const int32_t* __restrict__ C, int rpad, int n_t, con
 }
 
 template <bool CONTIG, bool BIG>
-__global__ void __launch_bounds__(ST) solve_mixed_kernel(const TbSolveMixedJob* __restrict__ jobs) {
+__global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJob* __restrict__ jobs) {
   extern __shared__ double msm[];
   const TbSolveMixedJob jb = jobs[blockIdx.x];
   const int ntp = jb.ntp, n_t = jb.n_t, n_v = jb.n_v, rpad = jb.rpad;
