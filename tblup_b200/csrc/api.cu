@@ -637,10 +637,18 @@ int tb_stage_genomes(tb_ctx* c, const int32_t* idx_flat, const int64_t* idx_off,
   for (int i = 0; i < P; ++i)
     if (idx_off[i + 1] < idx_off[i]) return fail(c, "tb_stage_genomes: offsets must be non-decreasing");
   const size_t total = (size_t)idx_off[P];
-  for (size_t q = 0; q < total; ++q)
-    if (idx_flat[q] < 0 || idx_flat[q] >= c->m)
-      return fail(c, "tb_stage_genomes: marker index " + std::to_string(idx_flat[q]) + " out of range [0, " +
-                         std::to_string(c->m) + ")");
+  {
+    // branch-free range check (vectorises): any index outside [0, m) sets the flag; the slow path names it
+    const unsigned um = (unsigned)c->m;
+    unsigned bad = 0;
+    for (size_t q = 0; q < total; ++q) bad |= (unsigned)((unsigned)idx_flat[q] >= um);
+    if (bad) {
+      for (size_t q = 0; q < total; ++q)
+        if (idx_flat[q] < 0 || idx_flat[q] >= c->m)
+          return fail(c, "tb_stage_genomes: marker index " + std::to_string(idx_flat[q]) + " out of range [0, " +
+                             std::to_string(c->m) + ")");
+    }
+  }
   TB_CUDA(c, cudaSetDevice(c->device));
   if (total > c->idx_cap) {
     TB_CUDA(c, cudaStreamSynchronize(c->stream));

@@ -100,21 +100,22 @@ __global__ void __launch_bounds__(256) centre_sq_kernel(const int* __restrict__ 
   }
 }
 
-// s[a] = sum_j panel[a][j] * csg[j]  (exact, int64).  One warp per animal row; each lane consumes 16 panel
-// bytes + 16 gathered column sums per iteration (panel streamed from HBM, csg stays in L1/L2).
+// s[a] = sum_j panel[a][j] * csg[j]  (exact, int64).  One warp per FOUR animal rows: the gathered column sums are
+// four times the bytes of the panel row they multiply, so sharing each csg load between four rows takes the kernel
+// from L1-bandwidth-bound to HBM-bound (panel streamed once from HBM, csg from L1/L2).
 __global__ void __launch_bounds__(256) centre_rows_kernel(const int8_t* __restrict__ panel, int rpad, int kstride,
                                                           const int* __restrict__ kblocks, int n_slots,
                                                           const int* __restrict__ csg, long long* __restrict__ s) {
   const int job = blockIdx.y;  // w * n_slots + slot
   const int w = job / n_slots;
-  const int a = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-  if (a >= rpad) return;
-  const int kbytes = kblocks[w] * TB_GRAM_BK;     // panel and csg are zero beyond k
-  const uint4* row = reinterpret_cast<const uint4*>(panel + ((size_t)w * rpad + a) * kstride);
+  const int a0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 4, lane = threadIdx.x & 31;
+  if (a0 >= rpad) return;      // rpad is a multiple of 128: rows a0 .. a0 + 3 are all inside
+  const int n16 = kblocks[w] * TB_GRAM_BK / 16;     // panel and csg are zero beyond k
+  const uint4* row = reinterpret_cast<const uint4*>(panel + ((size_t)w * rpad + a0) * kstride);
+  const size_t rs = kstride / 16;
   const int4* cg = reinterpret_cast<const int4*>(csg + (size_t)job * kstride);
-  long long acc = 0;
-  auto dot16 = [&](const uint4 v, const int4* g) -> int {
-    const int4 c0 = g[0], c1 = g[1], c2 = g[2], c3 = g[3];
+  long long acc[4] = {0, 0, 0, 0};
+  auto dot16 = [](const uint4 v, const int4 c0, const int4 c1, const int4 c2, const int4 c3) -> int {
     int t = 0;
     t += (int)(v.x & 0xff) * c0.x + (int)((v.x >> 8) & 0xff) * c0.y + (int)((v.x >> 16) & 0xff) * c0.z + (int)(v.x >> 24) * c0.w;
     t += (int)(v.y & 0xff) * c1.x + (int)((v.y >> 8) & 0xff) * c1.y + (int)((v.y >> 16) & 0xff) * c1.z + (int)(v.y >> 24) * c1.w;
@@ -122,18 +123,20 @@ __global__ void __launch_bounds__(256) centre_rows_kernel(const int8_t* __restri
     t += (int)(v.w & 0xff) * c3.x + (int)((v.w >> 8) & 0xff) * c3.y + (int)((v.w >> 16) & 0xff) * c3.z + (int)(v.w >> 24) * c3.w;
     return t;   // 16 products of (dosage <= 2) x (column sum <= 2n < 2^26) fit an int
   };
-  const int n16 = kbytes / 16;
-  int j = lane;
-  for (; j + 96 < n16; j += 128) {       // four 16-byte panel loads in flight per lane
-    const uint4 v0 = row[j], v1 = row[j + 32], v2 = row[j + 64], v3 = row[j + 96];
-    acc += dot16(v0, cg + 4 * j);
-    acc += dot16(v1, cg + 4 * (j + 32));
-    acc += dot16(v2, cg + 4 * (j + 64));
-    acc += dot16(v3, cg + 4 * (j + 96));
+  for (int j = lane; j < n16; j += 32) {
+    const uint4 v0 = row[j], v1 = row[rs + j], v2 = row[2 * rs + j], v3 = row[3 * rs + j];
+    const int4 c0 = cg[4 * j], c1 = cg[4 * j + 1], c2 = cg[4 * j + 2], c3 = cg[4 * j + 3];
+    acc[0] += dot16(v0, c0, c1, c2, c3);
+    acc[1] += dot16(v1, c0, c1, c2, c3);
+    acc[2] += dot16(v2, c0, c1, c2, c3);
+    acc[3] += dot16(v3, c0, c1, c2, c3);
   }
-  for (; j < n16; j += 32) acc += dot16(row[j], cg + 4 * j);
-  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-  if (lane == 0) s[(size_t)job * rpad + a] = acc;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    long long v = acc[r];
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s[(size_t)job * rpad + a0 + r] = v;
+  }
 }
 
 }  // namespace
@@ -152,7 +155,7 @@ cudaError_t tb_launch_centre_terms(const int8_t* d_panel, int rpad, int kstride,
   centre_sq_kernel<<<W * n_slots, 256, 0, st>>>(d_idx, d_off, w0, n_slots, kstride, d_colsum_of, d_csg, d_SQ);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
-  dim3 grid((rpad + 7) / 8, W * n_slots);
+  dim3 grid((rpad + 31) / 32, W * n_slots);
   centre_rows_kernel<<<grid, 256, 0, st>>>(d_panel, rpad, kstride, d_kblocks, n_slots, d_csg, d_s);
   return cudaGetLastError();
 }

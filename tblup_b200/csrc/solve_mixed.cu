@@ -480,16 +480,22 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
 }
 
 // fp32 copy of A = G_tt + lambda I (lower triangle, identity padding) for the tensor-core factorisation.
+// Block = 64 rows x 128 columns; a thread owns 4 consecutive columns (one 16-byte load of C, one 16-byte store) of
+// 8 rows, so the per-column setup (positions, column terms) is amortised over 8 rows and the 8 row loads are
+// independent.  fp32 output: exact int64 numerator, one fp64 multiply by 2/den (the exact operator lives in
+// solve_mixed_kernel, so no fp64 division is needed here).
+constexpr int S32_ROWS = 64;
 __global__ void __launch_bounds__(256) scale32_kernel(const TbScaleJob* __restrict__ jobs, float* __restrict__ L32,
                                                       int ntp_all) {
   const TbScaleJob jb = jobs[blockIdx.z];
   const int ntp = jb.ntp, n_t = jb.n_t, rpad = jb.rpad;
-  const int r0 = blockIdx.y * 16, c0 = blockIdx.x * 128;
-  if (r0 >= ntp || c0 >= ntp || c0 > r0 + 15) return;
+  const int r0 = blockIdx.y * S32_ROWS, c0 = blockIdx.x * 128;
+  if (r0 >= ntp || c0 >= ntp || c0 > r0 + S32_ROWS - 1) return;
   const int c = c0 + (threadIdx.x & 31) * 4;
   if (c >= ntp) return;
   const long long N = jb.N, S = jb.SQ[0], Q = jb.SQ[1];
-  const double inv_den2 = 2.0 / (double)(2 * N * S - Q);
+  const long long NN = N * N;
+  const float inv_den2 = (float)(2.0 / (double)(2 * N * S - Q)), lam = (float)jb.lambda;
   int pc[4];
   long long sc[4];
   bool creal[4];
@@ -501,40 +507,57 @@ __global__ void __launch_bounds__(256) scale32_kernel(const TbScaleJob* __restri
   }
   const bool run = creal[3] && pc[1] == pc[0] + 1 && pc[2] == pc[0] + 2 && pc[3] == pc[0] + 3 && (pc[0] & 3) == 0;
   float* out_base = L32 + (size_t)blockIdx.z * ntp_all * ntp_all;
+  const int rbase = r0 + (threadIdx.x >> 5);
+  // phase 1: positions, row terms and the integer cross-products of the 8 rows (independent loads)
+  int pr[8];
+  long long sr[8];
+  int4 cv[8];
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int r = r0 + (threadIdx.x >> 5) + 8 * h;
-    if (r >= ntp) break;
-    if (c > r) continue;
+  for (int h = 0; h < 8; ++h) {
+    const int r = rbase + 8 * h;
+    pr[h] = (r < n_t) ? jb.tpos[r] : -1;
+  }
+#pragma unroll
+  for (int h = 0; h < 8; ++h) {
+    const int r = rbase + 8 * h;
+    sr[h] = 0;
+    cv[h] = make_int4(0, 0, 0, 0);
+    if (pr[h] >= 0 && c <= r) {
+      sr[h] = jb.s[pr[h]];
+      if (run && pc[3] < pr[h]) {
+        cv[h] = *reinterpret_cast<const int4*>(jb.C + (size_t)pr[h] * rpad + pc[0]);
+      } else {
+        int t[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int hi = pr[h] > pc[i] ? pr[h] : pc[i], lo = pr[h] > pc[i] ? pc[i] : pr[h];
+          t[i] = creal[i] ? jb.C[(size_t)hi * rpad + lo] : 0;
+        }
+        cv[h] = make_int4(t[0], t[1], t[2], t[3]);
+      }
+    }
+  }
+  // phase 2: arithmetic and stores
+#pragma unroll
+  for (int h = 0; h < 8; ++h) {
+    const int r = rbase + 8 * h;
+    if (r >= ntp || c > r) continue;
     float out[4];
     if (r >= n_t) {
 #pragma unroll
       for (int i = 0; i < 4; ++i) out[i] = (r == c + i) ? 1.f : 0.f;
     } else {
-      const int pr = jb.tpos[r];
-      const long long sr = jb.s[pr];
-      int cv[4];
-      if (run && pc[3] < pr) {
-        const int4 q4 = *reinterpret_cast<const int4*>(jb.C + (size_t)pr * rpad + pc[0]);
-        cv[0] = q4.x; cv[1] = q4.y; cv[2] = q4.z; cv[3] = q4.w;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int hi = pr > pc[i] ? pr : pc[i], lo = pr > pc[i] ? pc[i] : pr;
-          cv[i] = creal[i] ? jb.C[(size_t)hi * rpad + lo] : 0;
-        }
-      }
+      const int cvv[4] = {cv[h].x, cv[h].y, cv[h].z, cv[h].w};
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        double g = 0.0;
+        float g = 0.f;
         if (creal[i]) {
-          // fp32 output: one exact int64 numerator, one fp64 multiply by 2/den (no fp64 division needed here --
-          // the result is rounded to fp32 anyway; the exact operator lives in solve_mixed_kernel)
-          const long long num = N * N * (long long)cv[i] - N * (sr + sc[i]) + Q;
-          g = (double)num * inv_den2;
-          if (r == c + i) g += jb.lambda;
+          // exact int64 numerator (after the cancellation), ONE rounding to fp32, one fp32 multiply
+          const long long num = NN * (long long)cvv[i] - N * (sr[h] + sc[i]) + Q;
+          g = (float)num * inv_den2;
+          if (r == c + i) g += lam;
         }
-        out[i] = (float)g;
+        out[i] = g;
       }
     }
     *reinterpret_cast<float4*>(out_base + (size_t)r * ntp_all + c) = make_float4(out[0], out[1], out[2], out[3]);
@@ -580,7 +603,7 @@ cudaError_t tb_launch_solve_mixed(const TbSolveMixedJob* d_jobs, int n_jobs, int
 }
 
 cudaError_t tb_launch_scale32(const TbScaleJob* d_jobs, int n_jobs, int ntp, float* L32, cudaStream_t st) {
-  dim3 grid((ntp + 127) / 128, (ntp + 15) / 16, n_jobs);
+  dim3 grid((ntp + 127) / 128, (ntp + S32_ROWS - 1) / S32_ROWS, n_jobs);
   scale32_kernel<<<grid, 256, 0, st>>>(d_jobs, L32, ntp);
   return cudaGetLastError();
 }
