@@ -5,7 +5,8 @@
 set -u
 TAG=${1:-r01}
 PREC=${2:-mixed}
-CMD="python bench.py --steps 1 --warmup 1 --pop 64 --no-cpu-baseline --precision $PREC"
+POP=${3:-64}
+CMD="python bench.py --steps 1 --warmup 1 --pop $POP --no-cpu-baseline --precision $PREC"
 mkdir -p gpurun_out
 $CMD > gpurun_out/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_$TAG.log; exit 1; }
 tail -1 gpurun_out/plain_$TAG.log | cut -c1-300
