@@ -379,8 +379,15 @@ def main():
             per_mat = 2 * n_t * (n_t + 1) / 2 * 8 + n_v * n_t * 8
             solve_kernel = "solve_kernel (fp64 blocked substitution + predictions + Pearson)"
         solve_gbs = per_mat * n_mats / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else None
+        # measured DRAM bytes per matrix of this kernel from the committed ncu capture (profiles/r01p_solve_raw.csv:
+        # dram__bytes_read.sum + dram__bytes_write.sum = 164.06 GB for 1 000 matrices, 2 sweeps, C2 shape)
+        ncu_bytes_per_mat = 164.06e6 if (precision == "mixed" and n_t == 3200 and mean_sweeps == 2.0) else None
+        mats_per_launch = n_mats / max(1, solve_launches)
         rl_solve = {"bound": "hbm", "kernel": solve_kernel, "achieved": solve_gbs, "peak": hbm, "unit": "GB/s",
-                    "frac": (solve_gbs / hbm) if solve_gbs else None, "traffic": None,
+                    "frac": (solve_gbs / hbm) if solve_gbs else None,
+                    "traffic": ncu_bytes_per_mat * mats_per_launch if ncu_bytes_per_mat else None,
+                    "traffic_source": "profiles/r01p_solve_raw.csv (ncu --set full), scaled to matrices per launch",
+                    "algorithmic_bytes_per_launch": per_mat * mats_per_launch,
                     "peak_source": "hbm_gbs of MEASURED_PEAKS.json" if peaks.get("hbm_gbs") else "fallback 6650 GB/s",
                     "algorithmic_bytes_per_matrix": per_mat, "mean_refinement_sweeps": mean_sweeps,
                     "launches": int(solve_launches), "avg_launch_ms": solve_ms / max(1, solve_launches),
