@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="mixed", choices=["mixed", "fp64"],
                     help="mixed: TF32 tensor-core Cholesky preconditioner + fp64 refinement (default); fp64: fp64 Cholesky")
+    ap.add_argument("--storage", default="int8", choices=["int8", "packed2"],
+                    help="resident genotype format: int8 dosages, or 2 bits per dosage (bit-identical results)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="individuals in the CPU sample (default: one per core)")
     return ap.parse_args()
 
@@ -217,7 +219,7 @@ def main():
     x, y = (synth.synth_dataset_fast if wl.get("fast_synth") else synth.synth_dataset)(n, m, h2=H2, seed=0)
     train, valid, test = synth.split_indices(n, seed=0)
     slots = [0]
-    eng = GblupEngine(x, y, perm=np.concatenate([train, valid, test]), device=local_rank)
+    eng = GblupEngine(x, y, perm=np.concatenate([train, valid, test]), device=local_rank, storage=args.storage)
     if folds == 1:
         eng.set_rowset(0, train, valid)
     else:
@@ -402,6 +404,7 @@ def main():
                       else "s8 Gram (s32 accumulate) + f64 Cholesky/solve"), "data": "synthetic",
             "config": {"workload": args.workload, "animals": n, "markers": m, "k": k, "pop_per_gpu": P, "folds": folds,
                        "h2": H2, "n_train": int(n_t), "n_valid": int(n_v), "individuals_per_wave": wave, "precision": precision,
+                       "genotype_storage": args.storage, "genotype_bytes_resident": eng.resident_genotype_bytes(),
                        "l2": "inputs larger than L2 (each step streams >20 GB of per-genome panels and matrices)",
                        "parallelism": "replicated genotypes, population sharded, NCCL all-gather of fitness"},
             "e2e": {"value": evals / (ms_e2e * 1e-3), "unit": UNIT,

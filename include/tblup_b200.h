@@ -57,7 +57,24 @@ const char* tb_last_error(const tb_ctx* ctx);
  * y: [n]; perm: [n] or NULL, animal stored at "universe" position p is perm[p] (put the animals the
  * fitness reads first: training, validation, testing -- the Gram then only covers that prefix). */
 int tb_create(const int8_t* geno, int n, int m, const double* y, const int32_t* perm, int device, tb_ctx** out);
+
+/* Same, with the input layout and the resident storage chosen by the caller (the reference only knows the dense
+ * float64 .npy of tblup/utils.py:95 / evaluator.py:188,215; at 20 000 x 500 000 that file would be 80 GB).
+ * layout TB_LAYOUT_INT8_ANIMAL_MAJOR: geno = int8 [n][m] as above.
+ * layout TB_LAYOUT_PACKED2_SNP_MAJOR: geno = uint8 [m][ceil(n/4)], marker-major, animal 4q+i of a marker in bits
+ *   2i..2i+1 of byte q (the row layout and bit order of a PLINK .bed body), each 2-bit code being the dosage 0/1/2;
+ *   code 3 is rejected (the reference has no missing-value handling).
+ * storage TB_STORE_INT8: resident as int8 dosages (m x n bytes); TB_STORE_PACKED2: resident at 2 bits per dosage
+ *   (m x n / 4 bytes), expanded inside the gather kernel.  Results are bit-identical between the two. */
+#define TB_LAYOUT_INT8_ANIMAL_MAJOR 0
+#define TB_LAYOUT_PACKED2_SNP_MAJOR 1
+#define TB_STORE_INT8 0
+#define TB_STORE_PACKED2 1
+int tb_create_ex(const void* geno, int layout, int storage, int n, int m, const double* y, const int32_t* perm,
+                 int device, tb_ctx** out);
 int tb_destroy(tb_ctx* ctx);
+/* resident genotype bytes and storage kind (TB_STORE_*) of a context */
+int tb_storage_info(const tb_ctx* ctx, int* storage, uint64_t* bytes);
 
 /* Define row set `slot`: the (train_indices, validation_indices) pair of tblup/evaluator.py:316-322,
  * :485-491, :555-561 (original animal indices).  Precomputes the training-row dosage sums

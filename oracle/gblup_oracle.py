@@ -250,3 +250,35 @@ def synth_genotypes(n, m, h2=0.4, seed=0, offset=0.0):
     e = rng.standard_normal(n) * np.sqrt(var_g * (1 - h2) / h2)
     y = g + e + offset
     return x, y
+
+
+# ---- genotype containers (SURVEY.md §8 F3): independent restatement of the 2-bit packing, loop form ------------
+# The reference only reads dense float64 .npy (tblup/utils.py:95, evaluator.py:188,215); the packed container is
+# ours, so the oracle for it is the definition itself, written the slow obvious way, plus the PLINK 1 .bed coding
+# (published format: magic 6c 1b 01, SNP-major rows of ceil(n/4) bytes, sample 4q+i in bits 2i..2i+1,
+# 00 = hom. first allele, 01 = missing, 10 = het, 11 = hom. second allele).
+
+def pack2_loops(x_int):
+    """[n][m] dosages -> uint8 [m][ceil(n/4)], animal 4q+i in bits 2i..2i+1 of byte q (pure-Python loops)."""
+    n, m = x_int.shape
+    out = np.zeros((m, (n + 3) // 4), dtype=np.uint8)
+    for j in range(m):
+        for a in range(n):
+            out[j, a // 4] |= np.uint8(int(x_int[a, j]) << (2 * (a % 4)))
+    return out
+
+
+def bed_bytes_loops(x_int):
+    """Bytes of the PLINK 1 .bed file holding these first-allele dosages."""
+    code = {2: 0b00, 1: 0b10, 0: 0b11}
+    n, m = x_int.shape
+    body = bytearray()
+    for j in range(m):
+        for q in range((n + 3) // 4):
+            b = 0
+            for i in range(4):
+                a = 4 * q + i
+                if a < n:
+                    b |= code[int(x_int[a, j])] << (2 * i)
+            body.append(b)
+    return bytes((0x6C, 0x1B, 0x01)) + bytes(body)

@@ -1,5 +1,5 @@
 """A/B helper: median / min / max device time per step of the resident evaluation and the per-stage split.
-usage: python scripts/ab.py [pop] [steps] [precision]"""
+usage: python scripts/ab.py [pop] [steps] [precision] [storage]"""
 import sys, os
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -9,9 +9,10 @@ from tblup_b200 import GblupEngine, synth
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 prec = sys.argv[3] if len(sys.argv) > 3 else "mixed"
+storage = sys.argv[4] if len(sys.argv) > 4 else "int8"
 x, y = synth.synth_dataset(5000, 50000, seed=0)
 tr, va, te = synth.split_indices(5000, seed=0)
-eng = GblupEngine(x, y, perm=np.concatenate([tr, va, te]))
+eng = GblupEngine(x, y, perm=np.concatenate([tr, va, te]), storage=storage)
 eng.set_rowset(0, tr, va)
 eng.set_precision(prec)
 stream = torch.cuda.current_stream()
@@ -30,8 +31,8 @@ for i in range(steps):
     torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
 ts = np.array(ts)
-print("pop %d %s: per-step ms median %.1f min %.1f max %.1f  -> %.0f evals/s (median)" % (
-    P, prec, np.median(ts), ts.min(), ts.max(), P / np.median(ts) * 1e3))
+print("pop %d %s %s: per-step ms median %.1f min %.1f max %.1f  -> %.0f evals/s (median)" % (
+    P, prec, storage, np.median(ts), ts.min(), ts.max(), P / np.median(ts) * 1e3))
 eng.set_option("profile", 1)
 agg = {}
 for i in range(5):

@@ -17,6 +17,9 @@ SYMBOLS = {
     "tb_abi_version": (C.c_int, []),
     "tb_last_error": (C.c_char_p, [C.c_void_p]),
     "tb_create": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
+    "tb_create_ex": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int,
+                               C.POINTER(C.c_void_p)]),
+    "tb_storage_info": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tb_destroy": (C.c_int, [C.c_void_p]),
     "tb_set_rowset": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "tb_stage_genomes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),

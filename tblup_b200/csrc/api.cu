@@ -354,7 +354,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     span_end(c, sp);
 
     sp = span_begin(c, TB_ST_GATHER);
-    TB_CUDA(c, tb_launch_gather(c->d_x, c->ldn, c->d_idx, d_off, w0, Wc, rpad, kstride, d_panel, st));
+    TB_CUDA(c, tb_launch_gather(c->geno(), c->d_idx, d_off, w0, Wc, rpad, kstride, d_panel, st));
     span_end(c, sp);
     count(c, TB_ST_GATHER, 1);
     if (c->stop_after == TB_ST_GATHER) continue;
@@ -447,12 +447,23 @@ int tb_abi_version(void) { return TB_ABI_VERSION; }
 const char* tb_last_error(const tb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_err.c_str(); }
 
 int tb_create(const int8_t* geno, int n, int m, const double* y, const int32_t* perm, int device, tb_ctx** out) {
+  return tb_create_ex(geno, TB_LAYOUT_INT8_ANIMAL_MAJOR, TB_STORE_INT8, n, m, y, perm, device, out);
+}
+
+int tb_create_ex(const void* geno_any, int layout, int storage, int n, int m, const double* y, const int32_t* perm,
+                 int device, tb_ctx** out) {
   if (!out) return -1;
   *out = nullptr;
-  if (!geno || !y || n <= 0 || m <= 0) {
+  if (!geno_any || !y || n <= 0 || m <= 0) {
     g_create_err = "tb_create: null or empty input";
     return -1;
   }
+  if ((layout != TB_LAYOUT_INT8_ANIMAL_MAJOR && layout != TB_LAYOUT_PACKED2_SNP_MAJOR) ||
+      (storage != TB_STORE_INT8 && storage != TB_STORE_PACKED2)) {
+    g_create_err = "tb_create_ex: unknown layout or storage";
+    return -1;
+  }
+  const int8_t* geno = static_cast<const int8_t*>(geno_any);
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
   if (e != cudaSuccess || ndev == 0) {
@@ -480,6 +491,7 @@ int tb_create(const int8_t* geno, int n, int m, const double* y, const int32_t* 
   c->n = n;
   c->m = m;
   c->ldn = tb_round_up(n, 128);
+  c->storage = storage;
   c->n_sm = prop.multiProcessorCount;
   if (cudaSetDevice(device) != cudaSuccess) return bail("cudaSetDevice failed");
   std::vector<int> p(n);
@@ -503,39 +515,71 @@ int tb_create(const int8_t* geno, int n, int m, const double* y, const int32_t* 
   if (chk(cudaMemsetAsync(c->d_x, 0, (size_t)m * c->ldn, c->stream), "memset")) return bail("");
   if (chk(cudaMalloc(&c->d_colsum_all, (size_t)m * sizeof(int)), "cudaMalloc colsum")) return bail("");
 
-  // upload in universe order, transposing chunks of animals to SNP-major on the device
-  int chunk = (int)std::max<long long>(64, std::min<long long>(n, ((long long)256 << 20) / m));
-  chunk = std::min(chunk, n);
-  int8_t *h_stage = nullptr, *d_stage = nullptr;
-  if (chk(cudaMallocHost(&h_stage, (size_t)chunk * m), "cudaMallocHost staging")) return bail("");
-  if (chk(cudaMalloc(&d_stage, (size_t)chunk * m), "cudaMalloc staging")) {
-    cudaFreeHost(h_stage);
-    return bail("");
-  }
   bool bad_value = false, cuda_bad = false;
-  for (int p0 = 0; p0 < n && !cuda_bad && !bad_value; p0 += chunk) {
-    const int rows = std::min(chunk, n - p0);
-    unsigned char maxv = 0;
-    for (int r = 0; r < rows; ++r) {
-      const int8_t* src = geno + (size_t)p[p0 + r] * m;
-      int8_t* dst = h_stage + (size_t)r * m;
-      for (int j = 0; j < m; ++j) {
-        const int8_t v = src[j];
-        dst[j] = v;
-        maxv = std::max(maxv, (unsigned char)v);   // negative values map to >= 128
+  if (layout == TB_LAYOUT_INT8_ANIMAL_MAJOR) {
+    // upload in universe order, transposing chunks of animals to SNP-major on the device
+    int chunk = (int)std::max<long long>(64, std::min<long long>(n, ((long long)256 << 20) / m));
+    chunk = std::min(chunk, n);
+    int8_t *h_stage = nullptr, *d_stage = nullptr;
+    if (chk(cudaMallocHost(&h_stage, (size_t)chunk * m), "cudaMallocHost staging")) return bail("");
+    if (chk(cudaMalloc(&d_stage, (size_t)chunk * m), "cudaMalloc staging")) {
+      cudaFreeHost(h_stage);
+      return bail("");
+    }
+    for (int p0 = 0; p0 < n && !cuda_bad && !bad_value; p0 += chunk) {
+      const int rows = std::min(chunk, n - p0);
+      unsigned char maxv = 0;
+      for (int r = 0; r < rows; ++r) {
+        const int8_t* src = geno + (size_t)p[p0 + r] * m;
+        int8_t* dst = h_stage + (size_t)r * m;
+        for (int j = 0; j < m; ++j) {
+          const int8_t v = src[j];
+          dst[j] = v;
+          maxv = std::max(maxv, (unsigned char)v);   // negative values map to >= 128
+        }
       }
+      if (maxv > 2) {
+        bad_value = true;
+        break;
+      }
+      cuda_bad |= chk(cudaMemcpyAsync(d_stage, h_stage, (size_t)rows * m, cudaMemcpyHostToDevice, c->stream), "H2D genotypes");
+      cuda_bad |= chk(tb_launch_transpose_rows(d_stage, rows, m, c->d_x, c->ldn, p0, c->stream), "transpose");
+      cuda_bad |= chk(cudaStreamSynchronize(c->stream), "sync after transpose");
+      c->launches += 1;
     }
-    if (maxv > 2) {
-      bad_value = true;
-      break;
+    cudaFreeHost(h_stage);
+    cudaFree(d_stage);
+  } else {
+    // SNP-major 2-bit rows in file order (stride = ceil(n / 4) bytes per marker, the layout of a PLINK .bed body
+    // with dosage codes): chunks of markers are contiguous, the device expands them and applies the permutation
+    const int stride = (n + 3) / 4;
+    const uint8_t* packed = static_cast<const uint8_t*>(geno_any);
+    int chunk = (int)std::max<long long>(1, std::min<long long>(m, ((long long)256 << 20) / stride));
+    uint8_t* d_stage = nullptr;
+    int *d_perm = nullptr, *d_bad = nullptr;
+    cuda_bad |= chk(cudaMalloc(&d_stage, (size_t)chunk * stride), "cudaMalloc staging");
+    cuda_bad |= chk(cudaMalloc(&d_perm, (size_t)n * sizeof(int)), "cudaMalloc perm");
+    cuda_bad |= chk(cudaMalloc(&d_bad, sizeof(int)), "cudaMalloc flag");
+    if (!cuda_bad) {
+      cuda_bad |= chk(cudaMemcpyAsync(d_perm, p.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice, c->stream), "H2D perm");
+      cuda_bad |= chk(cudaMemsetAsync(d_bad, 0, sizeof(int), c->stream), "memset");
     }
-    cuda_bad |= chk(cudaMemcpyAsync(d_stage, h_stage, (size_t)rows * m, cudaMemcpyHostToDevice, c->stream), "H2D genotypes");
-    cuda_bad |= chk(tb_launch_transpose_rows(d_stage, rows, m, c->d_x, c->ldn, p0, c->stream), "transpose");
-    cuda_bad |= chk(cudaStreamSynchronize(c->stream), "sync after transpose");
-    c->launches += 1;
+    for (int j0 = 0; j0 < m && !cuda_bad; j0 += chunk) {
+      const int rows = std::min(chunk, m - j0);
+      cuda_bad |= chk(cudaMemcpyAsync(d_stage, packed + (size_t)j0 * stride, (size_t)rows * stride, cudaMemcpyHostToDevice, c->stream), "H2D packed genotypes");
+      cuda_bad |= chk(tb_launch_unpack2_perm(d_stage, rows, stride, d_perm, n, c->d_x, c->ldn, j0, d_bad, c->stream), "unpack");
+      cuda_bad |= chk(cudaStreamSynchronize(c->stream), "sync after unpack");
+      c->launches += 1;
+    }
+    if (!cuda_bad) {
+      int h_bad = 0;
+      cuda_bad |= chk(cudaMemcpy(&h_bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost), "D2H flag");
+      bad_value = h_bad != 0;
+    }
+    cudaFree(d_stage);
+    cudaFree(d_perm);
+    cudaFree(d_bad);
   }
-  cudaFreeHost(h_stage);
-  cudaFree(d_stage);
   if (bad_value) return bail("tb_create: genotype values must be dosages in {0, 1, 2}");
   if (cuda_bad) return bail("");
   {
@@ -544,11 +588,21 @@ int tb_create(const int8_t* geno, int n, int m, const double* y, const int32_t* 
     int* d_pos = nullptr;
     if (chk(cudaMalloc(&d_pos, n * sizeof(int)), "cudaMalloc")) return bail("");
     bool b2 = chk(cudaMemcpyAsync(d_pos, ident.data(), n * sizeof(int), cudaMemcpyHostToDevice, c->stream), "H2D");
-    b2 |= chk(tb_launch_colsum(c->d_x, c->ldn, m, d_pos, n, c->d_colsum_all, c->stream), "colsum");
+    b2 |= chk(tb_launch_colsum(c->geno(), m, d_pos, n, c->d_colsum_all, c->stream), "colsum");
     b2 |= chk(cudaStreamSynchronize(c->stream), "sync after colsum");
     cudaFree(d_pos);
     c->launches += 1;
     if (b2) return bail("");
+  }
+  if (storage == TB_STORE_PACKED2) {
+    // keep only the 2-bit copy resident (a quarter of the bytes; the gather expands it on the fly)
+    if (chk(cudaMalloc(&c->d_x2, (size_t)m * (c->ldn / 4)), "cudaMalloc packed genotypes")) return bail("");
+    bool b2 = chk(tb_launch_pack2(c->d_x, c->ldn, m, c->d_x2, c->stream), "pack");
+    b2 |= chk(cudaStreamSynchronize(c->stream), "sync after pack");
+    c->launches += 1;
+    if (b2) return bail("");
+    cudaFree(c->d_x);
+    c->d_x = nullptr;
   }
   if (chk(tb_gram_tc_init(), "gram kernel init") || chk(tb_chol_init(), "cholesky kernel init") ||
       chk(tb_solve_init(), "solve kernel init") ||
@@ -566,6 +620,7 @@ int tb_destroy(tb_ctx* c) {
   tb_de_release(c);
   for (auto ev : c->ev_pool) cudaEventDestroy(ev);
   cudaFree(c->d_x);
+  cudaFree(c->d_x2);
   cudaFree(c->d_colsum_all);
   cudaFree(c->d_idx);
   cudaFree(c->ws);
@@ -623,7 +678,7 @@ int tb_set_rowset(tb_ctx* c, int slot, const int32_t* train, int n_t, const int3
   TB_CUDA(c, cudaMemcpyAsync(r.d_yt_raw, yt.data(), r.ntp * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   TB_CUDA(c, cudaMemcpyAsync(r.d_yt_ctr, ytc.data(), r.ntp * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   TB_CUDA(c, cudaMemcpyAsync(r.d_yv, yv.data(), n_v * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  TB_CUDA(c, tb_launch_colsum(c->d_x, c->ldn, c->m, r.d_tpos, n_t, r.d_colsum_train, c->stream));
+  TB_CUDA(c, tb_launch_colsum(c->geno(), c->m, r.d_tpos, n_t, r.d_colsum_train, c->stream));
   c->launches += 1;
   TB_CUDA(c, cudaStreamSynchronize(c->stream));
   r.valid = true;
@@ -733,7 +788,7 @@ int tb_gram_debug(tb_ctx* c, const int32_t* idx, int k, int rows, int impl, int3
     ck(cudaMemcpyAsync(d_t, tiles.data(), tiles.size() * sizeof(int), cudaMemcpyHostToDevice, st), "H2D");
     ck(cudaMemcpyAsync(d_kb, &kb, sizeof(int), cudaMemcpyHostToDevice, st), "H2D");
     ck(cudaMemcpyAsync(d_off, off, sizeof(off), cudaMemcpyHostToDevice, st), "H2D");
-    ck(tb_launch_gather(c->d_x, c->ldn, d_i, d_off, 0, 1, rpad, kstride, d_panel, st), "gather");
+    ck(tb_launch_gather(c->geno(), d_i, d_off, 0, 1, rpad, kstride, d_panel, st), "gather");
     if (impl == 0) {
       std::string e;
       cudaError_t ce = tb_launch_gram_tc(d_panel, 1, rpad, kstride, d_kb, d_t, (int)tiles.size(), d_C, c->n_sm, st, &e);
@@ -802,6 +857,7 @@ int tb_set_option(tb_ctx* c, const char* name, long long value) {
   else if (s == "workspace_mb") c->ws_limit = value > 0 ? (size_t)value << 20 : 0;
   else if (s == "max_wave") c->max_wave = (int)value;
   else if (s == "precision") c->precision = value != 0;
+  else if (s == "storage") return fail(c, "tb_set_option: storage is fixed at tb_create_ex");
   else return fail(c, "tb_set_option: unknown option '" + s + "'");
   return 0;
 }
@@ -829,6 +885,13 @@ int tb_reset_counters(tb_ctx* c) {
 
 int tb_last_wave(const tb_ctx* c) { return c ? c->last_wave : 0; }
 int tb_last_precision(const tb_ctx* c) { return c ? (c->last_mixed ? 0 : 1) : -1; }
+
+int tb_storage_info(const tb_ctx* c, int* storage, uint64_t* bytes) {
+  if (!c) return -1;
+  if (storage) *storage = c->storage;
+  if (bytes) *bytes = (uint64_t)c->m * (uint64_t)(c->storage == TB_STORE_PACKED2 ? c->ldn / 4 : c->ldn);
+  return 0;
+}
 
 int tb_set_stream(tb_ctx* c, void* cuda_stream) {
   if (!c) return -1;

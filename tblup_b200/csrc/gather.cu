@@ -13,6 +13,9 @@ namespace {
 // 128 markers x 128 animals per block, transposed through shared memory as 32-bit words.
 // Word (jl, c) holds animals 4c..4c+3 of marker jl and is stored at column (c + (jl >> 2)) & 31,
 // which makes both the row-wise fill and the 4x4 byte-transposing drain bank-conflict free.
+// PACKED: the source row holds 2 bits per dosage; a lane's byte (four animals) expands to the same 32-bit word the
+// int8 source would have delivered, so everything after the load is shared.  A quarter of the read traffic.
+template <bool PACKED>
 __global__ void __launch_bounds__(256) gather_kernel(const int8_t* __restrict__ x, int ldn,
                                                      const int* __restrict__ idx, const long long* __restrict__ off,
                                                      int w0, int rpad, int kstride, int8_t* __restrict__ panel) {
@@ -30,7 +33,12 @@ __global__ void __launch_bounds__(256) gather_kernel(const int8_t* __restrict__ 
     uint32_t v = 0;
     if (j < k) {
       const int src = idx[o0 + j];
-      v = *reinterpret_cast<const uint32_t*>(x + (size_t)src * ldn + a0 + lane * 4);
+      if (PACKED) {
+        const uint32_t b = reinterpret_cast<const uint8_t*>(x)[(size_t)src * ldn + (a0 >> 2) + lane];
+        v = (b | (b << 6) | (b << 12) | (b << 18)) & 0x03030303u;
+      } else {
+        v = *reinterpret_cast<const uint32_t*>(x + (size_t)src * ldn + a0 + lane * 4);
+      }
     }
     tile[jl][(lane + (jl >> 2)) & 31] = v;
   }
@@ -141,10 +149,14 @@ __global__ void __launch_bounds__(256) centre_rows_kernel(const int8_t* __restri
 
 }  // namespace
 
-cudaError_t tb_launch_gather(const int8_t* d_x, int ldn, const int* d_idx, const long long* d_off, int w0, int W,
+cudaError_t tb_launch_gather(const TbGeno& g, const int* d_idx, const long long* d_off, int w0, int W,
                              int rpad, int kstride, int8_t* d_panel, cudaStream_t st) {
   dim3 grid(kstride / 128, rpad / 128, W);
-  gather_kernel<<<grid, 256, 0, st>>>(d_x, ldn, d_idx, d_off, w0, rpad, kstride, d_panel);
+  if (g.x2)
+    gather_kernel<true><<<grid, 256, 0, st>>>(reinterpret_cast<const int8_t*>(g.x2), g.ld4, d_idx, d_off, w0, rpad,
+                                              kstride, d_panel);
+  else
+    gather_kernel<false><<<grid, 256, 0, st>>>(g.x, g.ldn, d_idx, d_off, w0, rpad, kstride, d_panel);
   return cudaGetLastError();
 }
 

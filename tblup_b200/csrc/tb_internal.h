@@ -44,10 +44,22 @@ struct TbRowSet {
   bool contiguous = false;      // training animal b sits at universe position b
 };
 
+// resident genotypes as the kernels see them: exactly one of x (int8 dosages, [m][ldn]) and x2 (2-bit packed,
+// [m][ld4], ld4 = ldn / 4, animal 4q + i of a marker in bits 2i..2i+1 of byte q) is non-null
+struct TbGeno {
+  const int8_t* x;
+  int ldn;
+  const uint8_t* x2;
+  int ld4;
+};
+
 struct TbCtx {
   int device = 0;
   int n = 0, m = 0, ldn = 0;
-  int8_t* d_x = nullptr;          // [m][ldn] SNP-major dosages, animals in universe order
+  int8_t* d_x = nullptr;          // [m][ldn] SNP-major dosages, animals in universe order (storage 0)
+  uint8_t* d_x2 = nullptr;        // [m][ldn / 4] the same matrix at 2 bits per dosage (storage 1; d_x is then freed)
+  int storage = 0;
+  TbGeno geno() const { return TbGeno{d_x, ldn, d_x2, ldn / 4}; }
   int* d_colsum_all = nullptr;    // [m]
   std::vector<double> y_univ;     // phenotypes in universe order
   std::vector<int> pos_of;        // original animal index -> universe position
@@ -119,11 +131,13 @@ __host__ __device__ static inline int tb_round_up(int x, int q) { return (x + q 
 // ingest.cu
 cudaError_t tb_launch_transpose_rows(const int8_t* d_rows, int n_rows, int m, int8_t* d_x, int ldn, int pos0,
                                      cudaStream_t st);
-cudaError_t tb_launch_colsum(const int8_t* d_x, int ldn, int m, const int* d_pos, int n_pos, int* d_colsum,
-                             cudaStream_t st);
+cudaError_t tb_launch_colsum(const TbGeno& g, int m, const int* d_pos, int n_pos, int* d_colsum, cudaStream_t st);
+cudaError_t tb_launch_pack2(const int8_t* d_x, int ldn, int m, uint8_t* d_x2, cudaStream_t st);
+cudaError_t tb_launch_unpack2_perm(const uint8_t* d_rows2, int n_rows, int stride, const int* d_perm, int n,
+                                   int8_t* d_x, int ldn, int j0, int* d_bad, cudaStream_t st);
 
 // gather.cu
-cudaError_t tb_launch_gather(const int8_t* d_x, int ldn, const int* d_idx, const long long* d_off, int w0, int W,
+cudaError_t tb_launch_gather(const TbGeno& g, const int* d_idx, const long long* d_off, int w0, int W,
                              int rpad, int kstride, int8_t* d_panel, cudaStream_t st);
 cudaError_t tb_launch_centre_terms(const int8_t* d_panel, int rpad, int kstride, const int* d_idx,
                                    const long long* d_off, int w0, int W, int n_slots, const int* d_kblocks,

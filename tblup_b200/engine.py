@@ -16,6 +16,8 @@ MODE_AUTO, MODE_GBLUP, MODE_SNPBLUP = 0, 1, 2
 STAGES = ["h2d", "gather", "centre", "gram", "scale", "chol_update", "chol_panel", "solve", "d2h"]
 DBG_C, DBG_S, DBG_SQ, DBG_M, DBG_ALPHA, DBG_PRED, DBG_DIMS, DBG_L32, DBG_SWEEPS = range(9)
 PRECISION_MIXED, PRECISION_FP64 = 0, 1
+LAYOUT_INT8_ANIMAL_MAJOR, LAYOUT_PACKED2_SNP_MAJOR = 0, 1
+STORAGE = {"int8": 0, "packed2": 1}
 
 
 def as_dosage_int8(geno):
@@ -62,21 +64,32 @@ def pack_genomes(genomes, n_markers):
 class GblupEngine:
     """One data set on one GPU.  Not thread-safe (one host thread per context, like the C-ABI)."""
 
-    def __init__(self, geno, pheno, perm=None, device=0):
+    def __init__(self, geno, pheno, perm=None, device=0, storage="int8"):
+        """``geno``: dense dosages (animals x markers, any real dtype holding 0/1/2) or a
+        ``genoio.PackedGenotypes``; ``storage``: how the matrix stays resident in HBM, ``"int8"`` (one byte per
+        dosage) or ``"packed2"`` (2 bits per dosage, a quarter of the bytes; same results bit for bit)."""
+        from .genoio import PackedGenotypes
         self._lib = _lib.load()
         self._ctx = C.c_void_p()
-        g = as_dosage_int8(geno)
+        if storage not in STORAGE:
+            raise ValueError("storage must be 'int8' or 'packed2', got %r" % (storage,))
+        if isinstance(geno, PackedGenotypes):
+            g, layout, shape = geno.data, LAYOUT_PACKED2_SNP_MAJOR, geno.shape
+        else:
+            g, layout = as_dosage_int8(geno), LAYOUT_INT8_ANIMAL_MAJOR
+            shape = g.shape
         y = np.ascontiguousarray(np.asarray(pheno, dtype=np.float64).ravel())
-        if y.shape[0] != g.shape[0]:
-            raise ValueError("phenotype vector has %d entries for %d animals" % (y.shape[0], g.shape[0]))
-        self.n, self.m = g.shape
+        if y.shape[0] != shape[0]:
+            raise ValueError("phenotype vector has %d entries for %d animals" % (y.shape[0], shape[0]))
+        self.n, self.m = shape
+        self.storage = storage
         p = None
         if perm is not None:
             p = np.ascontiguousarray(np.asarray(perm, dtype=np.int32))
             if p.shape != (self.n,):
                 raise ValueError("perm must list every animal exactly once")
-        rc = self._lib.tb_create(g.ctypes.data, self.n, self.m, y.ctypes.data,
-                                 p.ctypes.data if p is not None else None, int(device), C.byref(self._ctx))
+        rc = self._lib.tb_create_ex(g.ctypes.data, layout, STORAGE[storage], self.n, self.m, y.ctypes.data,
+                                    p.ctypes.data if p is not None else None, int(device), C.byref(self._ctx))
         if rc != 0:
             self._ctx = C.c_void_p()
             raise RuntimeError("tb_create failed (%d): %s" % (rc, self._lib.tb_last_error(None).decode()))
@@ -211,6 +224,11 @@ class GblupEngine:
 
     def last_precision(self):
         return {0: "mixed", 1: "fp64"}[int(self._lib.tb_last_precision(self._ctx))]
+
+    def resident_genotype_bytes(self):
+        b = C.c_uint64(0)
+        self._check(self._lib.tb_storage_info(self._ctx, None, C.byref(b)), "tb_storage_info")
+        return int(b.value)
 
     def last_wave(self):
         return int(self._lib.tb_last_wave(self._ctx))

@@ -127,10 +127,18 @@ class BlupParallelEvaluator(ParallelEvaluator):
         self.snp_remover = snp_remover
         self.h2 = h2
         self.devices = list(devices) if devices is not None else _devices_from_env()
-        shape = np.load(data_path, mmap_mode="r").shape
-        self.n_samples, self.n_columns = shape[0], shape[1]
+        # how the genotypes stay resident in HBM: "int8" or "packed2" (2 bits per dosage; bit-identical results)
+        self.storage = os.environ.get("TBLUP_B200_STORAGE", "int8")
+        if str(data_path).endswith(".bed"):
+            # PLINK binary genotypes (not a reference format: its float64 .npy stops fitting in host memory long
+            # before the GPU is full); animals = length of the phenotype vector
+            self.n_samples = int(np.asarray(np.load(labels_path)).size)
+            self.n_columns = (os.path.getsize(data_path) - 3) // ((self.n_samples + 3) // 4)
+        else:
+            shape = np.load(data_path, mmap_mode="r").shape
+            self.n_samples, self.n_columns = shape[0], shape[1]
         if splitter:
-            self.training_indices, self.testing_indices = splitter(np.load(data_path))
+            self.training_indices, self.testing_indices = splitter(self._load_dense())
         else:
             shuffled = random.sample(range(self.n_samples), self.n_samples)
             self.training_indices, self.testing_indices = train_test_split(
@@ -139,17 +147,22 @@ class BlupParallelEvaluator(ParallelEvaluator):
             self.training_indices, train_size=self.TRAIN_VALID_SPLIT, test_size=1 - self.TRAIN_VALID_SPLIT)
 
     # ---- device lifetime ---------------------------------------------------------------------------------
+    def _load_dense(self):
+        """What the reference hands a custom splitter (evaluator.py:188): the dense matrix as float64."""
+        if str(self.data_path).endswith(".bed"):
+            from .genoio import read_bed
+            return read_bed(self.data_path, self.n_samples).unpack().astype(np.float64)
+        return np.load(self.data_path)
+
     def __enter__(self):
-        geno = np.load(self.data_path)
+        from .genoio import load_genotypes
+        geno = load_genotypes(self.data_path, self.n_samples)
         pheno = np.load(self.labels_path)
         order = np.concatenate((self.training_indices, self.validation_indices, self.testing_indices)).astype(np.int64)
         if len(np.unique(order)) != self.n_samples:      # a custom splitter may not cover every animal
             order = np.concatenate((order, np.setdiff1d(np.arange(self.n_samples), order)))
-        from .engine import as_dosage_int8
-        dosages = as_dosage_int8(geno)
-        del geno
         for device in self.devices:
-            self.consumers.append(GblupEngine(dosages, pheno, perm=order, device=device))
+            self.consumers.append(GblupEngine(geno, pheno, perm=order, device=device, storage=self.storage))
         self._define_rowsets()
         return self
 

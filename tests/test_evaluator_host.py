@@ -119,6 +119,22 @@ def test_evaluate_sets_fitness_and_archive(dataset):
     assert e.consumers == [] and OracleEngine.instances[0].closed
 
 
+def test_bed_input_and_packed_storage_reach_the_engine(dataset, tmp_path, monkeypatch):
+    """A PLINK .bed data path gives the same splits (same RNG consumption) and hands the engine the same dosages."""
+    from tblup_b200.genoio import pack_dosages, write_bed
+    g, geno, pheno, ev = dataset
+    bed = tmp_path / "geno.bed"
+    write_bed(str(bed), pack_dosages(g["x"]))
+    monkeypatch.setenv("TBLUP_B200_STORAGE", "packed2")
+    seeded(int(g["seed"]))
+    e = ev.BlupParallelEvaluator(str(bed), pheno, float(g["h2"]), snp_remover=ev.SNPRemovalHandler(10, 0.0, 0.4, False))
+    assert (e.n_samples, e.n_columns) == g["x"].shape
+    assert list(e.training_indices) == list(g["train"]) and list(e.testing_indices) == list(g["test"])
+    with e:
+        inst = OracleEngine.instances[-1]
+        assert inst.storage == "packed2" and np.array_equal(inst.x, g["x"])
+
+
 def test_cv_variants_pick_the_right_row_sets(dataset):
     g, geno, pheno, ev = dataset
     h2, nf = float(g["h2"]), int(g["n_folds"])
