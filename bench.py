@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--precision", default="mixed", choices=["mixed", "fp64"],
                     help="mixed: TF32 tensor-core Cholesky preconditioner + fp64 refinement (default); fp64: fp64 Cholesky")
-    ap.add_argument("--storage", default="int8", choices=["int8", "packed2"],
+    ap.add_argument("--storage", default="packed2", choices=["int8", "packed2"],
                     help="resident genotype format: int8 dosages, or 2 bits per dosage (bit-identical results)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="individuals in the CPU sample (default: one per core)")
     return ap.parse_args()

@@ -9,7 +9,7 @@ from tblup_b200 import GblupEngine, synth
 P = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 12
 prec = sys.argv[3] if len(sys.argv) > 3 else "mixed"
-storage = sys.argv[4] if len(sys.argv) > 4 else "int8"
+storage = sys.argv[4] if len(sys.argv) > 4 else "packed2"
 x, y = synth.synth_dataset(5000, 50000, seed=0)
 tr, va, te = synth.split_indices(5000, seed=0)
 eng = GblupEngine(x, y, perm=np.concatenate([tr, va, te]), storage=storage)

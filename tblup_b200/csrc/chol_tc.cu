@@ -38,7 +38,9 @@ constexpr int TA_BYTES = TBM * TBK * 4;          // 16 KiB
 constexpr int TB_BYTES_MAX = MAX_N * TBK * 4;    // 32 KiB
 constexpr int TSTAGE_BYTES = TA_BYTES + TB_BYTES_MAX;
 constexpr int TACC = 2;
-constexpr int T_THREADS = 192;
+constexpr int EPI_WARPS = 8;                    // two warps per TMEM lane quarter, each owning half of the columns
+constexpr int T_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int HBK = 64;              // halves per k-block when the operands are fp16 (same 128-byte span)
 constexpr int T_SMEM = TSTAGES * TSTAGE_BYTES + 1024 + 256;
 
 struct GemmParams {
@@ -81,12 +83,29 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       : "memory");
 }
 
+// fp16 operands, fp32 accumulation: the factor is rounded to 10 mantissa bits anyway, so its half-precision copy
+// carries the same values at half the bytes and the MMA runs at twice the TF32 rate.
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n) {
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 __device__ __forceinline__ float round_tf32(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return __uint_as_float(r);
 }
 
+template <bool F16>
 __global__ void __launch_bounds__(T_THREADS, 1)
 tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ GemmParams p) {
@@ -95,7 +114,8 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   TBarriers* bars = reinterpret_cast<TBarriers*>(smem + TSTAGES * TSTAGE_BYTES);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = p.n_jobs * p.n_mtiles;
-  const int nkb = p.K / TBK;
+  constexpr int KB_ELEMS = F16 ? HBK : TBK;       // elements per 128-byte k-block
+  const int nkb = p.K / KB_ELEMS;
   const int n_bbox = p.N / BOX_ROWS;
   const uint32_t stage_tx = TA_BYTES + n_bbox * BOX_BYTES;
 
@@ -108,7 +128,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int s = 0; s < TACC; ++s) {
       mbar_init(&bars->acc_full[s], 1);
-      mbar_init(&bars->acc_empty[s], 4);
+      mbar_init(&bars->acc_empty[s], EPI_WARPS);
     }
     fence_barrier_init();
   }
@@ -130,10 +150,10 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           mbar_wait(&bars->empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * TSTAGE_BYTES;
           mbar_arrive_expect_tx(&bars->full[stage], stage_tx);
-          tma_load_2d(sa, &tmap_a, &bars->full[stage], p.a_col0 + kb * TBK, row_a);
-          tma_load_2d(sa + BOX_BYTES, &tmap_a, &bars->full[stage], p.a_col0 + kb * TBK, row_a + BOX_ROWS);
+          tma_load_2d(sa, &tmap_a, &bars->full[stage], p.a_col0 + kb * KB_ELEMS, row_a);
+          tma_load_2d(sa + BOX_BYTES, &tmap_a, &bars->full[stage], p.a_col0 + kb * KB_ELEMS, row_a + BOX_ROWS);
           for (int b = 0; b < n_bbox; ++b)
-            tma_load_2d(sa + TA_BYTES + b * BOX_BYTES, &tmap_b, &bars->full[stage], p.b_col0 + kb * TBK,
+            tma_load_2d(sa + TA_BYTES + b * BOX_BYTES, &tmap_b, &bars->full[stage], p.b_col0 + kb * KB_ELEMS,
                         row_b + b * BOX_ROWS);
           if (++stage == TSTAGES) {
             stage = 0;
@@ -144,7 +164,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      const uint32_t idesc = umma_idesc_tf32(TBM, p.N);
+      const uint32_t idesc = F16 ? umma_idesc_f16(TBM, p.N) : umma_idesc_tf32(TBM, p.N);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -160,7 +180,10 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint64_t adesc = umma_desc_k_sw128(sa);
           const uint64_t bdesc = umma_desc_k_sw128(sa + TA_BYTES);
 #pragma unroll
-          for (int k = 0; k < TBK / 8; ++k) umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          for (int k = 0; k < 4; ++k) {          // four 32-byte K slices per 128-byte span (8 floats / 16 halves)
+            if (F16) umma_f16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            else umma_tf32(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
           umma_commit(&bars->empty[stage]);
           if (++stage == TSTAGES) {
             stage = 0;
@@ -175,47 +198,64 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else {
-    const int q = warp & 3;
+    // Epilogue: warp w reads TMEM lanes 32 (w & 3) .. +31 (one accumulator row per thread); the two warps of a lane
+    // quarter split the N columns.  In update mode the C values a thread will modify do not depend on the MMA, so
+    // all of its loads (up to 4 x 128 B) are issued BEFORE it waits for the accumulator: the read latency of the
+    // read-modify-write hides behind the tile's own MMA instead of serialising chunk by chunk.
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int nch = p.N / 64;                                   // 32-column chunks per warp (1 .. 4)
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int job = item / p.n_mtiles, mt = item - job * p.n_mtiles;
       const int r = p.row0 + mt * TBM + q * 32 + lane;          // row inside the job's matrix
       const int r_hi = p.row0 + mt * TBM + TBM - 1;
+      float* crow = p.L32 + ((size_t)job * p.ntp + (r < p.ntp ? r : 0)) * p.ntp + p.c_col0 + half * nch * 32;
+      const int col_base = p.c_col0 + half * nch * 32;
+      float4 cv[4][8];
+      if (p.mode == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i < nch && col_base + i * 32 <= r_hi && r < p.ntp) {
+            const float4* src = reinterpret_cast<const float4*>(crow + i * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) cv[i][j] = src[j];
+          }
+        }
+      }
       mbar_wait(&bars->acc_full[acc], acc_phase);
       tc_fence_after();
-      float* crow = p.L32 + ((size_t)job * p.ntp + (r < p.ntp ? r : 0)) * p.ntp + p.c_col0;
-#pragma unroll 1
-      for (int c = 0; c < p.N / 32; ++c) {
-        if (p.c_col0 + c * 32 > r_hi) continue;                  // strictly above the diagonal: never read
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (i >= nch || col_base + i * 32 > r_hi) continue;      // beyond N, or strictly above the diagonal
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * MAX_N + c * 32, v);
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * MAX_N + (half * nch + i) * 32, v);
         tmem_ld_wait();
         if (r < p.ntp) {
-          float4* dst = reinterpret_cast<float4*>(crow + c * 32);
+          float4* dst = reinterpret_cast<float4*>(crow + i * 32);
           if (p.mode == 0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 o = dst[i];
-              o.x -= __uint_as_float(v[4 * i]);
-              o.y -= __uint_as_float(v[4 * i + 1]);
-              o.z -= __uint_as_float(v[4 * i + 2]);
-              o.w -= __uint_as_float(v[4 * i + 3]);
-              dst[i] = o;
+            for (int j = 0; j < 8; ++j) {
+              float4 o = cv[i][j];
+              o.x -= __uint_as_float(v[4 * j]);
+              o.y -= __uint_as_float(v[4 * j + 1]);
+              o.z -= __uint_as_float(v[4 * j + 2]);
+              o.w -= __uint_as_float(v[4 * j + 3]);
+              dst[j] = o;
             }
           } else {
             float o[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] = round_tf32(__uint_as_float(v[i]));
+            for (int j = 0; j < 32; ++j) o[j] = round_tf32(__uint_as_float(v[j]));
 #pragma unroll
-            for (int i = 0; i < 8; ++i) dst[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+            for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
             if (p.L16) {
-              uint4* h = reinterpret_cast<uint4*>(p.L16 + ((size_t)job * p.ntp + r) * p.ntp + p.c_col0 + c * 32);
+              uint4* h = reinterpret_cast<uint4*>(p.L16 + ((size_t)job * p.ntp + r) * p.ntp + col_base + i * 32);
 #pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const __half2 h0 = __floats2half2_rn(o[8 * i], o[8 * i + 1]), h1 = __floats2half2_rn(o[8 * i + 2], o[8 * i + 3]);
-                const __half2 h2 = __floats2half2_rn(o[8 * i + 4], o[8 * i + 5]), h3 = __floats2half2_rn(o[8 * i + 6], o[8 * i + 7]);
-                h[i] = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+              for (int j = 0; j < 4; ++j) {
+                const __half2 h0 = __floats2half2_rn(o[8 * j], o[8 * j + 1]), h1 = __floats2half2_rn(o[8 * j + 2], o[8 * j + 3]);
+                const __half2 h2 = __floats2half2_rn(o[8 * j + 4], o[8 * j + 5]), h3 = __floats2half2_rn(o[8 * j + 6], o[8 * j + 7]);
+                h[j] = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
                                   *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
               }
             }
@@ -337,6 +377,21 @@ cudaError_t encode_f32(CUtensorMap* tm, const float* base, size_t cols, size_t r
   return cudaSuccess;
 }
 
+cudaError_t encode_f16(CUtensorMap* tm, const __half* base, size_t cols, size_t rows, std::string* err) {
+  const cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)cols * sizeof(__half)};
+  const cuuint32_t box[2] = {(cuuint32_t)HBK, (cuuint32_t)BOX_ROWS};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode32(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    if (err) *err = "cuTensorMapEncodeTiled(f16) failed with CUresult " + std::to_string((int)r);
+    return cudaErrorInvalidValue;
+  }
+  return cudaSuccess;
+}
+
 }  // namespace
 
 cudaError_t tb_chol_tc_init() {
@@ -348,7 +403,9 @@ cudaError_t tb_chol_tc_init() {
     if (!fn || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
     g_encode32 = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  return cudaFuncSetAttribute(tf32_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(tf32_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(tf32_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
 }
 
 // Factor every job's fp32 matrix in place.  L32: [n_jobs * ntp + 128 slack rows][ntp]; Linv32: [n_jobs * ntp][64].
@@ -363,6 +420,13 @@ cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, int* status,
   if (e != cudaSuccess) return e;
   e = encode_f32(&tm_inv, Linv32, (size_t)NB, (size_t)n_jobs * ntp, err);
   if (e != cudaSuccess) return e;
+  // updates (C -= A B^T with both operands finished columns of L) stream the half-precision copy of the factor
+  const bool upd16 = L16 != nullptr;
+  CUtensorMap tm_l16;
+  if (upd16) {
+    e = encode_f16(&tm_l16, static_cast<const __half*>(L16), (size_t)ntp, (size_t)n_jobs * ntp, err);
+    if (e != cudaSuccess) return e;
+  }
   auto gemm = [&](const CUtensorMap& tb, GemmParams p) -> cudaError_t {
     p.n_jobs = n_jobs;
     p.ntp = ntp;
@@ -372,7 +436,10 @@ cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, int* status,
     if (p.n_mtiles <= 0 || p.K <= 0) return cudaSuccess;
     const int items = n_jobs * p.n_mtiles;
     const int grid = items < n_sm ? items : n_sm;
-    tf32_gemm_kernel<<<grid, T_THREADS, T_SMEM, st>>>(tm_l, tb, p);
+    if (p.mode == 0 && upd16)
+      tf32_gemm_kernel<true><<<grid, T_THREADS, T_SMEM, st>>>(tm_l16, tm_l16, p);
+    else
+      tf32_gemm_kernel<false><<<grid, T_THREADS, T_SMEM, st>>>(tm_l, tb, p);
     launches[0]++;
     return cudaGetLastError();
   };

@@ -13,9 +13,6 @@ namespace {
 // 128 markers x 128 animals per block, transposed through shared memory as 32-bit words.
 // Word (jl, c) holds animals 4c..4c+3 of marker jl and is stored at column (c + (jl >> 2)) & 31,
 // which makes both the row-wise fill and the 4x4 byte-transposing drain bank-conflict free.
-// PACKED: the source row holds 2 bits per dosage; a lane's byte (four animals) expands to the same 32-bit word the
-// int8 source would have delivered, so everything after the load is shared.  A quarter of the read traffic.
-template <bool PACKED>
 __global__ void __launch_bounds__(256) gather_kernel(const int8_t* __restrict__ x, int ldn,
                                                      const int* __restrict__ idx, const long long* __restrict__ off,
                                                      int w0, int rpad, int kstride, int8_t* __restrict__ panel) {
@@ -33,12 +30,7 @@ __global__ void __launch_bounds__(256) gather_kernel(const int8_t* __restrict__ 
     uint32_t v = 0;
     if (j < k) {
       const int src = idx[o0 + j];
-      if (PACKED) {
-        const uint32_t b = reinterpret_cast<const uint8_t*>(x)[(size_t)src * ldn + (a0 >> 2) + lane];
-        v = (b | (b << 6) | (b << 12) | (b << 18)) & 0x03030303u;
-      } else {
-        v = *reinterpret_cast<const uint32_t*>(x + (size_t)src * ldn + a0 + lane * 4);
-      }
+      v = *reinterpret_cast<const uint32_t*>(x + (size_t)src * ldn + a0 + lane * 4);
     }
     tile[jl][(lane + (jl >> 2)) & 31] = v;
   }
@@ -66,6 +58,66 @@ __global__ void __launch_bounds__(256) gather_kernel(const int8_t* __restrict__ 
     dst[rs] = o_1;
     dst[2 * rs] = o_2;
     dst[3 * rs] = o_3;
+  }
+}
+
+// Gather from the 2-bit packed matrix, tile = (32 * MPL) markers x 512 animals.  The tile stays PACKED in shared
+// memory (128 B per marker = 512 animals), so a block moves four times the animals of gather_kernel per byte of
+// shared memory: every selected marker contributes one full 128-byte line per block (read side) and every animal row
+// receives 32 * MPL contiguous bytes per block (write side, 8- or 16-byte stores, a warp writes 256 / 512 B
+// contiguous) -- the large-granule access pattern HBM wants, at a quarter of the read traffic.
+// Word (jl, c) = animals 16c .. 16c+15 of marker jl sits at column (c + jl / MPL) & 31: the fill (lane = c) and the
+// drain (lane = marker group, fixed c) are both bank-conflict free.
+template <int MPL>
+__global__ void __launch_bounds__(256) gather_packed_kernel(const uint8_t* __restrict__ x2, int ld4,
+                                                            const int* __restrict__ idx, const long long* __restrict__ off,
+                                                            int w0, int rpad, int kstride, int8_t* __restrict__ panel) {
+  constexpr int TM = 32 * MPL;
+  extern __shared__ uint32_t ptile[];            // [TM][32]
+  const int w = blockIdx.z;
+  const long long o0 = off[w0 + w];
+  const int k = (int)(off[w0 + w + 1] - o0);
+  const int j0 = blockIdx.x * TM;
+  const int kpad = tb_round_up(k, TB_GRAM_BK);   // the Gram reads [0, kpad): zeros beyond k
+  if (j0 >= kpad) return;
+  const int a0 = blockIdx.y * 512;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool lane_in = (a0 >> 2) + 4 * lane < ld4;
+
+  for (int jb = warp * 8; jb < TM; jb += 64) {   // 8 rows per warp per round, loads issued together
+    int src[8];
+    uint32_t v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) src[u] = (j0 + jb + u < k) ? idx[o0 + j0 + jb + u] : -1;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      v[u] = (src[u] >= 0 && lane_in)
+                 ? *reinterpret_cast<const uint32_t*>(x2 + (size_t)src[u] * ld4 + (a0 >> 2) + 4 * lane) : 0u;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) ptile[(jb + u) * 32 + ((lane + (jb + u) / MPL) & 31)] = v[u];
+  }
+  __syncthreads();
+
+  const int jl0 = lane * MPL;                    // this lane's markers inside the tile
+  if (j0 + jl0 >= kpad) return;                  // (kpad is a multiple of 128 >= MPL: whole lanes)
+  for (int c = warp; c < 32; c += 8) {
+    if (a0 + 16 * c >= rpad) break;              // rpad is a multiple of 128: whole 16-animal groups
+    uint32_t wv[MPL];
+#pragma unroll
+    for (int t = 0; t < MPL; ++t) wv[t] = ptile[(jl0 + t) * 32 + ((c + lane) & 31)];
+    int8_t* dst = panel + ((size_t)w * rpad + a0 + 16 * c) * kstride + j0 + jl0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      uint32_t o[MPL / 4];
+#pragma unroll
+      for (int g = 0; g < MPL / 4; ++g)
+        o[g] = ((wv[4 * g] >> (2 * i)) & 3u) | (((wv[4 * g + 1] >> (2 * i)) & 3u) << 8) |
+               (((wv[4 * g + 2] >> (2 * i)) & 3u) << 16) | (((wv[4 * g + 3] >> (2 * i)) & 3u) << 24);
+      if (MPL == 8)
+        *reinterpret_cast<uint2*>(dst + (size_t)i * kstride) = make_uint2(o[0], o[1]);
+      else
+        *reinterpret_cast<uint4*>(dst + (size_t)i * kstride) = make_uint4(o[0], o[1], o[2 % (MPL / 4)], o[3 % (MPL / 4)]);
+    }
   }
 }
 
@@ -152,11 +204,12 @@ __global__ void __launch_bounds__(256) centre_rows_kernel(const int8_t* __restri
 cudaError_t tb_launch_gather(const TbGeno& g, const int* d_idx, const long long* d_off, int w0, int W,
                              int rpad, int kstride, int8_t* d_panel, cudaStream_t st) {
   dim3 grid(kstride / 128, rpad / 128, W);
-  if (g.x2)
-    gather_kernel<true><<<grid, 256, 0, st>>>(reinterpret_cast<const int8_t*>(g.x2), g.ld4, d_idx, d_off, w0, rpad,
-                                              kstride, d_panel);
-  else
-    gather_kernel<false><<<grid, 256, 0, st>>>(g.x, g.ldn, d_idx, d_off, w0, rpad, kstride, d_panel);
+  if (g.x2) {
+    constexpr int MPL = 8, TM = 32 * MPL;
+    dim3 pgrid((kstride + TM - 1) / TM, (rpad + 511) / 512, W);
+    gather_packed_kernel<MPL><<<pgrid, 256, TM * 128, st>>>(g.x2, g.ld4, d_idx, d_off, w0, rpad, kstride, d_panel);
+  } else
+    gather_kernel<<<grid, 256, 0, st>>>(g.x, g.ldn, d_idx, d_off, w0, rpad, kstride, d_panel);
   return cudaGetLastError();
 }
 

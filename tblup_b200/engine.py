@@ -64,7 +64,7 @@ def pack_genomes(genomes, n_markers):
 class GblupEngine:
     """One data set on one GPU.  Not thread-safe (one host thread per context, like the C-ABI)."""
 
-    def __init__(self, geno, pheno, perm=None, device=0, storage="int8"):
+    def __init__(self, geno, pheno, perm=None, device=0, storage="packed2"):
         """``geno``: dense dosages (animals x markers, any real dtype holding 0/1/2) or a
         ``genoio.PackedGenotypes``; ``storage``: how the matrix stays resident in HBM, ``"int8"`` (one byte per
         dosage) or ``"packed2"`` (2 bits per dosage, a quarter of the bytes; same results bit for bit)."""

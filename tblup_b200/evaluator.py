@@ -128,7 +128,7 @@ class BlupParallelEvaluator(ParallelEvaluator):
         self.h2 = h2
         self.devices = list(devices) if devices is not None else _devices_from_env()
         # how the genotypes stay resident in HBM: "int8" or "packed2" (2 bits per dosage; bit-identical results)
-        self.storage = os.environ.get("TBLUP_B200_STORAGE", "int8")
+        self.storage = os.environ.get("TBLUP_B200_STORAGE", "packed2")
         if str(data_path).endswith(".bed"):
             # PLINK binary genotypes (not a reference format: its float64 .npy stops fitting in host memory long
             # before the GPU is full); animals = length of the phenotype vector

@@ -9,7 +9,7 @@ from oracle import gblup_oracle as O
 class OracleEngine:
     instances = []
 
-    def __init__(self, geno, pheno, perm=None, device=0, storage="int8"):
+    def __init__(self, geno, pheno, perm=None, device=0, storage="packed2"):
         self.storage = storage
         self.x = (geno.unpack() if hasattr(geno, "unpack") else np.asarray(geno)).astype(np.int8)
         self.y = np.asarray(pheno, dtype=np.float64).ravel()
