@@ -15,6 +15,9 @@ tr, va, te = synth.split_indices(5000, seed=0)
 eng = GblupEngine(x, y, perm=np.concatenate([tr, va, te]), storage=storage)
 eng.set_rowset(0, tr, va)
 eng.set_precision(prec)
+for kv in os.environ.get("TB_OPTS", "").split(","):      # e.g. TB_OPTS=fuse_scale=0
+    if "=" in kv:
+        eng.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 stream = torch.cuda.current_stream()
 eng.set_stream(stream.cuda_stream)
 flat, off = synth.random_genomes(P, 50000, 5001, seed=1)

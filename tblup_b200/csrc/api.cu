@@ -161,6 +161,8 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
       per_ind += (size_t)max_ntp * max_ntp * (sizeof(float) + 2) + (size_t)max_ntp * TB_NB * sizeof(float) +
                  (size_t)(max_ntp + sv[s].rs->n_v) * sizeof(double) + 1024;
   }
+  // one contiguous row set: the Gram epilogue writes the fp32 matrix itself (no separate scaling pass over C)
+  const bool fuse_scale = mixed && n_slots == 1 && sv[0].rs->contiguous && c->n <= 46340 && c->fuse_scale;
   const int P = c->P;
   int kmax = 0;
   for (int i = 0; i < P; ++i) {
@@ -368,7 +370,8 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     sp = span_begin(c, TB_ST_GRAM);
     {
       std::string e;
-      cudaError_t ce = tb_launch_gram_tc(d_panel, Wc, rpad, kstride, d_kb, d_tiles, n_tiles, d_C, c->n_sm, st, &e);
+      cudaError_t ce = tb_launch_gram_tc(d_panel, Wc, rpad, kstride, d_kb, d_tiles, n_tiles, d_C, c->n_sm, st, &e,
+                                         fuse_scale ? d_scale : nullptr, d_L32, max_ntp);
       if (ce != cudaSuccess) return fail(c, "gram launch: " + (e.empty() ? std::string(cudaGetErrorString(ce)) : e), -2);
     }
     span_end(c, sp);
@@ -376,10 +379,12 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     if (c->stop_after == TB_ST_GRAM) continue;
 
     if (mixed) {
-      sp = span_begin(c, TB_ST_SCALE);
-      TB_CUDA(c, tb_launch_scale32(d_scale, n_jobs, max_ntp, d_L32, st));
-      span_end(c, sp);
-      count(c, TB_ST_SCALE, 1);
+      if (!fuse_scale) {
+        sp = span_begin(c, TB_ST_SCALE);
+        TB_CUDA(c, tb_launch_scale32(d_scale, n_jobs, max_ntp, d_L32, st));
+        span_end(c, sp);
+        count(c, TB_ST_SCALE, 1);
+      }
       if (c->stop_after == TB_ST_SCALE) continue;
       {
         int nl[2] = {0, 0};
@@ -857,6 +862,7 @@ int tb_set_option(tb_ctx* c, const char* name, long long value) {
   else if (s == "workspace_mb") c->ws_limit = value > 0 ? (size_t)value << 20 : 0;
   else if (s == "max_wave") c->max_wave = (int)value;
   else if (s == "precision") c->precision = value != 0;
+  else if (s == "fuse_scale") c->fuse_scale = value != 0;
   else if (s == "storage") return fail(c, "tb_set_option: storage is fixed at tb_create_ex");
   else return fail(c, "tb_set_option: unknown option '" + s + "'");
   return 0;

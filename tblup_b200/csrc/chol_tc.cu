@@ -41,7 +41,8 @@ constexpr int TACC = 2;
 constexpr int EPI_WARPS = 8;                    // two warps per TMEM lane quarter, each owning half of the columns
 constexpr int T_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int HBK = 64;              // halves per k-block when the operands are fp16 (same 128-byte span)
-constexpr int T_SMEM = TSTAGES * TSTAGE_BYTES + 1024 + 256;
+constexpr int T_STAGING = EPI_WARPS * 2048;       // per-warp transposition buffers (coalescing epilogue stores)
+constexpr int T_SMEM = TSTAGES * TSTAGE_BYTES + 1024 + 256 + T_STAGING;
 
 struct GemmParams {
   int n_jobs;
@@ -203,6 +204,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     // all of its loads (up to 4 x 128 B) are issued BEFORE it waits for the accumulator: the read latency of the
     // read-modify-write hides behind the tile's own MMA instead of serialising chunk by chunk.
     const int q = warp & 3, half = (warp - 2) >> 2;
+    const uint32_t stg = smem_u32(smem + TSTAGES * TSTAGE_BYTES + 256) + (warp - 2) * 2048;
     const int nch = p.N / 64;                                   // 32-column chunks per warp (1 .. 4)
     int acc = 0;
     uint32_t acc_phase = 0;
@@ -225,41 +227,58 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       mbar_wait(&bars->acc_full[acc], acc_phase);
       tc_fence_after();
+      // stores go through the per-warp staging buffer (tb_ptx.cuh): 8 rows x 64 contiguous bytes per instruction
+      const int rw0 = p.row0 + mt * TBM + q * 32;               // first row of this warp
+      float* wbase = p.L32 + ((size_t)job * p.ntp + rw0) * p.ntp + col_base;
+      const int rl = lane >> 2, gl = 4 * (lane & 3);
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         if (i >= nch || col_base + i * 32 > r_hi) continue;      // beyond N, or strictly above the diagonal
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * MAX_N + (half * nch + i) * 32, v);
         tmem_ld_wait();
-        if (r < p.ntp) {
-          float4* dst = reinterpret_cast<float4*>(crow + i * 32);
-          if (p.mode == 0) {
+        uint32_t o[32];
+        if (p.mode == 0) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 o = cv[i][j];
-              o.x -= __uint_as_float(v[4 * j]);
-              o.y -= __uint_as_float(v[4 * j + 1]);
-              o.z -= __uint_as_float(v[4 * j + 2]);
-              o.w -= __uint_as_float(v[4 * j + 3]);
-              dst[j] = o;
-            }
-          } else {
-            float o[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = round_tf32(__uint_as_float(v[j]));
-#pragma unroll
-            for (int j = 0; j < 8; ++j) dst[j] = make_float4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-            if (p.L16) {
-              uint4* h = reinterpret_cast<uint4*>(p.L16 + ((size_t)job * p.ntp + r) * p.ntp + col_base + i * 32);
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const __half2 h0 = __floats2half2_rn(o[8 * j], o[8 * j + 1]), h1 = __floats2half2_rn(o[8 * j + 2], o[8 * j + 3]);
-                const __half2 h2 = __floats2half2_rn(o[8 * j + 4], o[8 * j + 5]), h3 = __floats2half2_rn(o[8 * j + 6], o[8 * j + 7]);
-                h[j] = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
-                                  *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
-              }
-            }
+          for (int j = 0; j < 8; ++j) {
+            o[4 * j] = __float_as_uint(cv[i][j].x - __uint_as_float(v[4 * j]));
+            o[4 * j + 1] = __float_as_uint(cv[i][j].y - __uint_as_float(v[4 * j + 1]));
+            o[4 * j + 2] = __float_as_uint(cv[i][j].z - __uint_as_float(v[4 * j + 2]));
+            o[4 * j + 3] = __float_as_uint(cv[i][j].w - __uint_as_float(v[4 * j + 3]));
           }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(round_tf32(__uint_as_float(v[j])));
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          stage_write16(stg, lane, o + 16 * h);
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const uint4 u = stage_read16(stg, lane, it);
+            if (rw0 + 8 * it + rl < p.ntp)
+              *reinterpret_cast<uint4*>(wbase + (size_t)(8 * it + rl) * p.ntp + i * 32 + 16 * h + gl) = u;
+          }
+          __syncwarp();
+        }
+        if (p.mode != 0 && p.L16) {
+          uint32_t hv[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const __half2 hh = __floats2half2_rn(__uint_as_float(o[2 * j]), __uint_as_float(o[2 * j + 1]));
+            hv[j] = *reinterpret_cast<const uint32_t*>(&hh);
+          }
+          __half* hbase = p.L16 + ((size_t)job * p.ntp + rw0) * p.ntp + col_base + i * 32;
+          stage_write16(stg, lane, hv);
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const uint4 u = stage_read16(stg, lane, it);
+            if (rw0 + 8 * it + rl < p.ntp)
+              *reinterpret_cast<uint4*>(hbase + (size_t)(8 * it + rl) * p.ntp + 2 * gl) = u;
+          }
+          __syncwarp();
         }
       }
       tc_fence_before();

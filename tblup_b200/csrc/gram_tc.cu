@@ -10,7 +10,8 @@
 //   warp 1      MMA issuer     one thread issues tcgen05.mma.kind::i8 (M=128, N=256, K=32), s32 accumulators
 //                              in TMEM, two accumulator stages (2 x 256 columns) so the epilogue of tile t
 //                              overlaps the main loop of tile t+1
-//   warps 2..5  epilogue       tcgen05.ld 32x32b -> registers -> 16-byte global stores of the int32 tile
+//   warps 2..9  epilogue       tcgen05.ld 32x32b -> registers -> 16-byte global stores of the int32 tile
+//                              (optionally also the scaled fp32 matrix, see GramFuse)
 // Only tiles that touch the lower triangle are scheduled (tile list built on the host per row set).
 #include "tb_internal.h"
 #include "tb_ptx.cuh"
@@ -26,8 +27,22 @@ constexpr int B_BYTES = BN * BK;                 // 32 KiB
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 48 KiB
 constexpr int ACC_STAGES = 2;
 constexpr int TMEM_COLS = ACC_STAGES * BN;       // 512
-constexpr int NUM_THREADS = 192;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/;
+constexpr int EPI_WARPS = 8;                     // two per TMEM lane quarter, each owning half of the tile's columns
+constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
+constexpr int COLTERM_BYTES = 2 * BN * 8;         // fused scaling: two buffers of per-column integer terms
+constexpr int STAGING_BYTES = EPI_WARPS * 2048;   // per-warp transposition buffers of the coalescing epilogue
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + COLTERM_BYTES +
+                           STAGING_BYTES;
+
+// Fused scaling (mixed-precision path, one contiguous row set): besides the raw int32 cross-products the epilogue
+// writes the fp32 matrix the tensor-core Cholesky factors, A = G_tt + lambda I, straight from the accumulator:
+//   A_ab = (float)(N^2 C_ab - N s_a + (Q - N s_b)) * 2/den  (+ lambda on the diagonal),  identity padding,
+// the arithmetic of scale32_kernel (solve_mixed.cu) without re-reading C from HBM.
+struct GramFuse {
+  const TbScaleJob* jobs;   // [W] (one row set): s, SQ, N, n_t, ntp, lambda
+  float* L32;               // [W][ntp_all][ntp_all]
+  int ntp_all;
+};
 constexpr uint32_t IDESC = umma_idesc_s8(BM, BN);
 
 struct Barriers {
@@ -38,9 +53,10 @@ struct Barriers {
   uint32_t tmem_base;
 };
 
+template <bool FUSE>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int* __restrict__ tiles, int n_tiles,
-               const int* __restrict__ kblocks, int W, int rpad, int32_t* __restrict__ C) {
+               const int* __restrict__ kblocks, int W, int rpad, int32_t* __restrict__ C, const GramFuse fz) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Barriers* bars = reinterpret_cast<Barriers*>(smem + STAGES * STAGE_BYTES);
@@ -56,7 +72,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int* __restrict__
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(&bars->acc_full[s], 1);
-      mbar_init(&bars->acc_empty[s], 4);   // one arrival per epilogue warp
+      mbar_init(&bars->acc_empty[s], EPI_WARPS);   // one arrival per epilogue warp
     }
     fence_barrier_init();
   }
@@ -128,29 +144,106 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int* __restrict__
       }
     }
   } else {
-    // ===================== epilogue (4 warps) =====================
+    // ===================== epilogue (8 warps) =====================
     const int q = warp & 3;   // TMEM lane quarter this warp may access
+    const int chalf = (warp - 2) >> 2;   // which half of the tile's 32-column chunks
     int acc = 0;
     uint32_t acc_phase = 0;
+    const uint32_t colterm = smem_u32(smem + STAGES * STAGE_BYTES + 256);     // [2][BN] doubles
+    const uint32_t stg = smem_u32(smem + STAGES * STAGE_BYTES + 256 + COLTERM_BYTES) + (warp - 2) * 2048;
+    int fbuf = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int w = item / n_tiles, t = tiles[item - w * n_tiles];
       const int ti = t >> 16, tj = t & 0xffff;
       const int row = ti * BM + q * 32 + lane;
       const int row_hi = ti * BM + BM - 1;
+      // ---- fused scaling: per-tile terms, prepared while the tile's MMAs run
+      bool a_tile = false;
+      int f_nt = 0, f_ntp = 0;
+      double f_NN = 0.0, f_rowterm = 0.0;
+      float f_inv = 0.f, f_lam = 0.f;
+      uint32_t ct = 0;
+      if (FUSE) {
+        const TbScaleJob& jb = fz.jobs[w];
+        f_ntp = jb.ntp;
+        f_nt = jb.n_t;
+        a_tile = ti * BM < f_ntp && tj * BN < f_ntp;      // uniform over the four epilogue warps
+        if (a_tile) {
+          const long long N = jb.N, S = jb.SQ[0], Q = jb.SQ[1];
+          // every integer below stays under 2^53 (N <= 46 340, C <= 4 k), so the fp64 arithmetic is exact
+          f_NN = (double)(N * N);
+          f_inv = (float)(2.0 / (double)(2 * N * S - Q));
+          f_lam = (float)jb.lambda;
+          const uint32_t cw = colterm + fbuf * BN * 8;
+          for (int e = threadIdx.x - 64; e < BN; e += 32 * EPI_WARPS) {
+            const int b = tj * BN + e;
+            const double term = b < f_nt ? (double)(Q - N * jb.s[b]) : 0.0;
+            asm volatile("st.shared.f64 [%0], %1;" ::"r"(cw + e * 8), "d"(term) : "memory");
+          }
+          f_rowterm = row < f_nt ? (double)(-N * jb.s[row]) : 0.0;
+          ct = cw;
+          fbuf ^= 1;
+          // the buffer written two A-tiles ago is free again: every warp passed this barrier once since
+          asm volatile("bar.sync 1, %0;" ::"n"(32 * EPI_WARPS) : "memory");
+        }
+      }
       mbar_wait(&bars->acc_full[acc], acc_phase);
       tc_fence_after();
-      int32_t* crow = C + ((size_t)w * rpad + row) * rpad;
+      // the warp's 32 rows; stores go through the staging buffer so that every instruction writes whole sectors
+      int32_t* cwarp = C + ((size_t)w * rpad + ti * BM + q * 32) * rpad;
+      float* awarp = (FUSE && a_tile) ? fz.L32 + ((size_t)w * fz.ntp_all + ti * BM + q * 32) * fz.ntp_all : nullptr;
+      const int rl = lane >> 2, gl = 4 * (lane & 3);          // read-back role: row 8 it + rl, words gl .. gl + 3
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
         const int col0 = tj * BN + c * 32;
         if (col0 >= rpad || col0 > row_hi) continue;   // outside the matrix / strictly above the diagonal
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, v);
         tmem_ld_wait();
-        int4* dst = reinterpret_cast<int4*>(crow + col0);
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          dst[i] = make_int4((int)v[4 * i], (int)v[4 * i + 1], (int)v[4 * i + 2], (int)v[4 * i + 3]);
+        for (int h = 0; h < 2; ++h) {
+          stage_write16(stg, lane, v + 16 * h);
+          __syncwarp();
+#pragma unroll
+          for (int it = 0; it < 4; ++it) {
+            const uint4 u = stage_read16(stg, lane, it);
+            *reinterpret_cast<uint4*>(cwarp + (size_t)(8 * it + rl) * rpad + col0 + 16 * h + gl) = u;
+          }
+          __syncwarp();
+        }
+        if (FUSE && a_tile && col0 < f_ntp) {
+          uint32_t o[32];
+          double cterm[32];
+#pragma unroll
+          for (int e = 0; e < 32; e += 2)
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
+                         : "=d"(cterm[e]), "=d"(cterm[e + 1])
+                         : "r"(ct + (c * 32 + e) * 8));
+#pragma unroll
+          for (int e = 0; e < 32; ++e) {
+            const int b = col0 + e;
+            // exact integer numerator N^2 C - N s_a + (Q - N s_b) held in fp64, ONE rounding to fp32, one fp32
+            // multiply.  Columns b >= n_t only occur above the diagonal of a training row (never read).
+            const double num = fma((double)(int)v[e], f_NN, f_rowterm + cterm[e]);
+            float g = (float)num * f_inv;
+            if (b == row) g += f_lam;
+            if (row >= f_nt) g = b == row ? 1.f : 0.f;      // identity padding rows
+            o[e] = __float_as_uint(g);
+          }
+          const int arow0 = ti * BM + q * 32;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            stage_write16(stg, lane, o + 16 * h);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const uint4 u = stage_read16(stg, lane, it);
+              if (arow0 + 8 * it + rl < f_ntp)
+                *reinterpret_cast<uint4*>(awarp + (size_t)(8 * it + rl) * fz.ntp_all + col0 + 16 * h + gl) = u;
+            }
+            __syncwarp();
+          }
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -186,13 +279,15 @@ cudaError_t tb_gram_tc_init() {
     if (!fn || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  return cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  cudaError_t e = cudaFuncSetAttribute(gram_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(gram_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
 }
 
 // d_panel must have (W * rpad + 128) rows of kstride bytes allocated (slack for the last B half-tile).
 cudaError_t tb_launch_gram_tc(const int8_t* d_panel, int W, int rpad, int kstride, const int* d_kblocks,
                               const int* d_tiles, int n_tiles, int32_t* d_C, int n_sm, cudaStream_t st,
-                              std::string* err) {
+                              std::string* err, const TbScaleJob* d_fuse_jobs, float* d_L32, int ntp_all) {
   CUtensorMap tmap;
   const cuuint64_t dims[2] = {(cuuint64_t)kstride, (cuuint64_t)W * rpad + 128};
   const cuuint64_t strides[1] = {(cuuint64_t)kstride};
@@ -207,6 +302,10 @@ cudaError_t tb_launch_gram_tc(const int8_t* d_panel, int W, int rpad, int kstrid
   }
   const int n_items = W * n_tiles;
   const int grid = n_items < n_sm ? n_items : n_sm;
-  gram_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmap, d_tiles, n_tiles, d_kblocks, W, rpad, d_C);
+  const GramFuse fz{d_fuse_jobs, d_L32, ntp_all};
+  if (d_fuse_jobs)
+    gram_tc_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmap, d_tiles, n_tiles, d_kblocks, W, rpad, d_C, fz);
+  else
+    gram_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmap, d_tiles, n_tiles, d_kblocks, W, rpad, d_C, fz);
   return cudaGetLastError();
 }

@@ -91,6 +91,7 @@ struct TbCtx {
   int max_wave = 0;
   int precision = 0;              // 0: mixed (TF32 tensor-core Cholesky + fp64 refinement) when possible, 1: fp64
   int last_mixed = 0;
+  int fuse_scale = 1;             // 1: Gram epilogue writes the fp32 matrix when the row set allows it
   int n_sm = 148;
   // layout of the last wave (for tb_debug_fetch)
   struct DbgLayout {
@@ -147,9 +148,13 @@ cudaError_t tb_launch_centre_terms(const int8_t* d_panel, int rpad, int kstride,
 
 // gram_tc.cu / gram_simt.cu
 cudaError_t tb_gram_tc_init();
+struct TbScaleJob;
+// d_fuse_jobs != nullptr (one contiguous row set, mixed precision): the epilogue also writes the fp32 matrix
+// A = G_tt + lambda I of every genome into d_L32 [W][ntp_all][ntp_all] (what tb_launch_scale32 would produce)
 cudaError_t tb_launch_gram_tc(const int8_t* d_panel, int W, int rpad, int kstride, const int* d_kblocks,
                               const int* d_tiles, int n_tiles, int32_t* d_C, int n_sm, cudaStream_t st,
-                              std::string* err);
+                              std::string* err, const TbScaleJob* d_fuse_jobs = nullptr, float* d_L32 = nullptr,
+                              int ntp_all = 0);
 cudaError_t tb_launch_gram_simt(const int8_t* d_panel, int W, int rpad, int kstride, const int* d_kblocks,
                                 int32_t* d_C, cudaStream_t st);
 

@@ -129,4 +129,32 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- coalescing epilogue stores ----------------------------------------------------------------
+// After tcgen05.ld.32x32b a thread holds consecutive columns of ONE row, so a direct 16-byte store per thread writes
+// 32 rows x 16 B per instruction (half sectors, the slowest pattern the L2 accepts).  These helpers bounce a
+// 32-row x 16-word block through a 2 KiB per-warp staging buffer so that each store instruction writes 8 rows x 64
+// contiguous bytes (whole sectors).  Granule (16 B) g of row t sits at position g ^ ((t >> 1) & 3): both the
+// row-wise write and the transposed read are bank-conflict free.  Callers __syncwarp() between write and read and
+// before reusing the buffer.
+// (explicit ld/st.shared on a 32-bit shared address: through a generic pointer the compiler emits generic LD/ST)
+__device__ __forceinline__ void stage_write16(uint32_t stg_addr, int lane, const uint32_t* v) {
+  const uint32_t base = stg_addr + lane * 64;
+  const int f = (lane >> 1) & 3;
+#pragma unroll
+  for (int g = 0; g < 4; ++g)
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(base + ((g ^ f) << 4)), "r"(v[4 * g]),
+                 "r"(v[4 * g + 1]), "r"(v[4 * g + 2]), "r"(v[4 * g + 3])
+                 : "memory");
+}
+// iteration it (0..3): lane reads granule (lane & 3) of row 8 it + (lane >> 2)
+__device__ __forceinline__ uint4 stage_read16(uint32_t stg_addr, int lane, int it) {
+  const int r = 8 * it + (lane >> 2), g = lane & 3;
+  uint4 u;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(u.x), "=r"(u.y), "=r"(u.z), "=r"(u.w)
+               : "r"(stg_addr + ((r * 4 + (g ^ ((r >> 1) & 3))) << 4))
+               : "memory");
+  return u;
+}
+
 }  // namespace tbptx
