@@ -159,6 +159,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     per_ind = 0;
     for (int s = 0; s < n_slots; ++s)
       per_ind += (size_t)max_ntp * max_ntp * (sizeof(float) + 2) + (size_t)max_ntp * TB_NB * sizeof(float) +
+                 (size_t)256 * 256 * sizeof(float) +
                  (size_t)(max_ntp + sv[s].rs->n_v) * sizeof(double) + 1024;
   }
   // one contiguous row set: the Gram epilogue writes the fp32 matrix itself (no separate scaling pass over C)
@@ -237,7 +238,9 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     float* d_L32 = nullptr;
     float* d_Linv32 = nullptr;
     unsigned short* d_L16 = nullptr;
+    float* d_Linv256 = nullptr;
     if (mixed) {
+      if (c->wide_panel) d_Linv256 = ar.take<float>((size_t)n_jobs * 256 * 256);
       d_L32 = ar.take<float>(((size_t)n_jobs * max_ntp + 128) * max_ntp);
       d_Linv32 = ar.take<float>((size_t)n_jobs * max_ntp * TB_NB);
       d_L16 = ar.take<unsigned short>((size_t)n_jobs * max_ntp * max_ntp);
@@ -390,7 +393,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
         int nl[2] = {0, 0};
         std::string e;
         MarkCtx mc{c, 0};
-        cudaError_t ce = tb_chol_tc_factor(d_L32, d_Linv32, d_L16, d_status, n_jobs, max_ntp, c->n_sm, st, nl, &e,
+        cudaError_t ce = tb_chol_tc_factor(d_L32, d_Linv32, d_L16, d_Linv256, d_status, n_jobs, max_ntp, c->n_sm, st, nl, &e,
                                            c->profile ? &mark_cb : nullptr, &mc);
         if (ce != cudaSuccess)
           return fail(c, "tensor-core Cholesky: " + (e.empty() ? std::string(cudaGetErrorString(ce)) : e), -2);
@@ -863,6 +866,7 @@ int tb_set_option(tb_ctx* c, const char* name, long long value) {
   else if (s == "max_wave") c->max_wave = (int)value;
   else if (s == "precision") c->precision = value != 0;
   else if (s == "fuse_scale") c->fuse_scale = value != 0;
+  else if (s == "wide_panel") c->wide_panel = value != 0;
   else if (s == "storage") return fail(c, "tb_set_option: storage is fixed at tb_create_ex");
   else return fail(c, "tb_set_option: unknown option '" + s + "'");
   return 0;

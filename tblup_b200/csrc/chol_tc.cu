@@ -48,7 +48,8 @@ struct GemmParams {
   int n_jobs;
   int ntp;           // rows (= columns) of every job's matrix; also rows per job in tensor map A
   int row0;          // first output row
-  int n_mtiles;      // ceil((ntp - row0) / 128)
+  int row_end;       // one past the last output row (<= ntp)
+  int n_mtiles;      // ceil((row_end - row0) / 128)
   int a_col0;        // K range of the A operand: columns [a_col0, a_col0 + K)
   int K;             // multiple of 32
   int b_row0;        // first row of the B operand inside its job
@@ -212,13 +213,13 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int job = item / p.n_mtiles, mt = item - job * p.n_mtiles;
       const int r = p.row0 + mt * TBM + q * 32 + lane;          // row inside the job's matrix
       const int r_hi = p.row0 + mt * TBM + TBM - 1;
-      float* crow = p.L32 + ((size_t)job * p.ntp + (r < p.ntp ? r : 0)) * p.ntp + p.c_col0 + half * nch * 32;
+      float* crow = p.L32 + ((size_t)job * p.ntp + (r < p.row_end ? r : 0)) * p.ntp + p.c_col0 + half * nch * 32;
       const int col_base = p.c_col0 + half * nch * 32;
       float4 cv[4][8];
       if (p.mode == 0) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          if (i < nch && col_base + i * 32 <= r_hi && r < p.ntp) {
+          if (i < nch && col_base + i * 32 <= r_hi && r < p.row_end) {
             const float4* src = reinterpret_cast<const float4*>(crow + i * 32);
 #pragma unroll
             for (int j = 0; j < 8; ++j) cv[i][j] = src[j];
@@ -257,7 +258,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const uint4 u = stage_read16(stg, lane, it);
-            if (rw0 + 8 * it + rl < p.ntp)
+            if (rw0 + 8 * it + rl < p.row_end)
               *reinterpret_cast<uint4*>(wbase + (size_t)(8 * it + rl) * p.ntp + i * 32 + 16 * h + gl) = u;
           }
           __syncwarp();
@@ -275,7 +276,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const uint4 u = stage_read16(stg, lane, it);
-            if (rw0 + 8 * it + rl < p.ntp)
+            if (rw0 + 8 * it + rl < p.row_end)
               *reinterpret_cast<uint4*>(hbase + (size_t)(8 * it + rl) * p.ntp + 2 * gl) = u;
           }
           __syncwarp();
@@ -375,6 +376,118 @@ __global__ void __launch_bounds__(256) chol_diag32_kernel(float* __restrict__ L3
   if (tid == 0 && bad) status[job] = 1;
 }
 
+// Inverse of the 256 x 256 lower-triangular diagonal block of the factor, from its 64 x 64 blocks and the inverses of
+// its four diagonal blocks (chol_diag32_kernel):   X_bb = Linv_b,   X_ib = -Linv_i * sum_{k=b}^{i-1} L_ik X_kb  (i > b).
+// With X = L_JJ^-1 the whole panel below the diagonal block is ONE tensor-core GEMM, L[:, J] = T[:, J] X^T (K = 256),
+// instead of four narrow triangular-solve / update rounds over all rows.  One CTA per job; the 64^3 block products
+// run on mma.sync m16n8k8 TF32 (every operand is already rounded to TF32; X is rounded on the way out).
+constexpr int XS_LD = 72, AS_LD = 68;     // smem strides: conflict-free B[k][n] and A[m][k] fragment loads
+constexpr int TRINV_SMEM = (4 * 64 * XS_LD + 64 * AS_LD + 64 * XS_LD) * 4;
+
+__device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, "
+      "{%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+// acc[nt] (16 x 8 fragments, nt = 0..3) += As[64][AS_LD] (rows 16 (warp & 3) ..) * Bs[64][XS_LD] (cols 32 (warp >> 2) ..)
+__device__ __forceinline__ void block_mma(float (&acc)[4][4], const float* As, const float* Bs, int warp, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const float* a_base = As + (16 * (warp & 3) + g) * AS_LD + t;
+  const float* b_base = Bs + t * XS_LD + 32 * (warp >> 2) + g;
+#pragma unroll
+  for (int k = 0; k < 64; k += 8) {
+    uint32_t a[4];
+    a[0] = __float_as_uint(a_base[k]);
+    a[1] = __float_as_uint(a_base[8 * AS_LD + k]);
+    a[2] = __float_as_uint(a_base[k + 4]);
+    a[3] = __float_as_uint(a_base[8 * AS_LD + k + 4]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      uint32_t b[2];
+      b[0] = __float_as_uint(b_base[k * XS_LD + 8 * nt]);
+      b[1] = __float_as_uint(b_base[(k + 4) * XS_LD + 8 * nt]);
+      mma_tf32_16x8x8(acc[nt], a, b);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) trinv256_kernel(const float* __restrict__ L32, const float* __restrict__ Linv32,
+                                                       float* __restrict__ Linv256, int ntp, int c0) {
+  extern __shared__ float tsm[];
+  float* Xs = tsm;                       // [4][64][XS_LD]  X_kb of the current block column b
+  float* As = Xs + 4 * 64 * XS_LD;       // [64][AS_LD]     left operand
+  float* Ss = As + 64 * AS_LD;           // [64][XS_LD]     sum_k L_ik X_kb
+  const int job = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const float* Lj = L32 + ((size_t)job * ntp + c0) * ntp + c0;
+  const float* Dj = Linv32 + ((size_t)job * ntp + c0) * NB;
+  float* Out = Linv256 + (size_t)job * 256 * 256;
+  const int g = lane >> 2, t = lane & 3;
+  const int frow = 16 * (warp & 3) + g, fcol = 32 * (warp >> 2) + 2 * t;    // this thread's fragment origin
+
+  // 64 x 64 block, row stride ld_src, into smem with row stride ld_dst (16-byte loads, coalesced rows)
+  auto load_block = [&](const float* src, size_t ld_src, float* dst, int ld_dst) {
+    for (int e = tid; e < 64 * 16; e += 256) {
+      const int r = e >> 4, c4 = (e & 15) * 4;
+      const float4 v = *reinterpret_cast<const float4*>(src + (size_t)r * ld_src + c4);
+      *reinterpret_cast<float4*>(dst + r * ld_dst + c4) = v;
+    }
+  };
+  for (int b = 0; b < 4; ++b) {
+    // the blocks above the diagonal of X are zero (the GEMM reads the full 256 x 256 operand)
+    for (int i = 0; i < b; ++i)
+      for (int e = tid; e < 64 * 16; e += 256)
+        *reinterpret_cast<float4*>(Out + (size_t)(64 * i + (e >> 4)) * 256 + 64 * b + (e & 15) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+    load_block(Dj + (size_t)b * 64 * NB, NB, Xs + b * 64 * XS_LD, XS_LD);
+    __syncthreads();
+    for (int e = tid; e < 64 * 16; e += 256) {
+      const int r = e >> 4, c4 = (e & 15) * 4;
+      *reinterpret_cast<float4*>(Out + (size_t)(64 * b + r) * 256 + 64 * b + c4) =
+          *reinterpret_cast<const float4*>(Xs + b * 64 * XS_LD + r * XS_LD + c4);
+    }
+    for (int i = b + 1; i < 4; ++i) {
+      float acc[4][4];
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+      for (int k = b; k < i; ++k) {
+        load_block(Lj + (size_t)(64 * i) * ntp + 64 * k, ntp, As, AS_LD);
+        __syncthreads();
+        block_mma(acc, As, Xs + k * 64 * XS_LD, warp, lane);
+        __syncthreads();
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        *reinterpret_cast<float2*>(Ss + frow * XS_LD + fcol + 8 * nt) = make_float2(round_tf32(acc[nt][0]), round_tf32(acc[nt][1]));
+        *reinterpret_cast<float2*>(Ss + (frow + 8) * XS_LD + fcol + 8 * nt) = make_float2(round_tf32(acc[nt][2]), round_tf32(acc[nt][3]));
+      }
+      load_block(Dj + (size_t)i * 64 * NB, NB, As, AS_LD);
+      __syncthreads();
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+      block_mma(acc, As, Ss, warp, lane);
+      float* Xi = Xs + i * 64 * XS_LD;
+      float* Oi = Out + (size_t)(64 * i) * 256 + 64 * b;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float2 lo = make_float2(round_tf32(-acc[nt][0]), round_tf32(-acc[nt][1]));
+        const float2 hi = make_float2(round_tf32(-acc[nt][2]), round_tf32(-acc[nt][3]));
+        *reinterpret_cast<float2*>(Xi + frow * XS_LD + fcol + 8 * nt) = lo;
+        *reinterpret_cast<float2*>(Xi + (frow + 8) * XS_LD + fcol + 8 * nt) = hi;
+        *reinterpret_cast<float2*>(Oi + (size_t)frow * 256 + fcol + 8 * nt) = lo;
+        *reinterpret_cast<float2*>(Oi + (size_t)(frow + 8) * 256 + fcol + 8 * nt) = hi;
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -424,21 +537,26 @@ cudaError_t tb_chol_tc_init() {
   }
   cudaError_t e = cudaFuncSetAttribute(tf32_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(trinv256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRINV_SMEM);
+  if (e != cudaSuccess) return e;
   return cudaFuncSetAttribute(tf32_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
 }
 
 // Factor every job's fp32 matrix in place.  L32: [n_jobs * ntp + 128 slack rows][ntp]; Linv32: [n_jobs * ntp][64].
 // L16 (optional): [n_jobs * ntp][ntp] halves, receives a half-precision copy of the factor.
 // launches[0] / launches[1] receive the number of GEMM / diagonal-block kernel launches.
-cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, int* status, int n_jobs, int ntp, int n_sm,
-                              cudaStream_t st,
-                              int* launches, std::string* err,
+cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, float* Linv256, int* status, int n_jobs, int ntp,
+                              int n_sm, cudaStream_t st, int* launches, std::string* err,
                               void (*mark)(void*, int, int), void* mark_ctx) {
-  CUtensorMap tm_l, tm_inv;
+  CUtensorMap tm_l, tm_inv, tm_inv256;
   cudaError_t e = encode_f32(&tm_l, L32, (size_t)ntp, (size_t)n_jobs * ntp + 128, err);
   if (e != cudaSuccess) return e;
   e = encode_f32(&tm_inv, Linv32, (size_t)NB, (size_t)n_jobs * ntp, err);
   if (e != cudaSuccess) return e;
+  if (Linv256) {
+    e = encode_f32(&tm_inv256, Linv256, 256, (size_t)n_jobs * 256, err);
+    if (e != cudaSuccess) return e;
+  }
   // updates (C -= A B^T with both operands finished columns of L) stream the half-precision copy of the factor
   const bool upd16 = L16 != nullptr;
   CUtensorMap tm_l16;
@@ -451,7 +569,8 @@ cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, int* status,
     p.ntp = ntp;
     p.L32 = L32;
     p.L16 = static_cast<__half*>(L16);
-    p.n_mtiles = (ntp - p.row0 + TBM - 1) / TBM;
+    if (p.row_end <= 0 || p.row_end > ntp) p.row_end = ntp;
+    p.n_mtiles = (p.row_end - p.row0 + TBM - 1) / TBM;
     if (p.n_mtiles <= 0 || p.K <= 0) return cudaSuccess;
     const int items = n_jobs * p.n_mtiles;
     const int grid = items < n_sm ? items : n_sm;
@@ -474,22 +593,35 @@ cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, int* status,
       if (mark) mark(mark_ctx, 0, 1);
     }
     if (mark) mark(mark_ctx, 1, 0);
+    // With the inverse of the whole diagonal block the rows below it need ONE GEMM (K = 256) instead of four narrow
+    // update / triangular-solve rounds; the narrow rounds then only cover the 256 rows of the diagonal block itself.
+    const bool wide = Linv256 != nullptr && w == OB && c0 + w < ntp;
+    const int narrow_end = wide ? c0 + w : ntp;
     for (int cc = c0; cc < c0 + w; cc += NB) {
       if (cc > c0) {
         GemmParams p{};
-        p.row0 = cc; p.a_col0 = c0; p.K = cc - c0; p.b_row0 = cc; p.b_col0 = c0; p.b_rows_per_job = ntp; p.c_col0 = cc;
-        p.N = NB; p.mode = 0;
+        p.row0 = cc; p.row_end = narrow_end; p.a_col0 = c0; p.K = cc - c0; p.b_row0 = cc; p.b_col0 = c0;
+        p.b_rows_per_job = ntp; p.c_col0 = cc; p.N = NB; p.mode = 0;
         if ((e = gemm(tm_l, p)) != cudaSuccess) return e;
       }
       chol_diag32_kernel<<<n_jobs, 256, DIAG32_SMEM, st>>>(L32, Linv32, static_cast<__half*>(L16), status, ntp, cc / NB);
       launches[1]++;
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
-      if (cc + NB < ntp) {
+      if (cc + NB < narrow_end) {
         GemmParams p{};
-        p.row0 = cc + NB; p.a_col0 = cc; p.K = NB; p.b_row0 = cc; p.b_col0 = 0; p.b_rows_per_job = ntp; p.c_col0 = cc;
-        p.N = NB; p.mode = 1;
+        p.row0 = cc + NB; p.row_end = narrow_end; p.a_col0 = cc; p.K = NB; p.b_row0 = cc; p.b_col0 = 0;
+        p.b_rows_per_job = ntp; p.c_col0 = cc; p.N = NB; p.mode = 1;
         if ((e = gemm(tm_inv, p)) != cudaSuccess) return e;
       }
+    }
+    if (wide) {
+      trinv256_kernel<<<n_jobs, 256, TRINV_SMEM, st>>>(L32, Linv32, Linv256, ntp, c0);
+      launches[1]++;
+      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      GemmParams p{};
+      p.row0 = c0 + w; p.a_col0 = c0; p.K = w; p.b_row0 = 0; p.b_col0 = 0; p.b_rows_per_job = 256; p.c_col0 = c0;
+      p.N = w; p.mode = 1;
+      if ((e = gemm(tm_inv256, p)) != cudaSuccess) return e;
     }
     if (mark) mark(mark_ctx, 1, 1);
   }

@@ -91,6 +91,7 @@ struct TbCtx {
   int max_wave = 0;
   int precision = 0;              // 0: mixed (TF32 tensor-core Cholesky + fp64 refinement) when possible, 1: fp64
   int last_mixed = 0;
+  int wide_panel = 1;             // 1: 256-wide panel solve through the inverse of the diagonal block (chol_tc.cu)
   int fuse_scale = 1;             // 1: Gram epilogue writes the fp32 matrix when the row set allows it
   int n_sm = 148;
   // layout of the last wave (for tb_debug_fetch)
@@ -226,9 +227,10 @@ cudaError_t tb_launch_solve_mixed(const TbSolveMixedJob* d_jobs, int n_jobs, int
                                   cudaStream_t st);
 cudaError_t tb_launch_scale32(const TbScaleJob* d_jobs, int n_jobs, int ntp, float* L32, cudaStream_t st);
 cudaError_t tb_chol_tc_init();
-cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, int* status, int n_jobs, int ntp, int n_sm,
-                              cudaStream_t st,
-                              int* launches, std::string* err, void (*mark)(void*, int, int), void* mark_ctx);
+// Linv256 (nullable): [n_jobs][256][256] scratch for the inverses of the 256-wide diagonal blocks (wide panel path)
+cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, float* Linv256, int* status, int n_jobs, int ntp,
+                              int n_sm, cudaStream_t st, int* launches, std::string* err,
+                              void (*mark)(void*, int, int), void* mark_ctx);
 
 // microbench.cu
 cudaError_t tb_microbench_dmma(int n_sm, cudaStream_t st, double* tflops);
