@@ -172,6 +172,9 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     kmax = std::max(kmax, k);
   }
   const int kstride_max = tb_round_up(kmax, TB_GRAM_BK);
+  // every cross-product is at most 4 k: int16 storage is exact for the whole batch when 4 kmax <= 32 767
+  const bool c16 = mixed && c->narrow_c && 4LL * kmax <= 32767;
+  c->last_c16 = c16 ? 1 : 0;
   per_ind += (size_t)rpad * kstride_max + (size_t)rpad * rpad * sizeof(int32_t) +
              (size_t)n_slots * (rpad + 2) * sizeof(long long) + (size_t)n_slots * kstride_max * sizeof(int) + 4096;
 
@@ -288,7 +291,8 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
         double* pj = ar.take<double>(rs->n_v);
         h_cs[cjob] = gblup ? c->d_colsum_all : rs->d_colsum_train;
         TbScaleJob& sj = h_scale[job];
-        sj.C = d_C + (size_t)w * rpad * rpad;
+        sj.C = c16 ? reinterpret_cast<const int32_t*>(reinterpret_cast<const int16_t*>(d_C) + (size_t)w * rpad * rpad)
+                   : d_C + (size_t)w * rpad * rpad;
         sj.s = d_s + (size_t)cjob * rpad;
         sj.SQ = d_SQ + (size_t)cjob * 2;
         sj.tpos = rs->d_tpos;
@@ -374,7 +378,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     {
       std::string e;
       cudaError_t ce = tb_launch_gram_tc(d_panel, Wc, rpad, kstride, d_kb, d_tiles, n_tiles, d_C, c->n_sm, st, &e,
-                                         fuse_scale ? d_scale : nullptr, d_L32, max_ntp);
+                                         fuse_scale ? d_scale : nullptr, d_L32, max_ntp, c16 ? 1 : 0);
       if (ce != cudaSuccess) return fail(c, "gram launch: " + (e.empty() ? std::string(cudaGetErrorString(ce)) : e), -2);
     }
     span_end(c, sp);
@@ -384,7 +388,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     if (mixed) {
       if (!fuse_scale) {
         sp = span_begin(c, TB_ST_SCALE);
-        TB_CUDA(c, tb_launch_scale32(d_scale, n_jobs, max_ntp, d_L32, st));
+        TB_CUDA(c, tb_launch_scale32(d_scale, n_jobs, max_ntp, d_L32, c16 ? 1 : 0, st));
         span_end(c, sp);
         count(c, TB_ST_SCALE, 1);
       }
@@ -402,7 +406,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
       }
       if (c->stop_after == TB_ST_CHOL_UPDATE || c->stop_after == TB_ST_CHOL_PANEL) continue;
       sp = span_begin(c, TB_ST_SOLVE);
-      TB_CUDA(c, tb_launch_solve_mixed(d_msolve, n_jobs, max_ntp, contig_all ? 1 : 0, st));
+      TB_CUDA(c, tb_launch_solve_mixed(d_msolve, n_jobs, max_ntp, contig_all ? 1 : 0, c16 ? 1 : 0, st));
       span_end(c, sp);
       count(c, TB_ST_SOLVE, 1);
       continue;
@@ -853,6 +857,15 @@ int tb_debug_fetch(tb_ctx* c, int what, int job, void* out, size_t nbytes) {
     default: return fail(c, "tb_debug_fetch: unknown item");
   }
   if (nbytes < need) return fail(c, "tb_debug_fetch: buffer too small (need " + std::to_string(need) + " bytes)");
+  if (what == TB_DBG_C && c->last_c16) {
+    // the wave stored int16 cross-products: widen to the int32 view the caller asked for
+    std::vector<int16_t> h((size_t)d.rpad * d.rpad);
+    const int16_t* src16 = reinterpret_cast<const int16_t*>(d.C) + (size_t)(job / d.n_slots) * d.rpad * d.rpad;
+    TB_CUDA(c, cudaMemcpy(h.data(), src16, h.size() * sizeof(int16_t), cudaMemcpyDeviceToHost));
+    int32_t* o = static_cast<int32_t*>(out);
+    for (size_t i = 0; i < h.size(); ++i) o[i] = h[i];
+    return 0;
+  }
   TB_CUDA(c, cudaMemcpy(out, src, need, cudaMemcpyDeviceToHost));
   return 0;
 }
@@ -867,6 +880,7 @@ int tb_set_option(tb_ctx* c, const char* name, long long value) {
   else if (s == "precision") c->precision = value != 0;
   else if (s == "fuse_scale") c->fuse_scale = value != 0;
   else if (s == "wide_panel") c->wide_panel = value != 0;
+  else if (s == "narrow_c") c->narrow_c = value != 0;
   else if (s == "storage") return fail(c, "tb_set_option: storage is fixed at tb_create_ex");
   else return fail(c, "tb_set_option: unknown option '" + s + "'");
   return 0;

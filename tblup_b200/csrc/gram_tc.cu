@@ -53,7 +53,9 @@ struct Barriers {
   uint32_t tmem_base;
 };
 
-template <bool FUSE>
+// C16: the cross-products are stored as int16 (the caller guarantees 4 k <= 32 767, so C_ab <= 4 k fits): half the
+// bytes for every later pass over C (scaling, refinement mat-vecs, predictions).  Row stride stays rpad ELEMENTS.
+template <bool FUSE, bool C16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int* __restrict__ tiles, int n_tiles,
                const int* __restrict__ kblocks, int W, int rpad, int32_t* __restrict__ C, const GramFuse fz) {
@@ -190,7 +192,9 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int* __restrict__
       mbar_wait(&bars->acc_full[acc], acc_phase);
       tc_fence_after();
       // the warp's 32 rows; stores go through the staging buffer so that every instruction writes whole sectors
-      int32_t* cwarp = C + ((size_t)w * rpad + ti * BM + q * 32) * rpad;
+      const size_t cwarp_off = ((size_t)w * rpad + ti * BM + q * 32) * rpad;
+      int32_t* cwarp = C + cwarp_off;
+      int16_t* cwarp16 = reinterpret_cast<int16_t*>(C) + cwarp_off;
       float* awarp = (FUSE && a_tile) ? fz.L32 + ((size_t)w * fz.ntp_all + ti * BM + q * 32) * fz.ntp_all : nullptr;
       const int rl = lane >> 2, gl = 4 * (lane & 3);          // read-back role: row 8 it + rl, words gl .. gl + 3
 #pragma unroll 1
@@ -200,16 +204,30 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int* __restrict__
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, v);
         tmem_ld_wait();
+        if (C16) {
+          uint32_t pk[16];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          stage_write16(stg, lane, v + 16 * h);
+          for (int e = 0; e < 16; ++e) pk[e] = (v[2 * e] & 0xffffu) | (v[2 * e + 1] << 16);
+          stage_write16(stg, lane, pk);
           __syncwarp();
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const uint4 u = stage_read16(stg, lane, it);
-            *reinterpret_cast<uint4*>(cwarp + (size_t)(8 * it + rl) * rpad + col0 + 16 * h + gl) = u;
+            *reinterpret_cast<uint4*>(cwarp16 + (size_t)(8 * it + rl) * rpad + col0 + 2 * gl) = u;
           }
           __syncwarp();
+        } else {
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            stage_write16(stg, lane, v + 16 * h);
+            __syncwarp();
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const uint4 u = stage_read16(stg, lane, it);
+              *reinterpret_cast<uint4*>(cwarp + (size_t)(8 * it + rl) * rpad + col0 + 16 * h + gl) = u;
+            }
+            __syncwarp();
+          }
         }
         if (FUSE && a_tile && col0 < f_ntp) {
           uint32_t o[32];
@@ -279,15 +297,21 @@ cudaError_t tb_gram_tc_init() {
     if (!fn || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
     g_encode = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  cudaError_t e = cudaFuncSetAttribute(gram_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(gram_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  cudaError_t e = cudaSuccess;
+  auto set = [&](const void* fn) {
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
+  };
+  set((const void*)gram_tc_kernel<false, false>);
+  set((const void*)gram_tc_kernel<true, false>);
+  set((const void*)gram_tc_kernel<false, true>);
+  set((const void*)gram_tc_kernel<true, true>);
+  return e;
 }
 
 // d_panel must have (W * rpad + 128) rows of kstride bytes allocated (slack for the last B half-tile).
 cudaError_t tb_launch_gram_tc(const int8_t* d_panel, int W, int rpad, int kstride, const int* d_kblocks,
                               const int* d_tiles, int n_tiles, int32_t* d_C, int n_sm, cudaStream_t st,
-                              std::string* err, const TbScaleJob* d_fuse_jobs, float* d_L32, int ntp_all) {
+                              std::string* err, const TbScaleJob* d_fuse_jobs, float* d_L32, int ntp_all, int c16) {
   CUtensorMap tmap;
   const cuuint64_t dims[2] = {(cuuint64_t)kstride, (cuuint64_t)W * rpad + 128};
   const cuuint64_t strides[1] = {(cuuint64_t)kstride};
@@ -303,9 +327,13 @@ cudaError_t tb_launch_gram_tc(const int8_t* d_panel, int W, int rpad, int kstrid
   const int n_items = W * n_tiles;
   const int grid = n_items < n_sm ? n_items : n_sm;
   const GramFuse fz{d_fuse_jobs, d_L32, ntp_all};
-  if (d_fuse_jobs)
-    gram_tc_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmap, d_tiles, n_tiles, d_kblocks, W, rpad, d_C, fz);
+  if (d_fuse_jobs && c16)
+    gram_tc_kernel<true, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmap, d_tiles, n_tiles, d_kblocks, W, rpad, d_C, fz);
+  else if (d_fuse_jobs)
+    gram_tc_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmap, d_tiles, n_tiles, d_kblocks, W, rpad, d_C, fz);
+  else if (c16)
+    gram_tc_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmap, d_tiles, n_tiles, d_kblocks, W, rpad, d_C, fz);
   else
-    gram_tc_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmap, d_tiles, n_tiles, d_kblocks, W, rpad, d_C, fz);
+    gram_tc_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmap, d_tiles, n_tiles, d_kblocks, W, rpad, d_C, fz);
   return cudaGetLastError();
 }

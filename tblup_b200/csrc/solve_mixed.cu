@@ -13,6 +13,7 @@
 // HBM-bound: per sweep the factor is streamed twice (fp32) and the lower triangle of C twice (int32).
 #include "tb_internal.h"
 #include <cuda_fp16.h>
+#include <type_traits>
 
 namespace {
 
@@ -57,6 +58,18 @@ __device__ __forceinline__ double dot4(const float4 l, const double* z) {
 __device__ __forceinline__ double dot4i(const int4 c, const double* z) {
   const double2 z0 = *reinterpret_cast<const double2*>(z), z1 = *reinterpret_cast<const double2*>(z + 2);
   return (double)c.x * z0.x + (double)c.y * z0.y + (double)c.z * z1.x + (double)c.w * z1.y;
+}
+
+// exact conversion of a non-negative integer below 2^32 without the (slow) I2F pipe: 2^52 + x is representable, so
+// placing x in the low mantissa word and subtracting 2^52 costs one fp64 add
+__device__ __forceinline__ double u2d(uint32_t x) { return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0; }
+
+// eight int16 cross-products (non-negative) against eight fp64 entries
+__device__ __forceinline__ double dot8s(const uint4 c, const double* z) {
+  const double2 z0 = *reinterpret_cast<const double2*>(z), z1 = *reinterpret_cast<const double2*>(z + 2);
+  const double2 z2 = *reinterpret_cast<const double2*>(z + 4), z3 = *reinterpret_cast<const double2*>(z + 6);
+  return (u2d(c.x & 0xffffu) * z0.x + u2d(c.x >> 16) * z0.y) + (u2d(c.y & 0xffffu) * z1.x + u2d(c.y >> 16) * z1.y) +
+         (u2d(c.z & 0xffffu) * z2.x + u2d(c.z >> 16) * z2.y) + (u2d(c.w & 0xffffu) * z3.x + u2d(c.w >> 16) * z3.y);
 }
 
 __device__ __forceinline__ double dot8h(const uint4 l, const double* z) {
@@ -193,12 +206,111 @@ __device__ void apply_minv(const __half* __restrict__ L, const float* __restrict
   }
 }
 
+// (C alpha)_a for contiguous training animals from int16 cross-products: the lower triangle is streamed once by
+// rows and once by columns with 16-byte loads (eight entries), four loads in flight per thread.
+__device__ void sym_matvec16(const int16_t* __restrict__ C, int rpad, int n_t, const double* alpha, double* work,
+                             double* part2) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int a = warp; a < n_t; a += ST / 32) {
+    const uint4* row = reinterpret_cast<const uint4*>(C + (size_t)a * rpad);
+    const int full = (a + 1) / 8;                   // 8-entry groups that lie entirely at or left of the diagonal
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+    int c = lane;
+    for (; c + 96 < full; c += 128) {
+      const uint4 v0 = row[c], v1 = row[c + 32], v2 = row[c + 64], v3 = row[c + 96];
+      d0 += dot8s(v0, alpha + 8 * c);
+      d1 += dot8s(v1, alpha + 8 * (c + 32));
+      d2 += dot8s(v2, alpha + 8 * (c + 64));
+      d3 += dot8s(v3, alpha + 8 * (c + 96));
+    }
+    for (; c + 32 < full; c += 64) {
+      const uint4 v0 = row[c], v1 = row[c + 32];
+      d0 += dot8s(v0, alpha + 8 * c);
+      d1 += dot8s(v1, alpha + 8 * (c + 32));
+    }
+    for (; c < full; c += 32) d2 += dot8s(row[c], alpha + 8 * c);
+    if (lane == 31 && 8 * full <= a) {              // the group that holds the diagonal (partial)
+      const uint4 v = row[full];
+      const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+      const int b = 8 * full;
+#pragma unroll
+      for (int e = 0; e < 8; ++e)
+        if (b + e <= a) d3 += u2d((wv[e >> 1] >> (16 * (e & 1))) & 0xffffu) * alpha[b + e];
+    }
+    const double d = warp_sum((d0 + d1) + (d2 + d3));
+    if (lane == 0) work[a] = d;
+  }
+  __syncthreads();
+  // columns: thread = 8 consecutive columns x one of 8 row groups (rows b = rg mod 8); the four row groups inside a
+  // warp are combined by shuffles, the two halves of the CTA through part2.  A thread starts at its first row
+  // below the diagonal of its own columns: at most one guarded load, nothing above the diagonal is read.
+  const int cgl = lane & 7, rsub = lane >> 3, cblk = warp & 7, rsup = warp >> 3;
+  const int rg = rsup * 4 + rsub;
+  for (int a0 = 0; a0 < n_t; a0 += 512) {
+    const int ca = a0 + 64 * cblk + 8 * cgl;
+    double acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.0;
+    auto add8 = [&](const uint4 v, const double w) {
+      acc[0] += u2d(v.x & 0xffffu) * w;
+      acc[1] += u2d(v.x >> 16) * w;
+      acc[2] += u2d(v.y & 0xffffu) * w;
+      acc[3] += u2d(v.y >> 16) * w;
+      acc[4] += u2d(v.z & 0xffffu) * w;
+      acc[5] += u2d(v.z >> 16) * w;
+      acc[6] += u2d(v.w & 0xffffu) * w;
+      acc[7] += u2d(v.w >> 16) * w;
+    };
+    if (ca < n_t) {
+      const int16_t* colp = C + ca;
+      int b = ca + 1 + rg;                          // rows ca + 1 + rg, + 8, ...: every row below the diagonal once
+      if (b < n_t && b <= ca + 7) {                 // crosses the 8 x 8 diagonal block: guard per column
+        const uint4 v = *reinterpret_cast<const uint4*>(colp + (size_t)b * rpad);
+        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
+        const double w = alpha[b];
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+          if (b > ca + e) acc[e] += u2d((wv[e >> 1] >> (16 * (e & 1))) & 0xffffu) * w;
+        b += 8;
+      }
+      for (; b + 24 < n_t; b += 32) {
+        const uint4 v0 = *reinterpret_cast<const uint4*>(colp + (size_t)b * rpad);
+        const uint4 v1 = *reinterpret_cast<const uint4*>(colp + (size_t)(b + 8) * rpad);
+        const uint4 v2 = *reinterpret_cast<const uint4*>(colp + (size_t)(b + 16) * rpad);
+        const uint4 v3 = *reinterpret_cast<const uint4*>(colp + (size_t)(b + 24) * rpad);
+        add8(v0, alpha[b]);
+        add8(v1, alpha[b + 8]);
+        add8(v2, alpha[b + 16]);
+        add8(v3, alpha[b + 24]);
+      }
+      for (; b < n_t; b += 8) add8(*reinterpret_cast<const uint4*>(colp + (size_t)b * rpad), alpha[b]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+    }
+    if (rsub == 0) {
+      double* pr = part2 + rsup * 512 + 64 * cblk + 8 * cgl;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) pr[e] = acc[e];
+    }
+    __syncthreads();
+    const int a = a0 + tid;
+    if (a < n_t) work[a] += part2[tid] + part2[512 + tid];
+    __syncthreads();
+  }
+}
+
 // (C alpha)_a over the training animals into work[a]; CONTIG: training animal b sits at universe position b.
-template <bool CONTIG>
-__device__ void sym_matvec(const int32_t* __restrict__ C, int rpad, int n_t, const int* tp, const double* alpha,
+// CT: element type of the stored cross-products (int32_t, or int16_t in C16 mode).
+template <bool CONTIG, typename CT>
+__device__ void sym_matvec(const CT* __restrict__ C, int rpad, int n_t, const int* tp, const double* alpha,
                            double* work, double* part2) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (CONTIG) {
+  if constexpr (CONTIG && sizeof(CT) == 2) {
+    sym_matvec16(reinterpret_cast<const int16_t*>(C), rpad, n_t, alpha, work, part2);
+  } else if constexpr (CONTIG) {
     // rows: (C alpha)_a += sum_{b <= a} C[a][b] alpha_b, 16-byte loads, four in flight
     for (int a = warp; a < n_t; a += ST / 32) {
       const int4* row = reinterpret_cast<const int4*>(C + (size_t)a * rpad);
@@ -319,8 +431,9 @@ __device__ void sym_matvec(const int32_t* __restrict__ C, int rpad, int n_t, con
   }
 }
 
-template <bool CONTIG, bool BIG>
+template <bool CONTIG, bool BIG, bool C16>
 __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJob* __restrict__ jobs) {
+  using CT = typename std::conditional<C16, int16_t, int32_t>::type;
   extern __shared__ double msm[];
   const TbSolveMixedJob jb = jobs[blockIdx.x];
   const int ntp = jb.ntp, n_t = jb.n_t, n_v = jb.n_v, rpad = jb.rpad;
@@ -347,7 +460,7 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const double Nd = (double)jb.N, Sd = (double)jb.SQ[0], Qd = (double)jb.SQ[1];
   const double coef = 2.0 / (2.0 * Nd * Sd - Qd);
-  const int32_t* C = jb.C;
+  const CT* C = reinterpret_cast<const CT*>(jb.C);
 
   for (int a = tid; a < ntp; a += ST) {
     if (tp_w) tp_w[a] = a < n_t ? jb.tpos[a] : 0;
@@ -369,7 +482,7 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
     sa = block_sum(l0, red);
     ssa = block_sum(l1, red);
     if (sweeps == MAX_SWEEPS) break;
-    sym_matvec<CONTIG>(C, rpad, n_t, tp, alpha, work, part2);      // work[a] = (C alpha)_a, a < n_t
+    sym_matvec<CONTIG, CT>(C, rpad, n_t, tp, alpha, work, part2);      // work[a] = (C alpha)_a, a < n_t
     for (int a = tid; a < ntp; a += ST) {
       double rr = 0.0;
       if (a < n_t) {
@@ -418,7 +531,27 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
   for (int v = warp; v < n_v; v += ST / 32) {
     const int pv = jb.vpos[v];
     double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
-    if (CONTIG && pv >= n_t) {
+    if constexpr (CONTIG && C16) {
+      if (pv >= n_t) {
+        const uint4* row = reinterpret_cast<const uint4*>(C + (size_t)pv * rpad);
+        const int n8 = n_t / 8;
+        int c = lane;
+        for (; c + 96 < n8; c += 128) {
+          const uint4 v0 = row[c], v1 = row[c + 32], v2 = row[c + 64], v3 = row[c + 96];
+          d0 += dot8s(v0, alpha + 8 * c);
+          d1 += dot8s(v1, alpha + 8 * (c + 32));
+          d2 += dot8s(v2, alpha + 8 * (c + 64));
+          d3 += dot8s(v3, alpha + 8 * (c + 96));
+        }
+        for (; c < n8; c += 32) d0 += dot8s(row[c], alpha + 8 * c);
+        for (int b = 8 * n8 + lane; b < n_t; b += 32) d1 += (double)C[(size_t)pv * rpad + b] * alpha[b];
+      } else {
+        for (int b = lane; b < n_t; b += 32) {
+          const int p0 = tp[b];
+          d0 += (double)C[(size_t)(pv > p0 ? pv : p0) * rpad + (pv > p0 ? p0 : pv)] * alpha[b];
+        }
+      }
+    } else if (CONTIG && !C16 && pv >= n_t) {
       const int4* row = reinterpret_cast<const int4*>(C + (size_t)pv * rpad);
       const int n4 = n_t / 4;
       int c = lane;
@@ -485,6 +618,7 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
 // independent.  fp32 output: exact int64 numerator, one fp64 multiply by 2/den (the exact operator lives in
 // solve_mixed_kernel, so no fp64 division is needed here).
 constexpr int S32_ROWS = 64;
+template <bool C16>
 __global__ void __launch_bounds__(256) scale32_kernel(const TbScaleJob* __restrict__ jobs, float* __restrict__ L32,
                                                       int ntp_all) {
   const TbScaleJob jb = jobs[blockIdx.z];
@@ -525,13 +659,20 @@ __global__ void __launch_bounds__(256) scale32_kernel(const TbScaleJob* __restri
     if (pr[h] >= 0 && c <= r) {
       sr[h] = jb.s[pr[h]];
       if (run && pc[3] < pr[h]) {
-        cv[h] = *reinterpret_cast<const int4*>(jb.C + (size_t)pr[h] * rpad + pc[0]);
+        if (C16) {
+          const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const int16_t*>(jb.C) + (size_t)pr[h] * rpad + pc[0]);
+          cv[h] = make_int4((int)(u.x & 0xffffu), (int)(u.x >> 16), (int)(u.y & 0xffffu), (int)(u.y >> 16));
+        } else {
+          cv[h] = *reinterpret_cast<const int4*>(jb.C + (size_t)pr[h] * rpad + pc[0]);
+        }
       } else {
         int t[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int hi = pr[h] > pc[i] ? pr[h] : pc[i], lo = pr[h] > pc[i] ? pc[i] : pr[h];
-          t[i] = creal[i] ? jb.C[(size_t)hi * rpad + lo] : 0;
+          t[i] = !creal[i] ? 0
+                 : C16 ? (int)reinterpret_cast<const int16_t*>(jb.C)[(size_t)hi * rpad + lo]
+                       : jb.C[(size_t)hi * rpad + lo];
         }
         cv[h] = make_int4(t[0], t[1], t[2], t[3]);
       }
@@ -579,10 +720,14 @@ cudaError_t tb_solve_mixed_init() {
   auto set = [&](const void* fn) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, g_solve_mixed_smem_max);
   };
-  set((const void*)solve_mixed_kernel<true, false>);
-  set((const void*)solve_mixed_kernel<false, false>);
-  set((const void*)solve_mixed_kernel<true, true>);
-  set((const void*)solve_mixed_kernel<false, true>);
+  set((const void*)solve_mixed_kernel<true, false, false>);
+  set((const void*)solve_mixed_kernel<false, false, false>);
+  set((const void*)solve_mixed_kernel<true, true, false>);
+  set((const void*)solve_mixed_kernel<false, true, false>);
+  set((const void*)solve_mixed_kernel<true, false, true>);
+  set((const void*)solve_mixed_kernel<false, false, true>);
+  set((const void*)solve_mixed_kernel<true, true, true>);
+  set((const void*)solve_mixed_kernel<false, true, true>);
   return e;
 }
 
@@ -590,20 +735,28 @@ bool tb_solve_mixed_fits(int ntp) { return solve_mixed_smem_bytes(ntp) <= 220 * 
 
 // contiguous != 0: every job's training animal b sits at universe position b and n_t is a multiple of 4
 // (vectorised symmetric mat-vec); otherwise positions are looked up per element.
-cudaError_t tb_launch_solve_mixed(const TbSolveMixedJob* d_jobs, int n_jobs, int ntp, int contiguous,
+cudaError_t tb_launch_solve_mixed(const TbSolveMixedJob* d_jobs, int n_jobs, int ntp, int contiguous, int c16,
                                   cudaStream_t st) {
   const int smem = solve_mixed_smem_bytes(ntp);
   if (smem > g_solve_mixed_smem_max) return cudaErrorInvalidConfiguration;
   const bool big = ntp > MIXED_SMEM_NTP;
-  if (contiguous && !big) solve_mixed_kernel<true, false><<<n_jobs, ST, smem, st>>>(d_jobs);
-  else if (!contiguous && !big) solve_mixed_kernel<false, false><<<n_jobs, ST, smem, st>>>(d_jobs);
-  else if (contiguous) solve_mixed_kernel<true, true><<<n_jobs, ST, smem, st>>>(d_jobs);
-  else solve_mixed_kernel<false, true><<<n_jobs, ST, smem, st>>>(d_jobs);
+  const int which = (contiguous ? 4 : 0) | (big ? 2 : 0) | (c16 ? 1 : 0);
+  switch (which) {
+    case 0: solve_mixed_kernel<false, false, false><<<n_jobs, ST, smem, st>>>(d_jobs); break;
+    case 1: solve_mixed_kernel<false, false, true><<<n_jobs, ST, smem, st>>>(d_jobs); break;
+    case 2: solve_mixed_kernel<false, true, false><<<n_jobs, ST, smem, st>>>(d_jobs); break;
+    case 3: solve_mixed_kernel<false, true, true><<<n_jobs, ST, smem, st>>>(d_jobs); break;
+    case 4: solve_mixed_kernel<true, false, false><<<n_jobs, ST, smem, st>>>(d_jobs); break;
+    case 5: solve_mixed_kernel<true, false, true><<<n_jobs, ST, smem, st>>>(d_jobs); break;
+    case 6: solve_mixed_kernel<true, true, false><<<n_jobs, ST, smem, st>>>(d_jobs); break;
+    default: solve_mixed_kernel<true, true, true><<<n_jobs, ST, smem, st>>>(d_jobs); break;
+  }
   return cudaGetLastError();
 }
 
-cudaError_t tb_launch_scale32(const TbScaleJob* d_jobs, int n_jobs, int ntp, float* L32, cudaStream_t st) {
+cudaError_t tb_launch_scale32(const TbScaleJob* d_jobs, int n_jobs, int ntp, float* L32, int c16, cudaStream_t st) {
   dim3 grid((ntp + 127) / 128, (ntp + S32_ROWS - 1) / S32_ROWS, n_jobs);
-  scale32_kernel<<<grid, 256, 0, st>>>(d_jobs, L32, ntp);
+  if (c16) scale32_kernel<true><<<grid, 256, 0, st>>>(d_jobs, L32, ntp);
+  else scale32_kernel<false><<<grid, 256, 0, st>>>(d_jobs, L32, ntp);
   return cudaGetLastError();
 }

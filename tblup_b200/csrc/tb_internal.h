@@ -91,6 +91,8 @@ struct TbCtx {
   int max_wave = 0;
   int precision = 0;              // 0: mixed (TF32 tensor-core Cholesky + fp64 refinement) when possible, 1: fp64
   int last_mixed = 0;
+  int narrow_c = 1;               // 1: int16 cross-products when every genome of the batch has 4 k <= 32 767
+  int last_c16 = 0;
   int wide_panel = 1;             // 1: 256-wide panel solve through the inverse of the diagonal block (chol_tc.cu)
   int fuse_scale = 1;             // 1: Gram epilogue writes the fp32 matrix when the row set allows it
   int n_sm = 148;
@@ -150,18 +152,19 @@ cudaError_t tb_launch_centre_terms(const int8_t* d_panel, int rpad, int kstride,
 // gram_tc.cu / gram_simt.cu
 cudaError_t tb_gram_tc_init();
 struct TbScaleJob;
+// c16 != 0: d_C receives int16 entries (row stride still rpad elements); the caller guarantees 4 k <= 32 767.
 // d_fuse_jobs != nullptr (one contiguous row set, mixed precision): the epilogue also writes the fp32 matrix
 // A = G_tt + lambda I of every genome into d_L32 [W][ntp_all][ntp_all] (what tb_launch_scale32 would produce)
 cudaError_t tb_launch_gram_tc(const int8_t* d_panel, int W, int rpad, int kstride, const int* d_kblocks,
                               const int* d_tiles, int n_tiles, int32_t* d_C, int n_sm, cudaStream_t st,
                               std::string* err, const TbScaleJob* d_fuse_jobs = nullptr, float* d_L32 = nullptr,
-                              int ntp_all = 0);
+                              int ntp_all = 0, int c16 = 0);
 cudaError_t tb_launch_gram_simt(const int8_t* d_panel, int W, int rpad, int kstride, const int* d_kblocks,
                                 int32_t* d_C, cudaStream_t st);
 
 // scale.cu
 struct TbScaleJob {       // one (individual, rowset) matrix
-  const int32_t* C;       // [rpad][rpad] lower triangle valid
+  const int32_t* C;       // [rpad][rpad] lower triangle valid (int16 entries when the wave runs in C16 mode)
   const long long* s;     // [rpad]
   const long long* SQ;    // {S, Q}
   const int* tpos;
@@ -223,9 +226,9 @@ struct TbSolveMixedJob {
 };
 cudaError_t tb_solve_mixed_init();
 bool tb_solve_mixed_fits(int ntp);
-cudaError_t tb_launch_solve_mixed(const TbSolveMixedJob* d_jobs, int n_jobs, int ntp, int contiguous,
+cudaError_t tb_launch_solve_mixed(const TbSolveMixedJob* d_jobs, int n_jobs, int ntp, int contiguous, int c16,
                                   cudaStream_t st);
-cudaError_t tb_launch_scale32(const TbScaleJob* d_jobs, int n_jobs, int ntp, float* L32, cudaStream_t st);
+cudaError_t tb_launch_scale32(const TbScaleJob* d_jobs, int n_jobs, int ntp, float* L32, int c16, cudaStream_t st);
 cudaError_t tb_chol_tc_init();
 // Linv256 (nullable): [n_jobs][256][256] scratch for the inverses of the 256-wide diagonal blocks (wide panel path)
 cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, float* Linv256, int* status, int n_jobs, int ntp,

@@ -266,3 +266,36 @@ def test_error_paths():
         assert a == b
     finally:
         eng.close()
+
+
+def test_int16_and_int32_cross_product_storage_agree():
+    """Mixed precision stores the cross-products as int16 when 4 k <= 32 767 for every genome of the batch (exact:
+    C_ab <= 4 k).  Same fitness and the same integers as the int32 layout, for contiguous and scattered row sets,
+    and a batch with a genome beyond the bound falls back to int32."""
+    from tblup_b200 import engine as E
+    g = load_golden("fit_mid")
+    x, y, h2 = g["x"], g["y"], float(g["h2"])
+    tr, va, te = g["train"], g["valid"], g["test"]
+    eng, perm = _engine(x, y, tr, va, te, extra_sets=[(np.concatenate([tr[40:], va[:10]]), np.concatenate([tr[:40], va[10:]]))])
+    try:
+        rng = np.random.default_rng(11)
+        m = x.shape[1]
+        genomes = [rng.choice(m, size=k, replace=False) for k in (3, 200, 1499)] + [rng.integers(0, m, size=8191)]
+        for slots in ([0], [1], [0, 1]):
+            eng.set_option("narrow_c", 1)
+            a = eng.evaluate(genomes, slots=slots, h2=h2, mode=E.MODE_GBLUP)
+            c16 = eng.debug_fetch(E.DBG_C, 0)
+            eng.set_option("narrow_c", 0)
+            b = eng.evaluate(genomes, slots=slots, h2=h2, mode=E.MODE_GBLUP)
+            c32 = eng.debug_fetch(E.DBG_C, 0)
+            if slots == [0]:     # training animals are universe positions 0 .. n_t-1: rows x training columns are formed
+                nt = len(tr) + len(va)
+                assert np.array_equal(np.tril(c16[:nt, :nt])[:, :len(tr)], np.tril(c32[:nt, :nt])[:, :len(tr)])
+            assert np.abs(a - b).max() < 1e-9
+        eng.set_option("narrow_c", 1)
+        big = genomes + [rng.integers(0, m, size=8192)]          # 4 * 8192 > 32 767: the whole batch uses int32
+        got = eng.evaluate(big, slots=[0], h2=h2, mode=E.MODE_GBLUP)[:, 0]
+        want = np.array([O.exact_fitness(gen, tr, va, x, y, h2, O.MODE_GBLUP) for gen in big])
+        assert np.abs(got - want).max() < FIT_TOL
+    finally:
+        eng.close()
