@@ -64,6 +64,23 @@ __device__ __forceinline__ double dot4i(const int4 c, const double* z) {
 // placing x in the low mantissa word and subtracting 2^52 costs one fp64 add
 __device__ __forceinline__ double u2d(uint32_t x) { return __hiloint2double(0x43300000, (int)x) - 4503599627370496.0; }
 
+// four rows of eight int16 cross-products against the same eight fp64 entries z (read from shared memory ONCE for
+// the four rows: ncu showed the LSU 82 % busy on these reads when every row fetched its own copy; a lane-rotated,
+// bank-conflict-free read order was tried and lost to the extra selects)
+__device__ __forceinline__ void fma4x8s(double (&d)[4], const uint4 v0, const uint4 v1, const uint4 v2, const uint4 v3,
+                                        const double* z) {
+  const uint32_t w0[4] = {v0.x, v0.y, v0.z, v0.w}, w1[4] = {v1.x, v1.y, v1.z, v1.w};
+  const uint32_t w2[4] = {v2.x, v2.y, v2.z, v2.w}, w3[4] = {v3.x, v3.y, v3.z, v3.w};
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const double2 zz = *reinterpret_cast<const double2*>(z + 2 * j);
+    d[0] += u2d(w0[j] & 0xffffu) * zz.x + u2d(w0[j] >> 16) * zz.y;
+    d[1] += u2d(w1[j] & 0xffffu) * zz.x + u2d(w1[j] >> 16) * zz.y;
+    d[2] += u2d(w2[j] & 0xffffu) * zz.x + u2d(w2[j] >> 16) * zz.y;
+    d[3] += u2d(w3[j] & 0xffffu) * zz.x + u2d(w3[j] >> 16) * zz.y;
+  }
+}
+
 // eight int16 cross-products (non-negative) against eight fp64 entries
 __device__ __forceinline__ double dot8s(const uint4 c, const double* z) {
   const double2 z0 = *reinterpret_cast<const double2*>(z), z1 = *reinterpret_cast<const double2*>(z + 2);
@@ -211,34 +228,29 @@ __device__ void apply_minv(const __half* __restrict__ L, const float* __restrict
 __device__ void sym_matvec16(const int16_t* __restrict__ C, int rpad, int n_t, const double* alpha, double* work,
                              double* part2) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int a = warp; a < n_t; a += ST / 32) {
+  // rows: a warp takes FOUR consecutive rows a .. a+3 (n_t is a multiple of 4) so that every alpha piece read from
+  // shared memory serves four 16-byte loads of C (four independent global loads in flight per thread).
+  for (int a = 4 * warp; a < n_t; a += 4 * (ST / 32)) {
     const uint4* row = reinterpret_cast<const uint4*>(C + (size_t)a * rpad);
-    const int full = (a + 1) / 8;                   // 8-entry groups that lie entirely at or left of the diagonal
-    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
-    int c = lane;
-    for (; c + 96 < full; c += 128) {
-      const uint4 v0 = row[c], v1 = row[c + 32], v2 = row[c + 64], v3 = row[c + 96];
-      d0 += dot8s(v0, alpha + 8 * c);
-      d1 += dot8s(v1, alpha + 8 * (c + 32));
-      d2 += dot8s(v2, alpha + 8 * (c + 64));
-      d3 += dot8s(v3, alpha + 8 * (c + 96));
-    }
-    for (; c + 32 < full; c += 64) {
-      const uint4 v0 = row[c], v1 = row[c + 32];
-      d0 += dot8s(v0, alpha + 8 * c);
-      d1 += dot8s(v1, alpha + 8 * (c + 32));
-    }
-    for (; c < full; c += 32) d2 += dot8s(row[c], alpha + 8 * c);
-    if (lane == 31 && 8 * full <= a) {              // the group that holds the diagonal (partial)
-      const uint4 v = row[full];
-      const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
-      const int b = 8 * full;
+    const size_t rs = rpad / 8;
+    const int full = (a + 1) / 8;                   // 8-entry groups at or left of the diagonal of ALL four rows
+    double d[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int c = lane; c < full; c += 32) fma4x8s(d, row[c], row[rs + c], row[2 * rs + c], row[3 * rs + c], alpha + 8 * c);
+    // the (at most 11) columns 8 full .. a + 3 that reach the diagonals: one lane per column, guarded per row
+    {
+      const int b = 8 * full + lane;
+      if (lane < 12 && b <= a + 3) {
+        const double z = alpha[b];
 #pragma unroll
-      for (int e = 0; e < 8; ++e)
-        if (b + e <= a) d3 += u2d((wv[e >> 1] >> (16 * (e & 1))) & 0xffffu) * alpha[b + e];
+        for (int rr = 0; rr < 4; ++rr)
+          if (b <= a + rr) d[rr] += (double)C[(size_t)(a + rr) * rpad + b] * z;
+      }
     }
-    const double d = warp_sum((d0 + d1) + (d2 + d3));
-    if (lane == 0) work[a] = d;
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const double t = warp_sum(d[rr]);
+      if (lane == 0) work[a + rr] = t;
+    }
   }
   __syncthreads();
   // columns: thread = 8 consecutive columns x one of 8 row groups (rows b = rg mod 8); the four row groups inside a
@@ -528,30 +540,50 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
   if (tid == 0 && jb.sweeps) *jb.sweeps = sweeps;
 
   // ---- predictions on the validation animals
-  for (int v = warp; v < n_v; v += ST / 32) {
-    const int pv = jb.vpos[v];
-    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
-    if constexpr (CONTIG && C16) {
-      if (pv >= n_t) {
-        const uint4* row = reinterpret_cast<const uint4*>(C + (size_t)pv * rpad);
+  if constexpr (CONTIG && C16) {
+    // four validation rows per warp share every alpha piece (see sym_matvec16); rows at/after n_t are plain rows of C
+      for (int v0i = 4 * warp; v0i < n_v; v0i += 4 * (ST / 32)) {
+      int pv[4];
+      bool fast = true;
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        pv[rr] = jb.vpos[min(v0i + rr, n_v - 1)];
+        fast = fast && pv[rr] >= n_t;
+      }
+      double d[4] = {0.0, 0.0, 0.0, 0.0};
+      if (fast) {
+        const uint4* r0 = reinterpret_cast<const uint4*>(C + (size_t)pv[0] * rpad);
+        const uint4* r1 = reinterpret_cast<const uint4*>(C + (size_t)pv[1] * rpad);
+        const uint4* r2 = reinterpret_cast<const uint4*>(C + (size_t)pv[2] * rpad);
+        const uint4* r3 = reinterpret_cast<const uint4*>(C + (size_t)pv[3] * rpad);
         const int n8 = n_t / 8;
-        int c = lane;
-        for (; c + 96 < n8; c += 128) {
-          const uint4 v0 = row[c], v1 = row[c + 32], v2 = row[c + 64], v3 = row[c + 96];
-          d0 += dot8s(v0, alpha + 8 * c);
-          d1 += dot8s(v1, alpha + 8 * (c + 32));
-          d2 += dot8s(v2, alpha + 8 * (c + 64));
-          d3 += dot8s(v3, alpha + 8 * (c + 96));
+        for (int c = lane; c < n8; c += 32) fma4x8s(d, r0[c], r1[c], r2[c], r3[c], alpha + 8 * c);
+        for (int b = 8 * n8 + lane; b < n_t; b += 32) {
+          const double z = alpha[b];
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr) d[rr] += (double)C[(size_t)pv[rr] * rpad + b] * z;
         }
-        for (; c < n8; c += 32) d0 += dot8s(row[c], alpha + 8 * c);
-        for (int b = 8 * n8 + lane; b < n_t; b += 32) d1 += (double)C[(size_t)pv * rpad + b] * alpha[b];
       } else {
         for (int b = lane; b < n_t; b += 32) {
           const int p0 = tp[b];
-          d0 += (double)C[(size_t)(pv > p0 ? pv : p0) * rpad + (pv > p0 ? p0 : pv)] * alpha[b];
+          const double z = alpha[b];
+#pragma unroll
+          for (int rr = 0; rr < 4; ++rr)
+            d[rr] += (double)C[(size_t)(pv[rr] > p0 ? pv[rr] : p0) * rpad + (pv[rr] > p0 ? p0 : pv[rr])] * z;
         }
       }
-    } else if (CONTIG && !C16 && pv >= n_t) {
+#pragma unroll
+      for (int rr = 0; rr < 4; ++rr) {
+        const double t = warp_sum(d[rr]);
+        if (lane == 0 && v0i + rr < n_v)
+          jb.pred[v0i + rr] = coef * (Nd * Nd * t - Nd * (double)jb.s[pv[rr]] * sa - Nd * ssa + Qd * sa);
+      }
+    }
+  } else {
+  for (int v = warp; v < n_v; v += ST / 32) {
+    const int pv = jb.vpos[v];
+    double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
+    if (CONTIG && !C16 && pv >= n_t) {
       const int4* row = reinterpret_cast<const int4*>(C + (size_t)pv * rpad);
       const int n4 = n_t / 4;
       int c = lane;
@@ -580,6 +612,7 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
     }
     const double d = warp_sum((d0 + d1) + (d2 + d3));
     if (lane == 0) jb.pred[v] = coef * (Nd * Nd * d - Nd * (double)jb.s[pv] * sa - Nd * ssa + Qd * sa);
+  }
   }
   __syncthreads();
 
