@@ -33,6 +33,13 @@ WORKLOADS = {
     "tiny": dict(n=300, m=2000, k=400, pop=16, folds=1),
 }
 DEFAULT_WORKLOAD = "c2_5000x50000_k5001_pop1000"
+# DRAM traffic per unit (matrix / genome) of the dominant kernels at the C2 shape, from the committed `ncu --set full`
+# captures (profiles/README.md says how each was taken); filled in after every re-profile
+NCU_TRAFFIC = {
+    "solve_c32": {"bytes_per_unit": 164.06e6, "source": "profiles/r01p_solve_raw.csv"},
+    "solve_c16": {"bytes_per_unit": 112.05e6, "source": "profiles/r01q_solve_raw.csv (1 000 matrices per launch)"},
+    "gram_fused_c16": {"bytes_per_unit": 58.93e6, "source": "profiles/r01q_gram_raw.csv (1 000 genomes per launch)"},
+}
 H2 = 0.4
 METRIC = "gblup_fitness_evals_per_sec"
 UNIT = "evals/s"
@@ -347,11 +354,16 @@ def main():
         except Exception:
             pass
         bf16 = peaks.get("bf16_tflops_sustained") or 1400.0
+        bf16_src = ("bf16_tflops_sustained of MEASURED_PEAKS.json" if peaks.get("bf16_tflops_sustained")
+                    else "fallback 1400 TFLOP/s sustained (B200_PROFILING.md)")
+        c16 = bool(eng.info("last_c16"))
+        fused = bool(eng.info("last_fused_scale"))
         if precision == "mixed":
             upd_flops = chol_update_flops(ntp, 256) * n_mats
-            upd_kernel = "tf32_gemm_kernel (outer left-looking Cholesky update, tcgen05 kind::tf32, M128 x N256)"
-            upd_peak = bf16 / 2
-            upd_peak_src = "0.5 x bf16_tflops_sustained of MEASURED_PEAKS.json (tf32 dense = half the bf16 rate)"
+            upd_kernel = ("tf32_gemm_kernel<F16> (outer left-looking Cholesky update on the fp16 copy of the factor, "
+                          "tcgen05 kind::f16, M128 x N256, fp32 accumulate)")
+            upd_peak = bf16
+            upd_peak_src = bf16_src + " (fp16 operands run at the bf16 rate)"
         else:
             upd_flops = chol_update_flops(ntp, 64) * n_mats
             upd_kernel = "chol_gemm_kernel<0> (left-looking Cholesky update, fp64 DMMA)"
@@ -369,42 +381,60 @@ def main():
                      "peak_source": upd_peak_src, "launches": int(upd_launches),
                      "avg_launch_ms": upd_ms / max(1, upd_launches), "share_of_step": upd_ms / ms_instrumented}
         solve_ms, solve_launches = stage["solve"]
-        tri_bytes = n_t * (n_t + 1) / 2 * 4          # lower triangle of the fp32 factor == of the int32 cross-products
+        csz = 2 if c16 else 4
+        tri_c = n_t * (n_t + 1) / 2 * csz            # lower triangle of the stored cross-products
+        tri_h = n_t * (n_t + 1) / 2 * 2              # lower triangle of the fp16 copy of the factor
         if precision == "mixed":
-            # per matrix: (1 + sweeps) preconditioner applications (factor read forwards and backwards), `sweeps`
+            # per matrix: (1 + sweeps) preconditioner applications (fp16 factor read forwards and backwards), `sweeps`
             # symmetric mat-vecs on the integer cross-products (lower triangle read by rows and by columns), one
             # pass over the validation rows
-            per_mat = (1 + mean_sweeps) * 2 * (tri_bytes / 2) + mean_sweeps * 2 * tri_bytes + n_v * n_t * 4   # fp16 factor
-            solve_kernel = ("solve_mixed_kernel (blocked substitution with the TF32 factor + fp64 refinement on the "
-                            "integer cross-products + predictions + Pearson)")
+            per_mat = (1 + mean_sweeps) * 2 * tri_h + mean_sweeps * 2 * tri_c + n_v * n_t * csz
+            solve_kernel = ("solve_mixed_kernel (blocked substitution with the fp16 copy of the TF32 factor + fp64 "
+                            "refinement on the %s cross-products + predictions + Pearson)" % ("int16" if c16 else "int32"))
         else:
             per_mat = 2 * n_t * (n_t + 1) / 2 * 8 + n_v * n_t * 8
             solve_kernel = "solve_kernel (fp64 blocked substitution + predictions + Pearson)"
         solve_gbs = per_mat * n_mats / (solve_ms * 1e-3) / 1e9 if solve_ms > 0 else None
-        # measured DRAM bytes per matrix of this kernel from the committed ncu capture (profiles/r01p_solve_raw.csv:
-        # dram__bytes_read.sum + dram__bytes_write.sum = 164.06 GB for 1 000 matrices, 2 sweeps, C2 shape)
-        ncu_bytes_per_mat = 164.06e6 if (precision == "mixed" and n_t == 3200 and mean_sweeps == 2.0) else None
         mats_per_launch = n_mats / max(1, solve_launches)
+        # measured DRAM bytes per launch from the committed ncu captures (dram__bytes_read.sum + dram__bytes_write.sum of
+        # one `ncu --set full` launch, scaled to the matrices / genomes of one bench launch); None for other shapes
+        ncu = NCU_TRAFFIC if (precision == "mixed" and n_t == 3200 and k == 5001 and folds == 1) else {}
+        solve_traffic = ncu.get("solve_c16" if c16 else "solve_c32")
         rl_solve = {"bound": "hbm", "kernel": solve_kernel, "achieved": solve_gbs, "peak": hbm, "unit": "GB/s",
                     "frac": (solve_gbs / hbm) if solve_gbs else None,
-                    "traffic": ncu_bytes_per_mat * mats_per_launch if ncu_bytes_per_mat else None,
-                    "traffic_source": "profiles/r01p_solve_raw.csv (ncu --set full), scaled to matrices per launch",
+                    "traffic": solve_traffic["bytes_per_unit"] * mats_per_launch if solve_traffic else None,
+                    "traffic_source": solve_traffic["source"] if solve_traffic else None,
                     "algorithmic_bytes_per_launch": per_mat * mats_per_launch,
                     "peak_source": "hbm_gbs of MEASURED_PEAKS.json" if peaks.get("hbm_gbs") else "fallback 6650 GB/s",
                     "algorithmic_bytes_per_matrix": per_mat, "mean_refinement_sweeps": mean_sweeps,
                     "launches": int(solve_launches), "avg_launch_ms": solve_ms / max(1, solve_launches),
                     "share_of_step": solve_ms / ms_instrumented}
-        dominant = rl_solve if solve_ms > upd_ms else rl_update
-        other = rl_update if dominant is rl_solve else rl_solve
+        gram_tops = gram_ops / (gram_ms * 1e-3) / 1e12 if gram_ms > 0 else None
+        gram_traffic = ncu.get("gram_fused_c16") if (fused and c16) else None
+        rl_gram = {"bound": "tensor",
+                   "kernel": "gram_tc_kernel (tcgen05 kind::i8, M128 x N256 x K32, s32 in TMEM%s)"
+                             % ("; epilogue also writes the scaled fp32 matrix" if fused else ""),
+                   "achieved": gram_tops, "peak": 2 * bf16, "unit": "TOP/s",
+                   "frac": gram_tops / (2 * bf16) if gram_tops else None,
+                   "traffic": gram_traffic["bytes_per_unit"] * P if gram_traffic else None,
+                   "traffic_source": gram_traffic["source"] if gram_traffic else None,
+                   "algorithmic_ops_per_launch": gram_ops / max(1, gram_launches),
+                   "peak_source": "2 x " + bf16_src + " (int8 dense = 2 x bf16; nominal 4 500 TOP/s)",
+                   "launches": int(gram_launches), "avg_launch_ms": gram_ms / max(1, gram_launches),
+                   "share_of_step": gram_ms / ms_instrumented}
+        ranked = sorted([("gram", rl_gram, gram_ms), ("solve", rl_solve, solve_ms), ("cholesky_update", rl_update, upd_ms)],
+                        key=lambda t: -t[2])
+        dominant = ranked[0][1]
         line = {
             "metric": METRIC, "value": evals / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
-            "dtype": ("s8 Gram (s32) + tf32 Cholesky preconditioner + f64 refinement/solve" if precision == "mixed"
+            "dtype": ("s8 Gram (s32) + tf32/f16 Cholesky preconditioner + f64 refinement/solve" if precision == "mixed"
                       else "s8 Gram (s32 accumulate) + f64 Cholesky/solve"), "data": "synthetic",
             "config": {"workload": args.workload, "animals": n, "markers": m, "k": k, "pop_per_gpu": P, "folds": folds,
                        "h2": H2, "n_train": int(n_t), "n_valid": int(n_v), "individuals_per_wave": wave, "precision": precision,
-                       "genotype_storage": args.storage, "genotype_bytes_resident": eng.resident_genotype_bytes(),
+                       "genotype_storage": args.storage, "cross_product_storage": "int16" if c16 else "int32",
+                       "scaling_fused_into_gram": fused, "genotype_bytes_resident": eng.resident_genotype_bytes(),
                        "l2": "inputs larger than L2 (each step streams >20 GB of per-genome panels and matrices)",
                        "parallelism": "replicated genotypes, population sharded, NCCL all-gather of fitness"},
             "e2e": {"value": evals / (ms_e2e * 1e-3), "unit": UNIT,
@@ -413,13 +443,8 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": dominant,
-            "roofline_" + ("cholesky_update" if other is rl_update else "solve"): other,
-            "roofline_gram": {"bound": "tensor", "kernel": "gram_tc_kernel (tcgen05 kind::i8)",
-                              "achieved": gram_ops / (gram_ms * 1e-3) / 1e12 if gram_ms > 0 else None,
-                              "peak": 2 * bf16, "unit": "TOP/s",
-                              "frac": gram_ops / (gram_ms * 1e-3) / 1e12 / (2 * bf16) if gram_ms > 0 else None,
-                              "peak_source": "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (int8 dense = 2 x bf16)",
-                              "share_of_step": gram_ms / ms_instrumented},
+            "roofline_" + ranked[1][0]: ranked[1][1],
+            "roofline_" + ranked[2][0]: ranked[2][1],
             "stage_ms_per_step": {s: v[0] / args.steps for s, v in stage.items()},
             "ms_per_step_instrumented": ms_instrumented / args.steps,
             "cpu_baseline": cpu_baseline,

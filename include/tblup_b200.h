@@ -106,8 +106,15 @@ int tb_debug_fetch(tb_ctx* ctx, int what, int job, void* out, size_t nbytes);
 /* options: "profile" (0/1: per-stage CUDA-event timing), "stop_after" (stage index, -1 = run all),
  * "workspace_mb" (cap for the wave workspace, 0 = auto), "max_wave" (cap individuals per wave, 0 = auto),
  * "precision" (0 = mixed: TF32 tensor-core Cholesky as preconditioner + fp64 refinement against the exact
- * integer operator [default]; 1 = fp64 Cholesky throughout) */
+ * integer operator [default]; 1 = fp64 Cholesky throughout),
+ * "fuse_scale" (0/1, default 1: with one contiguous row set in mixed precision the Gram epilogue writes the scaled
+ * fp32 matrix itself), "wide_panel" (0/1, default 1: 256-wide Cholesky panel through the inverse of the diagonal
+ * block), "narrow_c" (0/1, default 1: int16 storage of the cross-products when 4 k <= 32 767 for the whole batch) */
 int tb_set_option(tb_ctx* ctx, const char* name, long long value);
+
+/* Facts about the last evaluation / the context: "last_c16", "last_fused_scale", "last_mixed", "last_wave",
+ * "storage", "wide_panel". */
+int tb_get_info(const tb_ctx* ctx, const char* name, long long* value);
 
 /* Accumulated per-stage device milliseconds (valid with profile=1) and kernel launches since the last
  * tb_reset_counters(); either pointer may be NULL. */

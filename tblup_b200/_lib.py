@@ -29,6 +29,7 @@ SYMBOLS = {
     "tb_gram_debug": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "tb_debug_fetch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "tb_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_longlong]),
+    "tb_get_info": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_longlong)]),
     "tb_stage_times": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tb_launch_count": (C.c_uint64, [C.c_void_p]),
     "tb_reset_counters": (C.c_int, [C.c_void_p]),

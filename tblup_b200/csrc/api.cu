@@ -164,6 +164,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
   }
   // one contiguous row set: the Gram epilogue writes the fp32 matrix itself (no separate scaling pass over C)
   const bool fuse_scale = mixed && n_slots == 1 && sv[0].rs->contiguous && c->n <= 46340 && c->fuse_scale;
+  c->last_fused = fuse_scale ? 1 : 0;
   const int P = c->P;
   int kmax = 0;
   for (int i = 0; i < P; ++i) {
@@ -255,6 +256,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     h_msolve.resize(n_jobs);
     h_cs.resize(n_jobs);
     c->dbg.L32 = d_L32;
+    c->dbg.L16 = d_L16;
     c->dbg.sweeps = d_sweeps;
     c->dbg.ntp_all = max_ntp;
     c->dbg.W = Wc;
@@ -857,6 +859,26 @@ int tb_debug_fetch(tb_ctx* c, int what, int job, void* out, size_t nbytes) {
     default: return fail(c, "tb_debug_fetch: unknown item");
   }
   if (nbytes < need) return fail(c, "tb_debug_fetch: buffer too small (need " + std::to_string(need) + " bytes)");
+  if (what == TB_DBG_L32 && d.L16) {
+    // the factor of record is the fp16 copy (same 10-bit mantissa as the TF32 rounding; the wide panel solve does
+    // not write the fp32 copy below the diagonal blocks): widen it, upper triangle zero
+    const size_t nn = (size_t)d.ntp_all * d.ntp_all;
+    std::vector<unsigned short> h(nn);
+    TB_CUDA(c, cudaMemcpy(h.data(), d.L16 + (size_t)job * nn, nn * sizeof(unsigned short), cudaMemcpyDeviceToHost));
+    float* o = static_cast<float*>(out);
+    for (int r = 0; r < d.ntp_all; ++r)
+      for (int q = 0; q < d.ntp_all; ++q) {
+        float f = 0.f;
+        if (q <= r) {
+          const unsigned short b = h[(size_t)r * d.ntp_all + q];
+          const int sign = b >> 15, ex = (b >> 10) & 31, man = b & 1023;
+          f = ex == 0 ? std::ldexp((float)man, -24) : ex == 31 ? (man ? NAN : INFINITY) : std::ldexp((float)(man | 1024), ex - 25);
+          if (sign) f = -f;
+        }
+        o[(size_t)r * d.ntp_all + q] = f;
+      }
+    return 0;
+  }
   if (what == TB_DBG_C && c->last_c16) {
     // the wave stored int16 cross-products: widen to the int32 view the caller asked for
     std::vector<int16_t> h((size_t)d.rpad * d.rpad);
@@ -883,6 +905,19 @@ int tb_set_option(tb_ctx* c, const char* name, long long value) {
   else if (s == "narrow_c") c->narrow_c = value != 0;
   else if (s == "storage") return fail(c, "tb_set_option: storage is fixed at tb_create_ex");
   else return fail(c, "tb_set_option: unknown option '" + s + "'");
+  return 0;
+}
+
+int tb_get_info(const tb_ctx* c, const char* name, long long* value) {
+  if (!c || !name || !value) return -1;
+  const std::string s(name);
+  if (s == "last_c16") *value = c->last_c16;
+  else if (s == "last_fused_scale") *value = c->last_fused;
+  else if (s == "last_mixed") *value = c->last_mixed;
+  else if (s == "last_wave") *value = c->last_wave;
+  else if (s == "storage") *value = c->storage;
+  else if (s == "wide_panel") *value = c->wide_panel;
+  else return -1;
   return 0;
 }
 

@@ -58,6 +58,7 @@ struct GemmParams {
   int c_col0;        // first output column (in L32)
   int N;             // output columns: 64, 128, 192 or 256
   int mode;          // 0: C -= A B^T   1: C = A B^T rounded to TF32 (final L entries)
+  int skip32;        // mode 1 only: do not write the fp32 copy (nothing reads these entries of L32 again)
   float* L32;
   __half* L16;       // optional half-precision copy of the final factor entries (read by the solve)
 };
@@ -251,17 +252,19 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(round_tf32(__uint_as_float(v[j])));
         }
+        if (!(p.mode != 0 && p.skip32)) {
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          stage_write16(stg, lane, o + 16 * h);
-          __syncwarp();
+          for (int h = 0; h < 2; ++h) {
+            stage_write16(stg, lane, o + 16 * h);
+            __syncwarp();
 #pragma unroll
-          for (int it = 0; it < 4; ++it) {
-            const uint4 u = stage_read16(stg, lane, it);
-            if (rw0 + 8 * it + rl < p.row_end)
-              *reinterpret_cast<uint4*>(wbase + (size_t)(8 * it + rl) * p.ntp + i * 32 + 16 * h + gl) = u;
+            for (int it = 0; it < 4; ++it) {
+              const uint4 u = stage_read16(stg, lane, it);
+              if (rw0 + 8 * it + rl < p.row_end)
+                *reinterpret_cast<uint4*>(wbase + (size_t)(8 * it + rl) * p.ntp + i * 32 + 16 * h + gl) = u;
+            }
+            __syncwarp();
           }
-          __syncwarp();
         }
         if (p.mode != 0 && p.L16) {
           uint32_t hv[16];
@@ -621,6 +624,8 @@ cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, float* Linv2
       GemmParams p{};
       p.row0 = c0 + w; p.a_col0 = c0; p.K = w; p.b_row0 = 0; p.b_col0 = 0; p.b_rows_per_job = 256; p.c_col0 = c0;
       p.N = w; p.mode = 1;
+      // rows below the diagonal block: later steps read them only through the fp16 copy (updates, solve sweeps)
+      p.skip32 = upd16 ? 1 : 0;
       if ((e = gemm(tm_inv256, p)) != cudaSuccess) return e;
     }
     if (mark) mark(mark_ctx, 1, 1);

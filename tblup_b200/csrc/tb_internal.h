@@ -93,6 +93,7 @@ struct TbCtx {
   int last_mixed = 0;
   int narrow_c = 1;               // 1: int16 cross-products when every genome of the batch has 4 k <= 32 767
   int last_c16 = 0;
+  int last_fused = 0;
   int wide_panel = 1;             // 1: 256-wide panel solve through the inverse of the diagonal block (chol_tc.cu)
   int fuse_scale = 1;             // 1: Gram epilogue writes the fp32 matrix when the row set allows it
   int n_sm = 148;
@@ -101,7 +102,7 @@ struct TbCtx {
     int W = 0, n_slots = 0, rpad = 0, kstride = 0, centre_shared = 0;
     int32_t* C = nullptr; long long* s = nullptr; long long* SQ = nullptr;
     std::vector<double*> M, alpha, pred;
-    float* L32 = nullptr; int* sweeps = nullptr; int ntp_all = 0;
+    float* L32 = nullptr; const unsigned short* L16 = nullptr; int* sweeps = nullptr; int ntp_all = 0;
     std::vector<int> ntp, n_v;
   } dbg;
   // on-device differential evolution (de.cu)

@@ -225,6 +225,13 @@ class GblupEngine:
     def last_precision(self):
         return {0: "mixed", 1: "fp64"}[int(self._lib.tb_last_precision(self._ctx))]
 
+    def info(self, name):
+        """Facts about the last evaluation: 'last_c16', 'last_fused_scale', 'last_mixed', 'last_wave', 'storage'."""
+        v = C.c_longlong(0)
+        if self._lib.tb_get_info(self._ctx, name.encode(), C.byref(v)) != 0:
+            raise KeyError(name)
+        return int(v.value)
+
     def resident_genotype_bytes(self):
         b = C.c_uint64(0)
         self._check(self._lib.tb_storage_info(self._ctx, None, C.byref(b)), "tb_storage_info")

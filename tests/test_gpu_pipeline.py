@@ -299,3 +299,35 @@ def test_int16_and_int32_cross_product_storage_agree():
         assert np.abs(got - want).max() < FIT_TOL
     finally:
         eng.close()
+
+
+def test_mixed_factor_across_several_panels():
+    """n_t = 704 training animals: three 256-wide block columns, so the wide panel path (inverse of the 256 x 256
+    diagonal block + one K = 256 GEMM for the rows below) and the fp16-operand outer updates both run.  The factor
+    of record (fp16 copy) must reproduce A to TF32 accuracy and the refined solution the oracle's."""
+    import random
+    from tblup_b200 import engine as E
+    n, m = 1100, 3000
+    x, y = O.synth_genotypes(n, m, h2=0.4, seed=21)
+    random.seed(21)
+    np.random.seed(21)
+    tr, va, te = O.ref_splits(n)
+    assert len(tr) == 704
+    eng, perm = _engine(x, y, tr, va, te)
+    try:
+        rng = np.random.default_rng(22)
+        genomes = [rng.choice(m, size=k, replace=False) for k in (150, 1101, 2500)]
+        h2 = 0.4
+        for wide in (1, 0):
+            eng.set_option("wide_panel", wide)
+            fit = eng.evaluate(genomes, slots=[0], h2=h2, mode=E.MODE_GBLUP)[:, 0]
+            for job, gen in enumerate(genomes):
+                ref, d = O.exact_fitness(gen, tr, va, x, y, h2, O.MODE_GBLUP, detail=True)
+                nt = len(tr)
+                L = np.tril(eng.debug_fetch(E.DBG_L32, job)[:nt, :nt]).astype(np.float64)
+                rel = np.abs(np.tril(L @ L.T - d["A"])).max() / np.abs(d["A"]).max()
+                assert 1e-7 < rel < 5e-3, (wide, job, rel)
+                assert int(eng.debug_fetch(E.DBG_SWEEPS, job)[0]) <= 4
+                assert abs(fit[job] - ref) < 1e-7, (wide, job, fit[job], ref)
+    finally:
+        eng.close()
