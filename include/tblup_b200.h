@@ -113,8 +113,10 @@ int tb_debug_fetch(tb_ctx* ctx, int what, int job, void* out, size_t nbytes);
 int tb_set_option(tb_ctx* ctx, const char* name, long long value);
 
 /* Facts about the last evaluation / the context: "last_c16", "last_fused_scale", "last_mixed", "last_wave",
- * "storage", "wide_panel". */
+ * "storage", "wide_panel", "de_removed" (size of the removed-marker set), "staged" (genomes staged). */
 int tb_get_info(const tb_ctx* ctx, const char* name, long long* value);
+/* Offsets (P + 1 entries, P = tb_get_info "staged") of the ragged batch currently staged on the device. */
+int tb_staged_offsets(const tb_ctx* ctx, int64_t* off_out, int n);
 
 /* Accumulated per-stage device milliseconds (valid with profile=1) and kernel launches since the last
  * tb_reset_counters(); either pointer may be NULL. */
@@ -150,6 +152,18 @@ int tb_de_evaluate(tb_ctx* ctx, const int32_t* slots, int n_slots, double h2, in
 int tb_de_step(tb_ctx* ctx, const int32_t* slots, int n_slots, double h2, int mode_rule, double F, double CR, int clip,
                const int32_t* abc, const int32_t* fixed, const uint8_t* mask, uint64_t seed, int32_t* take_out);
 int tb_de_get(tb_ctx* ctx, int what, int which, void* out, size_t nbytes);
+/* SNP removal on the device (tblup/evaluator.py:569-633, SNPRemovalHandler).  The removed set lives next to the keys:
+ * once it is non-empty, tb_de_evaluate / tb_de_step score every individual on setdiff1d(genome, removed)
+ * (evaluator.py:617; an individual left with no marker gets fitness 0.0, :618-620) and tb_de_evaluate_testing scores
+ * union1d(genome, removed) on row set `slot` (evaluate_testing, evaluator.py:407-431; fitness_out: host, [P]).
+ * tb_de_set_removed replaces the set with a host list; tb_de_ban_genome adds the decoded genome of individual
+ * `which` of the current population (what genomes_to_evaluate does with the best individual, :603-606 -- the
+ * reference always bans the whole genome) without the list visiting the host.
+ * tb_de_get: what = 6 removed markers (ascending) i32, 7 lengths of the last filtered batch [P] i32,
+ * 8 the flat lists of the last evaluated batch. */
+int tb_de_set_removed(tb_ctx* ctx, const int32_t* markers, int n);
+int tb_de_ban_genome(tb_ctx* ctx, int which, int32_t* n_removed_out);
+int tb_de_evaluate_testing(tb_ctx* ctx, int slot, double h2, int mode_rule, double* fitness_out);
 
 #ifdef __cplusplus
 }

@@ -60,3 +60,27 @@ def decode(key_vector, length):
 def select(parent_fitness, child_fitness):
     """Boolean vector: child replaces parent."""
     return np.asarray(child_fitness) > np.asarray(parent_fitness)
+
+
+# ---- SNP removal (tblup/evaluator.py:569-633, SNPRemovalHandler) ------------------------------------------------
+
+def removal_threshold(h2, alpha):
+    """Fitness above which the best individual's markers are removed (evaluator.py:585)."""
+    return np.sqrt(h2) * (1 + alpha)
+
+
+def remove_best(removed, best_genome, r):
+    """New removed set after the handler fires: ``best.genome[-n:]`` with n = len(best) if r < len(best) else r
+    (evaluator.py:603-606) -- in both cases the whole genome -- united with what was removed before."""
+    n = len(best_genome) if r < len(best_genome) else r
+    return np.union1d(removed, np.asarray(best_genome)[-n:])
+
+
+def filtered_genome(genome, removed):
+    """What the fitness is computed on once markers have been removed (evaluator.py:617); empty -> fitness 0.0."""
+    return np.setdiff1d(genome, removed)
+
+
+def testing_genome(genome, removed):
+    """What the testing accuracy is computed on (evaluator.py:627-633)."""
+    return np.union1d(genome, removed).astype(int)

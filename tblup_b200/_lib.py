@@ -30,6 +30,7 @@ SYMBOLS = {
     "tb_debug_fetch": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "tb_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_longlong]),
     "tb_get_info": (C.c_int, [C.c_void_p, C.c_char_p, C.POINTER(C.c_longlong)]),
+    "tb_staged_offsets": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "tb_stage_times": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tb_launch_count": (C.c_uint64, [C.c_void_p]),
     "tb_reset_counters": (C.c_int, [C.c_void_p]),
@@ -40,6 +41,9 @@ SYMBOLS = {
     "tb_de_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int,
                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
     "tb_de_get": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
+    "tb_de_set_removed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
+    "tb_de_ban_genome": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "tb_de_evaluate_testing": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p]),
     "tb_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
     "tb_microbench": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
 }

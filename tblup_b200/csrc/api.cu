@@ -917,7 +917,16 @@ int tb_get_info(const tb_ctx* c, const char* name, long long* value) {
   else if (s == "last_wave") *value = c->last_wave;
   else if (s == "storage") *value = c->storage;
   else if (s == "wide_panel") *value = c->wide_panel;
+  else if (s == "de_removed") *value = c->de.n_banned;
+  else if (s == "staged") *value = c->P;
   else return -1;
+  return 0;
+}
+
+int tb_staged_offsets(const tb_ctx* c, int64_t* off_out, int n) {
+  if (!c || !off_out) return -1;
+  if (n < c->P + 1 || (int)c->h_off.size() < c->P + 1) return -1;
+  for (int i = 0; i <= c->P; ++i) off_out[i] = c->h_off[i];
   return 0;
 }
 

@@ -86,13 +86,13 @@ __device__ __forceinline__ unsigned long long sortable(double d) {
 // One CTA per individual: exact k-th largest key by MSD radix select (8 bits per pass), then an order-preserving
 // compaction of the indices whose key is above the threshold (ties at the threshold: lowest indices first).
 __global__ void __launch_bounds__(1024) de_decode_kernel(const double* __restrict__ keys, int m, int k,
-                                                         int* __restrict__ idx_out) {
+                                                         int* __restrict__ idx_out, int out_stride) {
   __shared__ unsigned int hist[256];
   __shared__ unsigned long long s_prefix;
   __shared__ unsigned int s_rank, s_base, s_tie_base;
   __shared__ unsigned int wsum[32][2];
   const double* row = keys + (size_t)blockIdx.x * m;
-  int* out = idx_out + (size_t)blockIdx.x * k;
+  int* out = idx_out + (size_t)blockIdx.x * out_stride;      // lists out_stride >= k apart
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (tid == 0) {
     s_prefix = 0;
@@ -177,6 +177,106 @@ __global__ void __launch_bounds__(1024) de_decode_kernel(const double* __restric
   }
 }
 
+// ---- SNP removal on the device (tblup/evaluator.py:589-633) -------------------------------------------------------
+// banned[j] = 1 for every marker removed so far.  The fitness of an individual is computed on
+// setdiff1d(genome, removed) (evaluator.py:617), its testing accuracy on union1d(genome, removed) (:627-633).
+
+// rows: [P][stride] decoded genomes (`len_in` entries each).  Keeps the entries that are not banned, in order,
+// in place; lens[i] = how many are left.
+__global__ void __launch_bounds__(1024) de_filter_banned_kernel(int* __restrict__ rows, int stride, int len_in,
+                                                                const unsigned char* __restrict__ banned,
+                                                                int* __restrict__ lens) {
+  __shared__ unsigned int wsum[32];
+  __shared__ unsigned int s_base;
+  int* row = rows + (size_t)blockIdx.x * stride;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) s_base = 0;
+  __syncthreads();
+  for (int j0 = 0; j0 < len_in; j0 += 1024) {
+    const int j = j0 + tid;
+    int v = -1;
+    bool keep = false;
+    if (j < len_in) {
+      v = row[j];
+      keep = banned[v] == 0;
+    }
+    const unsigned int mk = __ballot_sync(0xffffffffu, keep);
+    if (lane == 0) wsum[warp] = __popc(mk);
+    __syncthreads();                               // every read of this chunk is done before any write below
+    unsigned int before = 0, total = 0;
+    for (int w = 0; w < 32; ++w) {
+      if (w < warp) before += wsum[w];
+      total += wsum[w];
+    }
+    const unsigned int pos = s_base + before + __popc(mk & ((1u << lane) - 1u));
+    if (keep) row[pos] = v;                        // pos <= j: never overtakes an unread entry of a later chunk
+    __syncthreads();
+    if (tid == 0) s_base += total;
+    __syncthreads();
+  }
+  if (tid == 0) lens[blockIdx.x] = (int)s_base;
+}
+
+// rows: [P][stride], the first k entries hold the decoded genome.  Appends every banned marker that is not already in
+// the genome (membership through a bitmap in shared memory): rows[i] = union(genome_i, removed), lens[i] = its size.
+__global__ void __launch_bounds__(1024) de_union_banned_kernel(int* __restrict__ rows, int stride, int k, int m,
+                                                               const int* __restrict__ banned_list, int n_banned,
+                                                               int* __restrict__ lens) {
+  extern __shared__ unsigned int member[];         // m bits
+  __shared__ unsigned int wsum[32];
+  __shared__ unsigned int s_base;
+  int* row = rows + (size_t)blockIdx.x * stride;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int q = tid; q < (m + 31) / 32; q += 1024) member[q] = 0;
+  if (tid == 0) s_base = (unsigned int)k;
+  __syncthreads();
+  for (int j = tid; j < k; j += 1024) atomicOr(&member[row[j] >> 5], 1u << (row[j] & 31));
+  __syncthreads();
+  for (int j0 = 0; j0 < n_banned; j0 += 1024) {
+    const int j = j0 + tid;
+    int v = -1;
+    bool add = false;
+    if (j < n_banned) {
+      v = banned_list[j];
+      add = ((member[v >> 5] >> (v & 31)) & 1u) == 0;
+    }
+    const unsigned int mk = __ballot_sync(0xffffffffu, add);
+    if (lane == 0) wsum[warp] = __popc(mk);
+    __syncthreads();
+    unsigned int before = 0, total = 0;
+    for (int w = 0; w < 32; ++w) {
+      if (w < warp) before += wsum[w];
+      total += wsum[w];
+    }
+    if (add) row[s_base + before + __popc(mk & ((1u << lane) - 1u))] = v;
+    __syncthreads();
+    if (tid == 0) s_base += total;
+    __syncthreads();
+  }
+  if (tid == 0) lens[blockIdx.x] = (int)s_base;
+}
+
+// flat[off[i] + j] = rows[i][j], j < off[i+1] - off[i]  (ragged lists behind one another, what the pipeline reads)
+__global__ void de_pack_rows_kernel(const int* __restrict__ rows, int stride, const long long* __restrict__ off,
+                                    int* __restrict__ flat) {
+  const int i = blockIdx.y;
+  const long long o0 = off[i];
+  const int len = (int)(off[i + 1] - o0);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < len; j += gridDim.x * blockDim.x)
+    flat[o0 + j] = rows[(size_t)i * stride + j];
+}
+
+__global__ void de_set_flags_kernel(unsigned char* __restrict__ banned, const int* __restrict__ list, int n) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < n) banned[list[j]] = 1;
+}
+
+// an individual whose every marker is banned is not evaluated: its fitness is 0.0 (evaluator.py:617-619)
+__global__ void de_zero_empty_kernel(double* __restrict__ fit, const int* __restrict__ lens, int P) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P && lens[i] == 0) fit[i] = 0.0;
+}
+
 __global__ void de_mean_kernel(const double* __restrict__ f, int n_slots, int P, double* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
@@ -216,14 +316,15 @@ void de_free(TbCtx* c) {
   cudaFree(c->de.fixed);
   cudaFree(c->de.take);
   cudaFree(c->de.mask);
+  cudaFree(c->de.banned);
+  cudaFree(c->de.banned_list);
+  cudaFree(c->de.rows);
+  cudaFree(c->de.lens);
+  cudaFree(c->de.d_off);
   c->de = TbCtx::DeState();
 }
 
-// decode `src` keys into the context's staged-genome buffer and evaluate them; result (mean over slots) -> dst
-int de_decode_and_eval(TbCtx* c, const double* src, const int32_t* slots, int n_slots, double h2, int mode,
-                       double* dst) {
-  auto& d = c->de;
-  const size_t total = (size_t)d.P * d.k;
+int de_ensure_idx(TbCtx* c, size_t total) {
   if (total > c->idx_cap) {
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
     cudaFree(c->d_idx);
@@ -232,12 +333,47 @@ int de_decode_and_eval(TbCtx* c, const double* src, const int32_t* slots, int n_
     TB_CUDA(c, cudaMalloc(&c->d_idx, total * sizeof(int)));
     c->idx_cap = total;
   }
-  de_decode_kernel<<<d.P, 1024, 0, c->stream>>>(src, c->m, d.k, c->d_idx);
+  return 0;
+}
+
+int de_ensure_rows(TbCtx* c, int stride) {
+  auto& d = c->de;
+  if ((size_t)d.P * stride > d.rows_cap) {
+    TB_CUDA(c, cudaStreamSynchronize(c->stream));
+    cudaFree(d.rows);
+    d.rows = nullptr;
+    TB_CUDA(c, cudaMalloc(&d.rows, (size_t)d.P * stride * sizeof(int)));
+    d.rows_cap = (size_t)d.P * stride;
+  }
+  if (!d.lens) TB_CUDA(c, cudaMalloc(&d.lens, (size_t)d.P * sizeof(int)));
+  if (!d.d_off) TB_CUDA(c, cudaMalloc(&d.d_off, (size_t)(d.P + 1) * sizeof(long long)));
+  return 0;
+}
+
+// rows [P][stride] with lens on the device -> the context's staged ragged batch (c->d_idx, c->h_off, c->P).
+// Only the P lengths visit the host (the offsets the wave scheduler plans with); an empty list is staged as one
+// arbitrary marker and its fitness overwritten afterwards (h_lens tells which).
+int de_stage_rows(TbCtx* c, int stride, std::vector<int>& h_lens) {
+  auto& d = c->de;
+  h_lens.resize(d.P);
+  TB_CUDA(c, cudaMemcpyAsync(h_lens.data(), d.lens, (size_t)d.P * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  TB_CUDA(c, cudaStreamSynchronize(c->stream));
+  c->h_off.resize(d.P + 1);
+  c->h_off[0] = 0;
+  for (int i = 0; i < d.P; ++i) c->h_off[i + 1] = c->h_off[i] + std::max(h_lens[i], 1);
+  c->P = d.P;
+  if (int rc = de_ensure_idx(c, (size_t)c->h_off[d.P])) return rc;
+  TB_CUDA(c, cudaMemcpyAsync(d.d_off, c->h_off.data(), (size_t)(d.P + 1) * sizeof(long long), cudaMemcpyHostToDevice,
+                             c->stream));
+  dim3 grid((unsigned)std::min(64, (stride + 255) / 256), d.P);
+  de_pack_rows_kernel<<<grid, 256, 0, c->stream>>>(d.rows, stride, d.d_off, c->d_idx);
   TB_CUDA(c, cudaGetLastError());
   c->launches += 1;
-  c->h_off.resize(d.P + 1);
-  for (int i = 0; i <= d.P; ++i) c->h_off[i] = (long long)i * d.k;
-  c->P = d.P;
+  return 0;
+}
+
+int de_ensure_raw(TbCtx* c, int n_slots) {
+  auto& d = c->de;
   if ((size_t)d.P * n_slots > d.raw_cap) {
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
     cudaFree(d.raw_fit);
@@ -245,11 +381,67 @@ int de_decode_and_eval(TbCtx* c, const double* src, const int32_t* slots, int n_
     TB_CUDA(c, cudaMalloc(&d.raw_fit, (size_t)d.P * n_slots * sizeof(double)));
     d.raw_cap = (size_t)d.P * n_slots;
   }
+  return 0;
+}
+
+// decode `src` keys into the context's staged-genome buffer (minus the banned markers, if any) and evaluate them;
+// result (mean over slots) -> dst
+int de_decode_and_eval(TbCtx* c, const double* src, const int32_t* slots, int n_slots, double h2, int mode,
+                       double* dst) {
+  auto& d = c->de;
+  std::vector<int> h_lens;
+  if (d.n_banned == 0) {
+    if (int rc = de_ensure_idx(c, (size_t)d.P * d.k)) return rc;
+    de_decode_kernel<<<d.P, 1024, 0, c->stream>>>(src, c->m, d.k, c->d_idx, d.k);
+    TB_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    c->h_off.resize(d.P + 1);
+    for (int i = 0; i <= d.P; ++i) c->h_off[i] = (long long)i * d.k;
+    c->P = d.P;
+  } else {
+    if (int rc = de_ensure_rows(c, d.k)) return rc;
+    de_decode_kernel<<<d.P, 1024, 0, c->stream>>>(src, c->m, d.k, d.rows, d.k);
+    TB_CUDA(c, cudaGetLastError());
+    de_filter_banned_kernel<<<d.P, 1024, 0, c->stream>>>(d.rows, d.k, d.k, d.banned, d.lens);
+    TB_CUDA(c, cudaGetLastError());
+    c->launches += 2;
+    if (int rc = de_stage_rows(c, d.k, h_lens)) return rc;
+  }
+  if (int rc = de_ensure_raw(c, n_slots)) return rc;
   int rc = tb_internal_eval_device(c, slots, n_slots, h2, mode, d.raw_fit);
   if (rc) return rc;
   de_mean_kernel<<<(d.P + 255) / 256, 256, 0, c->stream>>>(d.raw_fit, n_slots, d.P, dst);
   TB_CUDA(c, cudaGetLastError());
   c->launches += 1;
+  if (d.n_banned) {
+    de_zero_empty_kernel<<<(d.P + 255) / 256, 256, 0, c->stream>>>(dst, d.lens, d.P);
+    TB_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+  }
+  return 0;
+}
+
+// banned flags -> ascending list on the device + count
+int de_refresh_banned_list(TbCtx* c) {
+  auto& d = c->de;
+  std::vector<unsigned char> flags(c->m);
+  TB_CUDA(c, cudaMemcpy(flags.data(), d.banned, (size_t)c->m, cudaMemcpyDeviceToHost));
+  std::vector<int> list;
+  for (int j = 0; j < c->m; ++j)
+    if (flags[j]) list.push_back(j);
+  d.n_banned = (int)list.size();
+  if (!d.banned_list) TB_CUDA(c, cudaMalloc(&d.banned_list, (size_t)c->m * sizeof(int)));
+  if (d.n_banned)
+    TB_CUDA(c, cudaMemcpy(d.banned_list, list.data(), list.size() * sizeof(int), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+int de_ensure_banned(TbCtx* c) {
+  auto& d = c->de;
+  if (!d.banned) {
+    TB_CUDA(c, cudaMalloc(&d.banned, (size_t)c->m));
+    TB_CUDA(c, cudaMemset(d.banned, 0, (size_t)c->m));
+  }
   return 0;
 }
 
@@ -354,6 +546,83 @@ int tb_de_step(tb_ctx* c, const int32_t* slots, int n_slots, double h2, int mode
   return 0;
 }
 
+int tb_de_set_removed(tb_ctx* c, const int32_t* markers, int n) {
+  if (!c) return -1;
+  auto& d = c->de;
+  if (!d.keys) return de_fail(c, "tb_de_set_removed: call tb_de_init first");
+  if (n < 0 || (n > 0 && !markers)) return de_fail(c, "tb_de_set_removed: bad argument");
+  for (int j = 0; j < n; ++j)
+    if (markers[j] < 0 || markers[j] >= c->m) return de_fail(c, "tb_de_set_removed: marker index out of range");
+  TB_CUDA(c, cudaSetDevice(c->device));
+  TB_CUDA(c, cudaStreamSynchronize(c->stream));
+  if (int rc = de_ensure_banned(c)) return rc;
+  std::vector<unsigned char> flags(c->m, 0);
+  for (int j = 0; j < n; ++j) flags[markers[j]] = 1;
+  TB_CUDA(c, cudaMemcpy(d.banned, flags.data(), (size_t)c->m, cudaMemcpyHostToDevice));
+  return de_refresh_banned_list(c);
+}
+
+int tb_de_ban_genome(tb_ctx* c, int which, int32_t* n_removed_out) {
+  if (!c) return -1;
+  auto& d = c->de;
+  if (!d.keys) return de_fail(c, "tb_de_ban_genome: call tb_de_init first");
+  if (which < 0 || which >= d.P) return de_fail(c, "tb_de_ban_genome: individual out of range");
+  TB_CUDA(c, cudaSetDevice(c->device));
+  if (int rc = de_ensure_banned(c)) return rc;
+  int* tmp = nullptr;
+  TB_CUDA(c, cudaMalloc(&tmp, (size_t)d.k * sizeof(int)));
+  de_decode_kernel<<<1, 1024, 0, c->stream>>>(d.keys + (size_t)which * c->m, c->m, d.k, tmp, d.k);
+  de_set_flags_kernel<<<(d.k + 255) / 256, 256, 0, c->stream>>>(d.banned, tmp, d.k);
+  cudaError_t e = cudaGetLastError();
+  cudaError_t e2 = cudaStreamSynchronize(c->stream);
+  cudaFree(tmp);
+  c->launches += 2;
+  if (e != cudaSuccess || e2 != cudaSuccess) return de_fail(c, "tb_de_ban_genome: device execution failed", -2);
+  if (int rc = de_refresh_banned_list(c)) return rc;
+  if (n_removed_out) *n_removed_out = d.n_banned;
+  return 0;
+}
+
+int tb_de_evaluate_testing(tb_ctx* c, int slot, double h2, int mode_rule, double* fitness_out) {
+  if (!c) return -1;
+  auto& d = c->de;
+  if (!d.keys) return de_fail(c, "tb_de_evaluate_testing: call tb_de_init first");
+  if (!fitness_out) return de_fail(c, "tb_de_evaluate_testing: null output");
+  TB_CUDA(c, cudaSetDevice(c->device));
+  const int stride = d.k + d.n_banned;
+  std::vector<int> h_lens;
+  if (int rc = de_ensure_rows(c, stride)) return rc;
+  de_decode_kernel<<<d.P, 1024, 0, c->stream>>>(d.keys, c->m, d.k, d.rows, stride);   // room for the removed markers
+  TB_CUDA(c, cudaGetLastError());
+  c->launches += 1;
+  if (d.n_banned) {
+    const size_t smem = ((size_t)(c->m + 31) / 32) * 4;
+    if (smem > 200 * 1024) return de_fail(c, "tb_de_evaluate_testing: marker bitmap exceeds shared memory");
+    if (smem > 48 * 1024)
+      TB_CUDA(c, cudaFuncSetAttribute(de_union_banned_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    de_union_banned_kernel<<<d.P, 1024, smem, c->stream>>>(d.rows, stride, d.k, c->m, d.banned_list, d.n_banned, d.lens);
+    TB_CUDA(c, cudaGetLastError());
+    c->launches += 1;
+    if (int rc = de_stage_rows(c, stride, h_lens)) return rc;
+  } else {
+    if (int rc = de_ensure_idx(c, (size_t)d.P * d.k)) return rc;
+    TB_CUDA(c, cudaMemcpyAsync(c->d_idx, d.rows, (size_t)d.P * d.k * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+    c->h_off.resize(d.P + 1);
+    for (int i = 0; i <= d.P; ++i) c->h_off[i] = (long long)i * d.k;
+    c->P = d.P;
+  }
+  if (int rc = de_ensure_raw(c, 1)) return rc;
+  const int32_t slots[1] = {slot};
+  int rc = tb_internal_eval_device(c, slots, 1, h2, mode_rule, d.raw_fit);
+  cudaError_t ce = cudaSuccess;
+  if (rc == 0) ce = cudaMemcpyAsync(fitness_out, d.raw_fit, (size_t)d.P * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+  cudaError_t se = cudaStreamSynchronize(c->stream);
+  tb_internal_collect_spans(c);
+  if (rc) return rc;
+  if (ce != cudaSuccess || se != cudaSuccess) return de_fail(c, "tb_de_evaluate_testing: device execution failed", -2);
+  return 0;
+}
+
 int tb_de_get(tb_ctx* c, int what, int which, void* out, size_t nbytes) {
   if (!c || !out) return -1;
   auto& d = c->de;
@@ -372,7 +641,7 @@ int tb_de_get(tb_ctx* c, int what, int which, void* out, size_t nbytes) {
       if (nbytes < need) return de_fail(c, "tb_de_get: buffer too small");
       int* tmp = nullptr;
       TB_CUDA(c, cudaMalloc(&tmp, need));
-      de_decode_kernel<<<1, 1024, 0, c->stream>>>(d.keys + (size_t)which * c->m, c->m, d.k, tmp);
+      de_decode_kernel<<<1, 1024, 0, c->stream>>>(d.keys + (size_t)which * c->m, c->m, d.k, tmp, d.k);
       cudaError_t e = cudaMemcpyAsync(out, tmp, need, cudaMemcpyDeviceToHost, c->stream);
       cudaError_t e2 = cudaStreamSynchronize(c->stream);
       cudaFree(tmp);
@@ -381,9 +650,16 @@ int tb_de_get(tb_ctx* c, int what, int which, void* out, size_t nbytes) {
       return 0;
     }
     case 5: src = c->d_idx; need = (size_t)d.P * d.k * 4; break;                  // genomes of the last evaluated batch
+    case 6: src = d.banned_list; need = (size_t)d.n_banned * 4; break;            // removed markers, ascending
+    case 7: src = d.lens; need = (size_t)d.P * 4; break;                          // list lengths of the last filtered batch
+    case 8: {                                                                     // flat lists of the last evaluated batch
+      src = c->d_idx; need = (size_t)c->h_off[c->P] * 4; break;
+    }
     default: return de_fail(c, "tb_de_get: unknown item");
   }
   if (nbytes < need) return de_fail(c, "tb_de_get: buffer too small");
+  if (need == 0) return 0;
+  if (!src) return de_fail(c, "tb_de_get: nothing recorded yet for this item");
   TB_CUDA(c, cudaMemcpy(out, src, need, cudaMemcpyDeviceToHost));
   return 0;
 }

@@ -112,6 +112,14 @@ struct TbCtx {
     size_t raw_cap = 0;
     int *abc = nullptr, *fixed = nullptr, *take = nullptr;
     unsigned char* mask = nullptr;
+    // SNP removal (tblup/evaluator.py:589-633): flags per marker, the same set as an ascending list, scratch rows
+    unsigned char* banned = nullptr;
+    int* banned_list = nullptr;
+    int n_banned = 0;
+    int* rows = nullptr;
+    size_t rows_cap = 0;
+    int* lens = nullptr;
+    long long* d_off = nullptr;
   } de;
   double stage_ms[TB_ST_COUNT] = {};
   unsigned long long stage_launches[TB_ST_COUNT] = {};

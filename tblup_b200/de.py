@@ -65,6 +65,54 @@ class DeviceDE:
             best.append(float(np.nanmax(self.fitness())))
         return best
 
+    # ---- SNP removal on the device (tblup/evaluator.py:569-633) ----------------------------------------------------
+    def set_removed(self, markers):
+        """Replace the removed-marker set with a host list (e.g. the state of a host-side SNPRemovalHandler)."""
+        a = np.ascontiguousarray(np.asarray(markers, dtype=np.int32).ravel())
+        self.eng._check(self.eng._lib.tb_de_set_removed(self.eng._ctx, a.ctypes.data if a.size else None, a.size),
+                        "tb_de_set_removed")
+
+    def ban_genome(self, i):
+        """Add the decoded genome of individual ``i`` to the removed set (device side); returns the set's new size."""
+        n = C.c_int32(0)
+        self.eng._check(self.eng._lib.tb_de_ban_genome(self.eng._ctx, int(i), C.byref(n)), "tb_de_ban_genome")
+        return int(n.value)
+
+    def removed(self):
+        """Removed markers, ascending (the handler's ``removed`` array)."""
+        lens = self._removed_count()
+        return self._get(6, (lens,), np.int32) if lens else np.empty(0, dtype=np.int32)
+
+    def _removed_count(self):
+        return int(self.eng.info("de_removed"))
+
+    def maybe_remove(self, threshold, slots=(0,), h2=0.4, mode=MODE_AUTO):
+        """The handler's rule (evaluator.py:601-611): when the best fitness exceeds ``threshold`` the best individual's
+        markers are removed and the population is scored again without them.  Returns True when it fired."""
+        fit = self.fitness()
+        if not np.any(fit > threshold):
+            return False
+        self.ban_genome(int(np.nanargmax(fit)))
+        self.evaluate(slots, h2, mode)
+        return True
+
+    def evaluate_testing(self, slot, h2=0.4, mode=MODE_AUTO):
+        """Testing accuracy of the population: union(genome, removed) on row set ``slot`` (evaluator.py:407-431)."""
+        out = np.empty(self.P, dtype=np.float64)
+        self.eng._check(self.eng._lib.tb_de_evaluate_testing(self.eng._ctx, int(slot), float(h2), int(mode),
+                                                             out.ctypes.data), "tb_de_evaluate_testing")
+        return out
+
+    def last_lengths(self):
+        """Marker counts of the last batch scored with a non-empty removed set."""
+        return self._get(7, (self.P,), np.int32)
+
+    def last_lists(self):
+        """The ragged marker lists of the last scored batch (after removal / union), one array per individual."""
+        off = np.asarray(self.eng.staged_offsets())
+        flat = self._get(8, (int(off[-1]),), np.int32)
+        return [flat[off[i]:off[i + 1]] for i in range(self.P)]
+
     def _get(self, what, shape, dtype, which=0):
         out = np.empty(shape, dtype=dtype)
         self.eng._check(self.eng._lib.tb_de_get(self.eng._ctx, what, int(which), out.ctypes.data, out.nbytes), "tb_de_get")

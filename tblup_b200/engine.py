@@ -232,6 +232,13 @@ class GblupEngine:
             raise KeyError(name)
         return int(v.value)
 
+    def staged_offsets(self):
+        """Offsets (P + 1) of the ragged batch currently staged on the device."""
+        P = self.info("staged")
+        off = np.zeros(P + 1, dtype=np.int64)
+        self._check(self._lib.tb_staged_offsets(self._ctx, off.ctypes.data, off.size), "tb_staged_offsets")
+        return off
+
     def resident_genotype_bytes(self):
         b = C.c_uint64(0)
         self._check(self._lib.tb_storage_info(self._ctx, None, C.byref(b)), "tb_storage_info")

@@ -108,3 +108,90 @@ def test_device_driven_generations_improve_fitness():
         assert abs(O.exact_blup(de.genome(best), tr, va, x, y, 0.4) - prev[best]) < 1e-7
     finally:
         eng.close()
+
+
+def test_device_snp_removal_and_testing_accuracy():
+    """SNP removal on the device against the handler's arithmetic (oracle/de_oracle.py, itself checked against the
+    reference class in tests/test_oracle_golden.py): banned set, filtered lists, fitness on the filtered lists,
+    fitness 0.0 for an emptied individual, and the testing accuracy on union(genome, removed)."""
+    from tblup_b200.de import DeviceDE
+    from tblup_b200 import engine as E
+    dim, P, length = 900, 10, 120
+    eng, x, y, tr, va = _engine(dim, n=150, seed=5)
+    n = x.shape[0]
+    te = np.setdiff1d(np.arange(n), np.concatenate([tr, va]))
+    both = np.concatenate([tr, va])
+    eng.set_rowset(1, both, te)
+    try:
+        rng = np.random.default_rng(9)
+        keys = rng.uniform(size=(P, dim))
+        keys[3] = keys[7]                                   # a twin of the individual that will be banned
+        de = DeviceDE(eng, P, length, keys=keys)
+        genomes = [np.sort(D.decode(kv, length)) for kv in keys]
+        fit0 = de.evaluate(slots=[0], h2=0.4)
+        want0 = np.array([O.exact_blup(g, tr, va, x, y, 0.4) for g in genomes])
+        assert np.abs(fit0 - want0).max() < 1e-7
+        # testing accuracy before any removal: the plain genomes on train+valid -> test
+        t0 = de.evaluate_testing(1, h2=0.4)
+        assert np.abs(t0 - np.array([O.exact_blup(g, both, te, x, y, 0.4) for g in genomes])).max() < 1e-7
+
+        removed = D.remove_best(np.array([]), D.decode(keys[7], length), r=length)
+        assert de.ban_genome(7) == len(removed)
+        assert np.array_equal(de.removed(), removed.astype(np.int32))
+
+        fit1 = de.evaluate(slots=[0], h2=0.4)
+        kept = [D.filtered_genome(g, removed) for g in genomes]
+        assert np.array_equal(de.last_lengths(), [len(kk) for kk in kept])
+        lists = de.last_lists()
+        for i in range(P):
+            if len(kept[i]):
+                assert np.array_equal(np.sort(lists[i]), kept[i])
+        want1 = np.array([O.exact_blup(kk, tr, va, x, y, 0.4) if len(kk) else 0.0 for kk in kept])
+        assert len(kept[7]) == 0 and len(kept[3]) == 0 and fit1[7] == 0.0 and fit1[3] == 0.0
+        assert np.abs(fit1 - want1).max() < 1e-7
+
+        # a second ban accumulates (union), and a host-provided list replaces the set
+        removed2 = D.remove_best(removed, D.decode(keys[0], length), r=5)       # r < len: still the whole genome
+        assert de.ban_genome(0) == len(removed2)
+        assert np.array_equal(de.removed(), removed2.astype(np.int32))
+        t1 = de.evaluate_testing(1, h2=0.4)
+        want_t = np.array([O.exact_blup(D.testing_genome(g, removed2), both, te, x, y, 0.4) for g in genomes])
+        assert np.abs(t1 - want_t).max() < 1e-7
+        assert np.array_equal(np.sort(de.last_lists()[4]), D.testing_genome(genomes[4], removed2))
+        de.set_removed(removed)
+        assert np.array_equal(de.removed(), removed.astype(np.int32))
+        assert np.abs(de.evaluate(slots=[0], h2=0.4) - want1).max() < 1e-7
+
+        # one generation with the removed set active: offspring are scored on their filtered lists
+        abc = np.array([[(i + 1) % P, (i + 2) % P, (i + 3) % P] for i in range(P)], dtype=np.int32)
+        fixed = np.arange(P, dtype=np.int32)
+        mask = rng.uniform(size=(P, dim)) < 0.5
+        take = de.step(0.5, 0.5, slots=[0], h2=0.4, abc=abc, fixed=fixed, mask=mask)
+        child = de.child_keys()
+        ckept = [D.filtered_genome(np.sort(D.decode(kv, length)), removed) for kv in child]
+        cwant = np.array([O.exact_blup(kk, tr, va, x, y, 0.4) if len(kk) else 0.0 for kk in ckept])
+        assert np.abs(de.child_fitness() - cwant).max() < 1e-7
+        near_tie = np.abs(cwant - want1) < 1e-6
+        assert np.array_equal(take[~near_tie], D.select(want1, cwant)[~near_tie])
+        de.set_removed([])
+        assert de.removed().size == 0
+    finally:
+        eng.close()
+
+
+def test_maybe_remove_follows_the_handler_rule():
+    from tblup_b200.de import DeviceDE
+    dim, P, length = 600, 8, 80
+    eng, x, y, tr, va = _engine(dim, n=150, seed=6)
+    try:
+        de = DeviceDE(eng, P, length, seed=4)
+        fit = de.evaluate(slots=[0], h2=0.4)
+        assert not de.maybe_remove(float(np.nanmax(fit)) + 1e-9)          # threshold not exceeded: nothing happens
+        assert de.removed().size == 0
+        best = int(np.nanargmax(fit))
+        genome = de.genome(best)
+        assert de.maybe_remove(float(np.nanmax(fit)) - 1e-9)              # exceeded: best genome banned, rescored
+        assert np.array_equal(de.removed(), np.sort(genome))
+        assert de.fitness()[best] == 0.0
+    finally:
+        eng.close()

@@ -4,6 +4,8 @@ Both layers are pinned: the reference-faithful restatement must reproduce the re
 rounding noise, and the exact-integer restatement (the specification of the CUDA kernels) must agree
 with them far inside the 1e-6 fitness tolerance of BASELINE.json's north_star.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -83,3 +85,41 @@ def test_pearson_conventions():
     a, b = rng.standard_normal(50), rng.standard_normal(50)
     assert abs(O.pearson_abs(a, b) - abs(pearsonr(a, b)[0])) < 1e-15
     assert np.isnan(O.pearson_abs(np.ones(5), np.arange(5.0)))
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/tblup"), reason="reference checkout not present")
+def test_removal_restatement_matches_reference_handler():
+    """oracle/de_oracle.py's SNP-removal helpers against the live tblup.evaluator.SNPRemovalHandler."""
+    import sys
+    sys.path.insert(0, "/root/reference")
+    try:
+        from tblup.evaluator import SNPRemovalHandler
+    finally:
+        sys.path.remove("/root/reference")
+    from oracle import de_oracle as D
+
+    class Indv:
+        def __init__(self, uid, genome, fitness):
+            self.uid, self.genome, self.fitness = uid, np.asarray(genome), fitness
+
+        def set_fitness(self, f):
+            self.fitness = f
+
+        def __len__(self):
+            return len(self.genome)
+
+    rng = np.random.default_rng(3)
+    for r in (3, 40, 400):
+        h = SNPRemovalHandler(r, 0.1, 0.4, True)
+        assert abs(h.threshold - D.removal_threshold(0.4, 0.1)) < 1e-15
+        pop = [Indv(i, rng.choice(500, size=40, replace=False), f) for i, f in enumerate([0.2, 0.9, 0.5, 0.1])]
+        pop[3].genome = pop[1].genome[::-1].copy()         # emptied by the removal
+        archive = {0: 0.2}
+        to_eval, idx, fired = h.genomes_to_evaluate(pop, archive)
+        assert fired
+        want_removed = D.remove_best(np.array([]), pop[1].genome, r)
+        assert np.array_equal(h.removed, want_removed)
+        assert idx == [0, 2] and pop[1].fitness == 0.0 and pop[3].fitness == 0.0
+        for g, i in zip(to_eval, idx):
+            assert np.array_equal(g, D.filtered_genome(pop[i].genome, want_removed))
+        assert np.array_equal(h.combine_with_removed(pop[2].genome), D.testing_genome(pop[2].genome, want_removed))
