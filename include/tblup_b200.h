@@ -97,7 +97,8 @@ int tb_eval(tb_ctx* ctx, const int32_t* slots, int n_slots, const int32_t* idx_f
             int P, double h2, int mode_rule, double* fitness_out);
 
 /* Raw uncentred cross-products of one genome over universe rows [0, rows): out[a*rows + b], b <= a
- * (upper triangle zero).  impl 0 = tcgen05 kernel, 1 = plain dp4a verification kernel.
+ * (upper triangle zero).  impl 0 = tcgen05 int8 kernel, 1 = plain dp4a verification kernel, 2 = tcgen05 fp4 (E2M1)
+ * kernel (packed resident genotypes only).
  * The integer part of make_grm (tblup/utils.py:17). */
 int tb_gram_debug(tb_ctx* ctx, const int32_t* idx, int k, int rows, int impl, int32_t* out);
 
@@ -109,7 +110,9 @@ int tb_debug_fetch(tb_ctx* ctx, int what, int job, void* out, size_t nbytes);
  * integer operator [default]; 1 = fp64 Cholesky throughout),
  * "fuse_scale" (0/1, default 1: with one contiguous row set in mixed precision the Gram epilogue writes the scaled
  * fp32 matrix itself), "wide_panel" (0/1, default 1: 256-wide Cholesky panel through the inverse of the diagonal
- * block), "narrow_c" (0/1, default 1: int16 storage of the cross-products when 4 k <= 32 767 for the whole batch) */
+ * block), "narrow_c" (0/1, default 1: int16 storage of the cross-products when 4 k <= 32 767 for the whole batch),
+ * "gram_fp4" (0/1, default 1: with packed resident genotypes the Gram runs on E2M1 operands, tcgen05 kind::mxf4 --
+ * dosages 0/1/2 are exact in E2M1 and the fp32 accumulators hold the same integers; 0 = int8 operands) */
 int tb_set_option(tb_ctx* ctx, const char* name, long long value);
 
 /* Facts about the last evaluation / the context: "last_c16", "last_fused_scale", "last_mixed", "last_wave",

@@ -74,20 +74,18 @@ inline void count(TbCtx* c, int stage, int n) {
 // Order matters for L2 reuse when one genome's panel is larger than L2 (config 4: 800 MB): the persistent CTAs
 // take consecutive list entries, so the list walks super-blocks of 12 x 6 tiles (1 536 x 1 536 entries): the ~148
 // tiles in flight then share 12 A row-blocks and 6 B row-blocks instead of streaming one long tile row.
-void build_tiles(int rpad, const std::vector<unsigned char>& has_train, std::vector<int>& tiles) {
+void build_tiles(int rpad, const std::vector<unsigned char>& has_train, std::vector<int>& tiles, int bn = TB_GRAM_BN) {
   tiles.clear();
-  const int nI = rpad / TB_GRAM_BM, nJ = (rpad + TB_GRAM_BN - 1) / TB_GRAM_BN;
+  const int nI = rpad / TB_GRAM_BM, nJ = (rpad + bn - 1) / bn;
   const int SBI = 12, SBJ = 6;
   for (int I0 = 0; I0 < nI; I0 += SBI) {
     for (int J0 = 0; J0 < nJ; J0 += SBJ) {
       for (int I = I0; I < std::min(nI, I0 + SBI); ++I) {
         for (int J = J0; J < std::min(nJ, J0 + SBJ); ++J) {
-          if (J * TB_GRAM_BN > I * TB_GRAM_BM + TB_GRAM_BM - 1) continue;
+          if (J * bn > I * TB_GRAM_BM + TB_GRAM_BM - 1) continue;
           bool need = has_train.empty() || has_train[I];
-          for (int h = 0; h < 2 && !need; ++h) {
-            int blk = 2 * J + h;
+          for (int blk = J * bn / TB_GRAM_BM; blk <= (J * bn + bn - 1) / TB_GRAM_BM && !need; ++blk)
             if (blk < nI && has_train[blk]) need = true;
-          }
           if (need) tiles.push_back((I << 16) | J);
         }
       }
@@ -172,7 +170,12 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     if (k <= 0) return fail(c, "tb_eval_staged: empty genome at position " + std::to_string(i));
     kmax = std::max(kmax, k);
   }
-  const int kstride_max = tb_round_up(kmax, TB_GRAM_BK);
+  // E2M1 Gram: needs the packed resident matrix (its gather is written for it); every sum is an integer <= 4 kmax,
+  // exact in the fp32 accumulators below 2^24
+  const bool fp4 = c->gram_fp4 && c->d_x2 != nullptr && 4LL * kmax < (1LL << 24);
+  c->last_fp4 = fp4 ? 1 : 0;
+  const int kq = fp4 ? TB_GRAM_BK_FP4 : TB_GRAM_BK;      // markers per k-block
+  const int kstride_max = tb_round_up(kmax, kq);
   // every cross-product is at most 4 k: int16 storage is exact for the whole batch when 4 kmax <= 32 767
   const bool c16 = mixed && c->narrow_c && 4LL * kmax <= 32767;
   c->last_c16 = c16 ? 1 : 0;
@@ -194,7 +197,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
   cudaStream_t st = c->stream;
   // tile list + genome offsets (device copies live at the start of the arena)
   std::vector<int> tiles;
-  build_tiles(rpad, has_train, tiles);
+  build_tiles(rpad, has_train, tiles, fp4 ? TB_GRAM_BN_FP4 : TB_GRAM_BN);
   const int n_tiles = (int)tiles.size();
 
   Arena ar;
@@ -221,12 +224,13 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     for (int w = 0; w < Wc; ++w) {
       const int k = (int)(c->h_off[w0 + w + 1] - c->h_off[w0 + w]);
       kw = std::max(kw, k);
-      h_kb[w] = tb_round_up(k, TB_GRAM_BK) / TB_GRAM_BK;
+      h_kb[w] = tb_round_up(k, kq) / kq;
     }
-    const int kstride = tb_round_up(kw, TB_GRAM_BK);
+    const int kstride = tb_round_up(kw, kq);             // markers
+    const int kstride_b = fp4 ? kstride / 2 : kstride;    // bytes of one panel row
 
     ar.off = arena_mark;
-    int8_t* d_panel = ar.take<int8_t>(((size_t)Wc * rpad + 128) * kstride);
+    int8_t* d_panel = ar.take<int8_t>(((size_t)Wc * rpad + 128) * kstride_b);
     int32_t* d_C = ar.take<int32_t>((size_t)Wc * rpad * rpad);
     long long* d_s = ar.take<long long>((size_t)n_jobs * rpad);
     long long* d_SQ = ar.take<long long>((size_t)n_jobs * 2);
@@ -365,13 +369,16 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     span_end(c, sp);
 
     sp = span_begin(c, TB_ST_GATHER);
-    TB_CUDA(c, tb_launch_gather(c->geno(), c->d_idx, d_off, w0, Wc, rpad, kstride, d_panel, st));
+    if (fp4)
+      TB_CUDA(c, tb_launch_gather_fp4(c->geno(), c->d_idx, d_off, w0, Wc, rpad, kstride_b, d_panel, st));
+    else
+      TB_CUDA(c, tb_launch_gather(c->geno(), c->d_idx, d_off, w0, Wc, rpad, kstride, d_panel, st));
     span_end(c, sp);
     count(c, TB_ST_GATHER, 1);
     if (c->stop_after == TB_ST_GATHER) continue;
 
     sp = span_begin(c, TB_ST_CENTRE);
-    TB_CUDA(c, tb_launch_centre_terms(d_panel, rpad, kstride, c->d_idx, d_off, w0, Wc, centre_slots, d_kb, d_cs, d_csg, d_s, d_SQ, st));
+    TB_CUDA(c, tb_launch_centre_terms(d_panel, rpad, kstride, c->d_idx, d_off, w0, Wc, centre_slots, d_kb, d_cs, d_csg, d_s, d_SQ, st, fp4 ? 1 : 0));
     span_end(c, sp);
     count(c, TB_ST_CENTRE, 2);
     if (c->stop_after == TB_ST_CENTRE) continue;
@@ -379,8 +386,8 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     sp = span_begin(c, TB_ST_GRAM);
     {
       std::string e;
-      cudaError_t ce = tb_launch_gram_tc(d_panel, Wc, rpad, kstride, d_kb, d_tiles, n_tiles, d_C, c->n_sm, st, &e,
-                                         fuse_scale ? d_scale : nullptr, d_L32, max_ntp, c16 ? 1 : 0);
+      cudaError_t ce = tb_launch_gram_tc(d_panel, Wc, rpad, kstride_b, d_kb, d_tiles, n_tiles, d_C, c->n_sm, st, &e,
+                                         fuse_scale ? d_scale : nullptr, d_L32, max_ntp, c16 ? 1 : 0, fp4 ? 1 : 0);
       if (ce != cudaSuccess) return fail(c, "gram launch: " + (e.empty() ? std::string(cudaGetErrorString(ce)) : e), -2);
     }
     span_end(c, sp);
@@ -620,7 +627,8 @@ int tb_create_ex(const void* geno_any, int layout, int storage, int n, int m, co
   }
   if (chk(tb_gram_tc_init(), "gram kernel init") || chk(tb_chol_init(), "cholesky kernel init") ||
       chk(tb_solve_init(), "solve kernel init") ||
-      chk(tb_chol_tc_init(), "tensor-core cholesky init") || chk(tb_solve_mixed_init(), "mixed solve init"))
+      chk(tb_chol_tc_init(), "tensor-core cholesky init") || chk(tb_solve_mixed_init(), "mixed solve init") ||
+      chk(tb_gather_init(), "gather init"))
     return bail("");
   *out = c;
   return 0;
@@ -776,11 +784,15 @@ int tb_gram_debug(tb_ctx* c, const int32_t* idx, int k, int rows, int impl, int3
   for (int q = 0; q < k; ++q)
     if (idx[q] < 0 || idx[q] >= c->m) return fail(c, "tb_gram_debug: marker index out of range");
   TB_CUDA(c, cudaSetDevice(c->device));
-  const int rpad = tb_round_up(rows, TB_GRAM_BM), kstride = tb_round_up(k, TB_GRAM_BK);
+  const bool fp4 = impl == 2;
+  if (fp4 && !c->d_x2) return fail(c, "tb_gram_debug: the fp4 Gram needs packed resident genotypes");
+  const int kq = fp4 ? TB_GRAM_BK_FP4 : TB_GRAM_BK;
+  const int rpad = tb_round_up(rows, TB_GRAM_BM), kmark = tb_round_up(k, kq);
+  const int kstride = fp4 ? kmark / 2 : kmark;          // bytes per panel row
   std::vector<int> tiles;
-  build_tiles(rpad, std::vector<unsigned char>(), tiles);
+  build_tiles(rpad, std::vector<unsigned char>(), tiles, fp4 ? TB_GRAM_BN_FP4 : TB_GRAM_BN);
   const long long off[2] = {0, k};
-  const int kb = kstride / TB_GRAM_BK;
+  const int kb = kmark / kq;
   int8_t* d_panel = nullptr;
   int32_t* d_C = nullptr;
   int *d_i = nullptr, *d_t = nullptr, *d_kb = nullptr;
@@ -802,10 +814,12 @@ int tb_gram_debug(tb_ctx* c, const int32_t* idx, int k, int rows, int impl, int3
     ck(cudaMemcpyAsync(d_t, tiles.data(), tiles.size() * sizeof(int), cudaMemcpyHostToDevice, st), "H2D");
     ck(cudaMemcpyAsync(d_kb, &kb, sizeof(int), cudaMemcpyHostToDevice, st), "H2D");
     ck(cudaMemcpyAsync(d_off, off, sizeof(off), cudaMemcpyHostToDevice, st), "H2D");
-    ck(tb_launch_gather(c->geno(), d_i, d_off, 0, 1, rpad, kstride, d_panel, st), "gather");
-    if (impl == 0) {
+    if (fp4) ck(tb_launch_gather_fp4(c->geno(), d_i, d_off, 0, 1, rpad, kstride, d_panel, st), "gather");
+    else ck(tb_launch_gather(c->geno(), d_i, d_off, 0, 1, rpad, kstride, d_panel, st), "gather");
+    if (impl == 0 || fp4) {
       std::string e;
-      cudaError_t ce = tb_launch_gram_tc(d_panel, 1, rpad, kstride, d_kb, d_t, (int)tiles.size(), d_C, c->n_sm, st, &e);
+      cudaError_t ce = tb_launch_gram_tc(d_panel, 1, rpad, kstride, d_kb, d_t, (int)tiles.size(), d_C, c->n_sm, st, &e,
+                                         nullptr, nullptr, 0, 0, fp4 ? 1 : 0);
       if (ce != cudaSuccess && rc == 0) rc = fail(c, "tb_gram_debug gram_tc: " + (e.empty() ? std::string(cudaGetErrorString(ce)) : e), -2);
     } else {
       ck(tb_launch_gram_simt(d_panel, 1, rpad, kstride, d_kb, d_C, st), "gram_simt");
@@ -903,6 +917,7 @@ int tb_set_option(tb_ctx* c, const char* name, long long value) {
   else if (s == "fuse_scale") c->fuse_scale = value != 0;
   else if (s == "wide_panel") c->wide_panel = value != 0;
   else if (s == "narrow_c") c->narrow_c = value != 0;
+  else if (s == "gram_fp4") c->gram_fp4 = value != 0;
   else if (s == "storage") return fail(c, "tb_set_option: storage is fixed at tb_create_ex");
   else return fail(c, "tb_set_option: unknown option '" + s + "'");
   return 0;
@@ -918,6 +933,7 @@ int tb_get_info(const tb_ctx* c, const char* name, long long* value) {
   else if (s == "storage") *value = c->storage;
   else if (s == "wide_panel") *value = c->wide_panel;
   else if (s == "de_removed") *value = c->de.n_banned;
+  else if (s == "last_fp4") *value = c->last_fp4;
   else if (s == "staged") *value = c->P;
   else return -1;
   return 0;

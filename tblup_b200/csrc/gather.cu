@@ -121,6 +121,60 @@ __global__ void __launch_bounds__(256) gather_packed_kernel(const uint8_t* __res
   }
 }
 
+// The same gather for the fp4 Gram (gram_tc_kernel<.., FP4>): the panel holds E2M1 nibbles, two markers per byte,
+// marker 2q in the low nibble of byte q; dosage d is the nibble 2 d (E2M1: 0b0010 = 1.0, 0b0100 = 2.0).  Tile = 512
+// markers x 512 animals (64 KiB packed), a lane owns 16 markers = 8 output bytes per animal, a warp writes 256
+// contiguous bytes per animal row.  Half the panel bytes of the int8 layout.
+__global__ void __launch_bounds__(256) gather_fp4_kernel(const uint8_t* __restrict__ x2, int ld4,
+                                                         const int* __restrict__ idx, const long long* __restrict__ off,
+                                                         int w0, int rpad, int kstride_b, int8_t* __restrict__ panel) {
+  constexpr int MPL = 16, TM = 32 * MPL;
+  extern __shared__ uint32_t ptile[];            // [TM][32]
+  const int w = blockIdx.z;
+  const long long o0 = off[w0 + w];
+  const int k = (int)(off[w0 + w + 1] - o0);
+  const int j0 = blockIdx.x * TM;
+  const int kpad = tb_round_up(k, TB_GRAM_BK_FP4);   // the Gram reads [0, kpad): zeros beyond k
+  if (j0 >= kpad) return;
+  const int a0 = blockIdx.y * 512;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool lane_in = (a0 >> 2) + 4 * lane < ld4;
+
+  for (int jb = warp * 8; jb < TM; jb += 64) {
+    int src[8];
+    uint32_t v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) src[u] = (j0 + jb + u < k) ? idx[o0 + j0 + jb + u] : -1;
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      v[u] = (src[u] >= 0 && lane_in)
+                 ? *reinterpret_cast<const uint32_t*>(x2 + (size_t)src[u] * ld4 + (a0 >> 2) + 4 * lane) : 0u;
+#pragma unroll
+    for (int u = 0; u < 8; ++u) ptile[(jb + u) * 32 + ((lane + (jb + u) / MPL) & 31)] = v[u];
+  }
+  __syncthreads();
+
+  const int jl0 = lane * MPL;
+  if (j0 + jl0 >= kpad) return;                  // kpad is a multiple of 256 >= MPL: whole lanes
+  for (int c = warp; c < 32; c += 8) {
+    if (a0 + 16 * c >= rpad) break;
+    uint32_t wv[MPL];
+#pragma unroll
+    for (int t = 0; t < MPL; ++t) wv[t] = ptile[(jl0 + t) * 32 + ((c + lane) & 31)];
+    int8_t* dst = panel + ((size_t)w * rpad + a0 + 16 * c) * kstride_b + ((j0 + jl0) >> 1);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      uint32_t lo = 0, hi = 0;
+#pragma unroll
+      for (int t = 0; t < 8; ++t) {
+        lo |= ((wv[t] >> (2 * i)) & 3u) << (4 * t + 1);
+        hi |= ((wv[t + 8] >> (2 * i)) & 3u) << (4 * t + 1);
+      }
+      *reinterpret_cast<uint2*>(dst + (size_t)i * kstride_b) = make_uint2(lo, hi);
+    }
+  }
+}
+
 // csg[job][j] = colsum_job[idx[j]] (zero padded to kstride) and SQ[job] = { sum_j csg, sum_j csg^2 }.
 __global__ void __launch_bounds__(256) centre_sq_kernel(const int* __restrict__ idx, const long long* __restrict__ off,
                                                         int w0, int n_slots, int kstride,
@@ -199,7 +253,57 @@ __global__ void __launch_bounds__(256) centre_rows_kernel(const int8_t* __restri
   }
 }
 
+// centre_rows_kernel for the fp4 panel: 16 bytes = 32 markers (nibble = 2 x dosage), kstride counts markers.
+__global__ void __launch_bounds__(256) centre_rows_fp4_kernel(const int8_t* __restrict__ panel, int rpad, int kstride,
+                                                              const int* __restrict__ kblocks, int n_slots,
+                                                              const int* __restrict__ csg, long long* __restrict__ s) {
+  const int job = blockIdx.y;
+  const int w = job / n_slots;
+  const int a0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 4, lane = threadIdx.x & 31;
+  if (a0 >= rpad) return;
+  const int kstride_b = kstride / 2;
+  const int n16 = kblocks[w] * TB_GRAM_BK / 16;          // a k-block is 128 bytes in either layout
+  const uint4* row = reinterpret_cast<const uint4*>(panel + ((size_t)w * rpad + a0) * kstride_b);
+  const size_t rs = kstride_b / 16;
+  const int4* cg = reinterpret_cast<const int4*>(csg + (size_t)job * kstride);
+  long long acc[4] = {0, 0, 0, 0};
+  auto dot8 = [](const uint32_t v, const int4 c0, const int4 c1) -> int {
+    return (int)((v >> 1) & 3u) * c0.x + (int)((v >> 5) & 3u) * c0.y + (int)((v >> 9) & 3u) * c0.z +
+           (int)((v >> 13) & 3u) * c0.w + (int)((v >> 17) & 3u) * c1.x + (int)((v >> 21) & 3u) * c1.y +
+           (int)((v >> 25) & 3u) * c1.z + (int)((v >> 29) & 3u) * c1.w;
+  };
+  for (int j = lane; j < n16; j += 32) {
+    const uint4 v0 = row[j], v1 = row[rs + j], v2 = row[2 * rs + j], v3 = row[3 * rs + j];
+    const uint32_t a[4][4] = {{v0.x, v0.y, v0.z, v0.w}, {v1.x, v1.y, v1.z, v1.w}, {v2.x, v2.y, v2.z, v2.w},
+                              {v3.x, v3.y, v3.z, v3.w}};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {                        // 8 markers per 32-bit word
+      const int4 c0 = cg[8 * j + 2 * q], c1 = cg[8 * j + 2 * q + 1];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[r] += dot8(a[r][q], c0, c1);   // 8 x (<= 2) x (< 2^26) fits an int
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    long long v = acc[r];
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s[(size_t)job * rpad + a0 + r] = v;
+  }
+}
+
 }  // namespace
+
+cudaError_t tb_gather_init() {
+  return cudaFuncSetAttribute(gather_fp4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 512 * 128);
+}
+
+cudaError_t tb_launch_gather_fp4(const TbGeno& g, const int* d_idx, const long long* d_off, int w0, int W, int rpad,
+                                 int kstride_b, int8_t* d_panel, cudaStream_t st) {
+  if (!g.x2) return cudaErrorInvalidValue;       // written for the packed matrix
+  dim3 grid((2 * kstride_b + 511) / 512, (rpad + 511) / 512, W);
+  gather_fp4_kernel<<<grid, 256, 512 * 128, st>>>(g.x2, g.ld4, d_idx, d_off, w0, rpad, kstride_b, d_panel);
+  return cudaGetLastError();
+}
 
 cudaError_t tb_launch_gather(const TbGeno& g, const int* d_idx, const long long* d_off, int w0, int W,
                              int rpad, int kstride, int8_t* d_panel, cudaStream_t st) {
@@ -216,11 +320,14 @@ cudaError_t tb_launch_gather(const TbGeno& g, const int* d_idx, const long long*
 cudaError_t tb_launch_centre_terms(const int8_t* d_panel, int rpad, int kstride, const int* d_idx,
                                    const long long* d_off, int w0, int W, int n_slots, const int* d_kblocks,
                                    const int* const* d_colsum_of, int* d_csg, long long* d_s, long long* d_SQ,
-                                   cudaStream_t st) {
+                                   cudaStream_t st, int fp4) {
   centre_sq_kernel<<<W * n_slots, 256, 0, st>>>(d_idx, d_off, w0, n_slots, kstride, d_colsum_of, d_csg, d_SQ);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   dim3 grid((rpad + 31) / 32, W * n_slots);
-  centre_rows_kernel<<<grid, 256, 0, st>>>(d_panel, rpad, kstride, d_kblocks, n_slots, d_csg, d_s);
+  if (fp4)
+    centre_rows_fp4_kernel<<<grid, 256, 0, st>>>(d_panel, rpad, kstride, d_kblocks, n_slots, d_csg, d_s);
+  else
+    centre_rows_kernel<<<grid, 256, 0, st>>>(d_panel, rpad, kstride, d_kblocks, n_slots, d_csg, d_s);
   return cudaGetLastError();
 }

@@ -23,10 +23,19 @@ using namespace tbptx;
 constexpr int BM = TB_GRAM_BM, BN = TB_GRAM_BN, BK = TB_GRAM_BK;
 constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK;                 // 16 KiB
-constexpr int B_BYTES = BN * BK;                 // 32 KiB
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 48 KiB
+constexpr int B_BYTES = BN * BK;                 // 32 KiB (int8 tiles; the fp4 variant uses 224 rows = 28 KiB)
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES;   // 48 KiB (stage slots are sized for the wider variant)
 constexpr int ACC_STAGES = 2;
-constexpr int TMEM_COLS = ACC_STAGES * BN;       // 512
+constexpr int TMEM_COLS = 512;                   // int8: 2 x 256 accumulator columns; fp4: 2 x 224 + scale factors
+// fp4 variant (kind::mxf4, E2M1 operands, K = 64 per instruction): dosages 0/1/2 are exact in E2M1 and every partial
+// sum is an integer below 2^24, so the fp32 accumulators hold the same integers the int8 path produces -- at twice
+// the MMA rate and half the operand bytes.  The block scale factors (UE8M0, one per 32 elements) are all 2^0: their
+// TMEM columns are filled once with 0x7f bytes, whatever the layout.  TMEM has 512 columns in total, so the tile is
+// 224 wide: 2 x 224 accumulator columns + 32 columns of scale factors.
+constexpr int BN_I8 = BN;
+constexpr int BN4 = TB_GRAM_BN_FP4;              // 224
+constexpr int ACC_STRIDE4 = 240;
+constexpr int SF_COL = 480;
 constexpr int EPI_WARPS = 8;                     // two per TMEM lane quarter, each owning half of the tile's columns
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
 constexpr int COLTERM_BYTES = 2 * BN * 8;         // fused scaling: two buffers of per-column integer terms
@@ -55,10 +64,39 @@ struct Barriers {
 
 // C16: the cross-products are stored as int16 (the caller guarantees 4 k <= 32 767, so C_ab <= 4 k fits): half the
 // bytes for every later pass over C (scaling, refinement mat-vecs, predictions).  Row stride stays rpad ELEMENTS.
-template <bool FUSE, bool C16>
+__host__ __device__ constexpr uint32_t umma_idesc_mxf4(int m, int n) {
+  // block-scaled descriptor: a/b format E2M1 (1), scale format UE8M0 (bit 23), K = 64 (bit 31 = 0), K-major operands
+  return (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) | (1u << 23) |
+         (static_cast<uint32_t>(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_mxf4(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate, uint32_t tmem_sfa, uint32_t tmem_sfb) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+      : "memory");
+}
+// 32 lanes x 32 columns of one 32-bit value (whole warp; lane i writes TMEM lane base + i)
+__device__ __forceinline__ void tmem_fill_32x32(uint32_t taddr, uint32_t v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, "
+      "%1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1, %1};"
+      ::"r"(taddr), "r"(v)
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+
+template <bool FUSE, bool C16, bool FP4>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int* __restrict__ tiles, int n_tiles,
+gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_b,
+               const int* __restrict__ tiles, int n_tiles,
                const int* __restrict__ kblocks, int W, int rpad, int32_t* __restrict__ C, const GramFuse fz) {
+  constexpr int BN = FP4 ? BN4 : BN_I8;                     // tile columns of this variant
+  constexpr int ACC_STRIDE = FP4 ? ACC_STRIDE4 : BN_I8;     // TMEM columns between the two accumulators
+  constexpr uint32_t STAGE_TX = A_BYTES + BN * BK;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   Barriers* bars = reinterpret_cast<Barriers*>(smem + STAGES * STAGE_BYTES);
@@ -83,6 +121,13 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int* __restrict__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = bars->tmem_base;
+  if (FP4) {
+    // scale factors: every byte 0x7f = 2^0 (UE8M0); columns SF_COL .. SF_COL + 31 of all 128 lanes
+    if (warp >= 2 && warp < 6) tmem_fill_32x32(tmem_base + (static_cast<uint32_t>((warp & 3) * 32) << 16) + SF_COL, 0x7f7f7f7fu);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+  }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -97,10 +142,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int* __restrict__
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
-          mbar_arrive_expect_tx(&bars->full[stage], STAGE_BYTES);
+          mbar_arrive_expect_tx(&bars->full[stage], STAGE_TX);
           tma_load_2d(sa, &tmap, &bars->full[stage], kb * BK, row_a);
-          tma_load_2d(sa + A_BYTES, &tmap, &bars->full[stage], kb * BK, row_b);
-          tma_load_2d(sa + A_BYTES + B_BYTES / 2, &tmap, &bars->full[stage], kb * BK, row_b + BN / 2);
+          tma_load_2d(sa + A_BYTES, &tmap_b, &bars->full[stage], kb * BK, row_b);
+          tma_load_2d(sa + A_BYTES + (BN / 2) * BK, &tmap_b, &bars->full[stage], kb * BK, row_b + BN / 2);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -120,7 +165,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int* __restrict__
         const int nkb = kblocks[w];
         mbar_wait(&bars->acc_empty[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
+        const uint32_t tmem_d = tmem_base + acc * ACC_STRIDE;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&bars->full[stage], phase);
           tc_fence_after();
@@ -130,7 +175,11 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int* __restrict__
 #pragma unroll
           for (int k = 0; k < BK / 32; ++k) {
             // advance 32 bytes along K inside the 128-byte swizzle span: +2 in 16-byte units
-            umma_s8(tmem_d, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
+            if (FP4)
+              umma_mxf4(tmem_d, adesc + 2 * k, bdesc + 2 * k, umma_idesc_mxf4(BM, BN), (kb | k) != 0,
+                        tmem_base + SF_COL, tmem_base + SF_COL + 8);
+            else
+              umma_s8(tmem_d, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
           }
           umma_commit(&bars->empty[stage]);
           if (++stage == STAGES) {
@@ -176,7 +225,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int* __restrict__
           f_NN = (double)(N * N);
           f_inv = (float)(2.0 / (double)(2 * N * S - Q));
           f_lam = (float)jb.lambda;
-          const uint32_t cw = colterm + fbuf * BN * 8;
+          const uint32_t cw = colterm + fbuf * BN_I8 * 8;
           for (int e = threadIdx.x - 64; e < BN; e += 32 * EPI_WARPS) {
             const int b = tj * BN + e;
             const double term = b < f_nt ? (double)(Q - N * jb.s[b]) : 0.0;
@@ -198,12 +247,16 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const int* __restrict__
       float* awarp = (FUSE && a_tile) ? fz.L32 + ((size_t)w * fz.ntp_all + ti * BM + q * 32) * fz.ntp_all : nullptr;
       const int rl = lane >> 2, gl = 4 * (lane & 3);          // read-back role: row 8 it + rl, words gl .. gl + 3
 #pragma unroll 1
-      for (int c = chalf * (BN / 64); c < (chalf + 1) * (BN / 64); ++c) {
+      for (int c = chalf * 4; c < (chalf + 1) * 4 && c < BN / 32; ++c) {
         const int col0 = tj * BN + c * 32;
         if (col0 >= rpad || col0 > row_hi) continue;   // outside the matrix / strictly above the diagonal
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 32, v);
+        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_STRIDE + c * 32, v);
         tmem_ld_wait();
+        if (FP4) {                                     // fp32 accumulators holding exact integers
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = (uint32_t)__float2int_rn(__uint_as_float(v[e]));
+        }
         if (C16) {
           uint32_t pk[16];
 #pragma unroll
@@ -301,39 +354,54 @@ cudaError_t tb_gram_tc_init() {
   auto set = [&](const void* fn) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   };
-  set((const void*)gram_tc_kernel<false, false>);
-  set((const void*)gram_tc_kernel<true, false>);
-  set((const void*)gram_tc_kernel<false, true>);
-  set((const void*)gram_tc_kernel<true, true>);
+  set((const void*)gram_tc_kernel<false, false, false>);
+  set((const void*)gram_tc_kernel<true, false, false>);
+  set((const void*)gram_tc_kernel<false, true, false>);
+  set((const void*)gram_tc_kernel<true, true, false>);
+  set((const void*)gram_tc_kernel<false, false, true>);
+  set((const void*)gram_tc_kernel<true, false, true>);
+  set((const void*)gram_tc_kernel<false, true, true>);
+  set((const void*)gram_tc_kernel<true, true, true>);
   return e;
 }
 
-// d_panel must have (W * rpad + 128) rows of kstride bytes allocated (slack for the last B half-tile).
+// d_panel must have (W * rpad + 128) rows of kstride BYTES allocated (slack for the last B half-tile).
+// fp4 != 0: the panel holds E2M1 nibbles (two markers per byte, dosage d stored as 2 d), kstride = padded k / 2, one
+// k-block = 256 markers, tiles are TB_GRAM_BN_FP4 columns wide (the tile list must be built for that width).
 cudaError_t tb_launch_gram_tc(const int8_t* d_panel, int W, int rpad, int kstride, const int* d_kblocks,
                               const int* d_tiles, int n_tiles, int32_t* d_C, int n_sm, cudaStream_t st,
-                              std::string* err, const TbScaleJob* d_fuse_jobs, float* d_L32, int ntp_all, int c16) {
-  CUtensorMap tmap;
+                              std::string* err, const TbScaleJob* d_fuse_jobs, float* d_L32, int ntp_all, int c16,
+                              int fp4) {
+  CUtensorMap tmap, tmap_b;
   const cuuint64_t dims[2] = {(cuuint64_t)kstride, (cuuint64_t)W * rpad + 128};
   const cuuint64_t strides[1] = {(cuuint64_t)kstride};
-  const cuuint32_t box[2] = {(cuuint32_t)BK, 128};
   const cuuint32_t estr[2] = {1, 1};
-  CUresult r = g_encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(d_panel), dims, strides, box,
-                        estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    if (err) *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
-    return cudaErrorInvalidValue;
+  for (int which = 0; which < 2; ++which) {
+    const cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)(which == 0 ? 128 : (fp4 ? BN4 / 2 : BN / 2))};
+    CUresult r = g_encode(which == 0 ? &tmap : &tmap_b, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<int8_t*>(d_panel),
+                          dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+      if (err) *err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
+      return cudaErrorInvalidValue;
+    }
   }
   const int n_items = W * n_tiles;
   const int grid = n_items < n_sm ? n_items : n_sm;
   const GramFuse fz{d_fuse_jobs, d_L32, ntp_all};
-  if (d_fuse_jobs && c16)
-    gram_tc_kernel<true, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmap, d_tiles, n_tiles, d_kblocks, W, rpad, d_C, fz);
-  else if (d_fuse_jobs)
-    gram_tc_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmap, d_tiles, n_tiles, d_kblocks, W, rpad, d_C, fz);
-  else if (c16)
-    gram_tc_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmap, d_tiles, n_tiles, d_kblocks, W, rpad, d_C, fz);
-  else
-    gram_tc_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmap, d_tiles, n_tiles, d_kblocks, W, rpad, d_C, fz);
+  const int which = (d_fuse_jobs ? 4 : 0) | (c16 ? 2 : 0) | (fp4 ? 1 : 0);
+#define TB_GRAM_LAUNCH(F, S, P4) \
+  gram_tc_kernel<F, S, P4><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmap, tmap_b, d_tiles, n_tiles, d_kblocks, W, rpad, d_C, fz)
+  switch (which) {
+    case 0: TB_GRAM_LAUNCH(false, false, false); break;
+    case 1: TB_GRAM_LAUNCH(false, false, true); break;
+    case 2: TB_GRAM_LAUNCH(false, true, false); break;
+    case 3: TB_GRAM_LAUNCH(false, true, true); break;
+    case 4: TB_GRAM_LAUNCH(true, false, false); break;
+    case 5: TB_GRAM_LAUNCH(true, false, true); break;
+    case 6: TB_GRAM_LAUNCH(true, true, false); break;
+    default: TB_GRAM_LAUNCH(true, true, true); break;
+  }
+#undef TB_GRAM_LAUNCH
   return cudaGetLastError();
 }

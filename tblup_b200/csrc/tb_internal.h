@@ -14,6 +14,8 @@
 #define TB_GRAM_BM 128    // Gram tile rows
 #define TB_GRAM_BN 256    // Gram tile cols
 #define TB_GRAM_BK 128    // Gram K bytes per pipeline stage (one 128-byte swizzle span)
+#define TB_GRAM_BN_FP4 224  // Gram tile cols of the fp4 (E2M1) variant: 2 x 224 accumulator columns + scale factors = TMEM
+#define TB_GRAM_BK_FP4 256  // markers per k-block of the fp4 panel (128 bytes)
 
 enum TbStage {
   TB_ST_H2D = 0,
@@ -91,6 +93,8 @@ struct TbCtx {
   int max_wave = 0;
   int precision = 0;              // 0: mixed (TF32 tensor-core Cholesky + fp64 refinement) when possible, 1: fp64
   int last_mixed = 0;
+  int gram_fp4 = 1;               // 1: E2M1 Gram (kind::mxf4) when the genotypes are resident in packed form
+  int last_fp4 = 0;
   int narrow_c = 1;               // 1: int16 cross-products when every genome of the batch has 4 k <= 32 767
   int last_c16 = 0;
   int last_fused = 0;
@@ -152,11 +156,15 @@ cudaError_t tb_launch_unpack2_perm(const uint8_t* d_rows2, int n_rows, int strid
 // gather.cu
 cudaError_t tb_launch_gather(const TbGeno& g, const int* d_idx, const long long* d_off, int w0, int W,
                              int rpad, int kstride, int8_t* d_panel, cudaStream_t st);
+// fp4 panel: E2M1 nibbles, two markers per byte, kstride_b bytes per animal row (= padded k / 2), from packed genotypes
+cudaError_t tb_launch_gather_fp4(const TbGeno& g, const int* d_idx, const long long* d_off, int w0, int W, int rpad,
+                                 int kstride_b, int8_t* d_panel, cudaStream_t st);
+cudaError_t tb_gather_init();
 cudaError_t tb_launch_centre_terms(const int8_t* d_panel, int rpad, int kstride, const int* d_idx,
                                    const long long* d_off, int w0, int W, int n_slots, const int* d_kblocks,
                                    const int* const* d_colsum_of, /* [W*n_slots] device ptrs */
                                    int* d_csg /* [W*n_slots][kstride] scratch */, long long* d_s, long long* d_SQ,
-                                   cudaStream_t st);
+                                   cudaStream_t st, int fp4 = 0 /* panel rows hold nibbles; kstride counts markers */);
 
 // gram_tc.cu / gram_simt.cu
 cudaError_t tb_gram_tc_init();
@@ -167,7 +175,7 @@ struct TbScaleJob;
 cudaError_t tb_launch_gram_tc(const int8_t* d_panel, int W, int rpad, int kstride, const int* d_kblocks,
                               const int* d_tiles, int n_tiles, int32_t* d_C, int n_sm, cudaStream_t st,
                               std::string* err, const TbScaleJob* d_fuse_jobs = nullptr, float* d_L32 = nullptr,
-                              int ntp_all = 0, int c16 = 0);
+                              int ntp_all = 0, int c16 = 0, int fp4 = 0);
 cudaError_t tb_launch_gram_simt(const int8_t* d_panel, int W, int rpad, int kstride, const int* d_kblocks,
                                 int32_t* d_C, cudaStream_t st);
 

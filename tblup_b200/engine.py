@@ -172,7 +172,7 @@ class GblupEngine:
         flat, _ = pack_genomes([indices], self.m)
         out = np.empty((rows, rows), dtype=np.int32)
         self._check(self._lib.tb_gram_debug(self._ctx, flat.ctypes.data, flat.size, int(rows),
-                                            0 if impl == "tc" else 1, out.ctypes.data), "tb_gram_debug")
+                                            {"tc": 0, "simt": 1, "fp4": 2}[impl], out.ctypes.data), "tb_gram_debug")
         return out
 
     def debug_dims(self, job=0):

@@ -111,3 +111,36 @@ def test_evaluator_reads_bed(tmp_path, monkeypatch):
     b, tr_b = run(tmp_path / "g.bed", "packed2")
     assert tr_a == tr_b
     assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("k", [1, 63, 255, 256, 257, 1500, -900, -4000])
+def test_fp4_gram_bit_exact(engines, k):
+    """E2M1 operands on tcgen05 kind::mxf4 (all block scales 2^0): the fp32 accumulators must hold exactly the
+    integers of the int8 path / the oracle, for every k-block remainder and with duplicated markers."""
+    g, perm, made = engines
+    rng = np.random.default_rng(abs(k) + 17)
+    m = g["x"].shape[1]
+    idx = rng.integers(0, m, size=-k) if k < 0 else rng.choice(m, size=k, replace=False)
+    for rows in (389, 128, 31):
+        got = made["packed_from_dense"].gram_debug(idx, rows, impl="fp4")
+        assert np.array_equal(got.astype(np.int64), np.tril(O.exact_gram(g["x"], idx, perm[:rows])))
+
+
+def test_fp4_and_int8_gram_give_identical_fitness(engines):
+    from tblup_b200 import engine as E
+    g, perm, made = engines
+    genomes = unpack(g["genomes_flat"], g["genomes_off"])
+    h2 = float(g["h2"])
+    eng = made["packed_from_dense"]
+    eng.set_option("gram_fp4", 1)
+    a = eng.evaluate(genomes, slots=[0, 1], h2=h2, mode=E.MODE_AUTO)
+    assert eng.info("last_fp4") == 1
+    ca = eng.debug_fetch(E.DBG_C, 2)
+    eng.set_option("gram_fp4", 0)
+    b = eng.evaluate(genomes, slots=[0, 1], h2=h2, mode=E.MODE_AUTO)
+    assert eng.info("last_fp4") == 0
+    cb = eng.debug_fetch(E.DBG_C, 2)
+    eng.set_option("gram_fp4", 1)
+    nt = len(g["train"])
+    assert np.array_equal(np.tril(ca)[:, :nt], np.tril(cb)[:, :nt])
+    assert np.array_equal(a, b)
