@@ -378,7 +378,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     if (c->stop_after == TB_ST_GATHER) continue;
 
     sp = span_begin(c, TB_ST_CENTRE);
-    TB_CUDA(c, tb_launch_centre_terms(d_panel, rpad, kstride, c->d_idx, d_off, w0, Wc, centre_slots, d_kb, d_cs, d_csg, d_s, d_SQ, st, fp4 ? 1 : 0));
+    TB_CUDA(c, tb_launch_centre_terms(d_panel, rpad, kstride, c->d_idx, d_off, w0, Wc, centre_slots, d_kb, d_cs, d_csg, d_s, d_SQ, st, fp4 ? (c->n <= 32767 ? 2 : 1) : 0));
     span_end(c, sp);
     count(c, TB_ST_CENTRE, 2);
     if (c->stop_after == TB_ST_CENTRE) continue;

@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(256) gather_fp4_kernel(const uint8_t* __restri
     for (int i = 0; i < 16; ++i) {
       uint32_t lo = 0, hi = 0;
 #pragma unroll
-      for (int t = 0; t < 8; ++t) {
+      for (int t = 0; t < 8; ++t) {                // (bfe/bfi inline PTX was tried here: slower than shift + LOP3)
         lo |= ((wv[t] >> (2 * i)) & 3u) << (4 * t + 1);
         hi |= ((wv[t + 8] >> (2 * i)) & 3u) << (4 * t + 1);
       }
@@ -176,6 +176,11 @@ __global__ void __launch_bounds__(256) gather_fp4_kernel(const uint8_t* __restri
 }
 
 // csg[job][j] = colsum_job[idx[j]] (zero padded to kstride) and SQ[job] = { sum_j csg, sum_j csg^2 }.
+// SPLIT8 (fp4 panel, column sums below 65 536): instead of ints, csg receives the sums as two unsigned bytes per
+// marker, c = lo + 256 hi, grouped per 8 markers (= one 32-bit panel word) as
+//   [lo of markers 0,2,4,6 | lo of 1,3,5,7 | hi of 0,2,4,6 | hi of 1,3,5,7]      (16 bytes)
+// so that centre_rows_fp4_kernel can use dp4a on the even / odd nibbles of the word.
+template <bool SPLIT8>
 __global__ void __launch_bounds__(256) centre_sq_kernel(const int* __restrict__ idx, const long long* __restrict__ off,
                                                         int w0, int n_slots, int kstride,
                                                         const int* const* __restrict__ colsum_of,
@@ -190,7 +195,13 @@ __global__ void __launch_bounds__(256) centre_sq_kernel(const int* __restrict__ 
   for (int j = threadIdx.x; j < kstride; j += blockDim.x) {
     int c = 0;
     if (j < k) c = cs[idx[o0 + j]];
-    out[j] = c;
+    if (SPLIT8) {
+      unsigned char* o8 = reinterpret_cast<unsigned char*>(out) + 16 * (j >> 3) + ((j & 1) << 2) + ((j & 7) >> 1);
+      o8[0] = (unsigned char)(c & 255);
+      o8[8] = (unsigned char)(c >> 8);
+    } else {
+      out[j] = c;
+    }
     S += c;
     Q += (long long)c * c;
   }
@@ -291,6 +302,46 @@ __global__ void __launch_bounds__(256) centre_rows_fp4_kernel(const int8_t* __re
   }
 }
 
+// The same with dp4a: the column sums arrive as split bytes (centre_sq_kernel<true>), the even / odd nibbles of a panel
+// word become two words of dosage bytes with one shift + mask each, and 8 markers cost 4 dp4a instead of 24 ALU ops.
+__global__ void __launch_bounds__(256) centre_rows_fp4_dp4a_kernel(const int8_t* __restrict__ panel, int rpad, int kstride,
+                                                                   const int* __restrict__ kblocks, int n_slots,
+                                                                   const int* __restrict__ csg, long long* __restrict__ s) {
+  const int job = blockIdx.y;
+  const int w = job / n_slots;
+  const int a0 = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 4, lane = threadIdx.x & 31;
+  if (a0 >= rpad) return;
+  const int kstride_b = kstride / 2;
+  const int n16 = kblocks[w] * TB_GRAM_BK / 16;
+  const uint4* row = reinterpret_cast<const uint4*>(panel + ((size_t)w * rpad + a0) * kstride_b);
+  const size_t rs = kstride_b / 16;
+  const uint4* cg = reinterpret_cast<const uint4*>(csg + (size_t)job * kstride);      // 16 bytes per 8 markers
+  unsigned int lo[4] = {0, 0, 0, 0}, hi[4] = {0, 0, 0, 0};
+  for (int j = lane; j < n16; j += 32) {
+    const uint4 v0 = row[j], v1 = row[rs + j], v2 = row[2 * rs + j], v3 = row[3 * rs + j];
+    const uint32_t a[4][4] = {{v0.x, v0.y, v0.z, v0.w}, {v1.x, v1.y, v1.z, v1.w}, {v2.x, v2.y, v2.z, v2.w},
+                              {v3.x, v3.y, v3.z, v3.w}};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint4 g = cg[4 * j + q];
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        const unsigned int ev = (a[r][q] >> 1) & 0x03030303u, od = (a[r][q] >> 5) & 0x03030303u;
+        lo[r] = __dp4a(ev, g.x, lo[r]);
+        lo[r] = __dp4a(od, g.y, lo[r]);
+        hi[r] = __dp4a(ev, g.z, hi[r]);
+        hi[r] = __dp4a(od, g.w, hi[r]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    long long v = (long long)lo[r] + 256LL * (long long)hi[r];
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) s[(size_t)job * rpad + a0 + r] = v;
+  }
+}
+
 }  // namespace
 
 cudaError_t tb_gather_init() {
@@ -321,11 +372,17 @@ cudaError_t tb_launch_centre_terms(const int8_t* d_panel, int rpad, int kstride,
                                    const long long* d_off, int w0, int W, int n_slots, const int* d_kblocks,
                                    const int* const* d_colsum_of, int* d_csg, long long* d_s, long long* d_SQ,
                                    cudaStream_t st, int fp4) {
-  centre_sq_kernel<<<W * n_slots, 256, 0, st>>>(d_idx, d_off, w0, n_slots, kstride, d_colsum_of, d_csg, d_SQ);
+  // fp4 == 2: column sums fit 16 bits (at most 32 767 animals behind the frequencies) -> split bytes + dp4a
+  if (fp4 == 2)
+    centre_sq_kernel<true><<<W * n_slots, 256, 0, st>>>(d_idx, d_off, w0, n_slots, kstride, d_colsum_of, d_csg, d_SQ);
+  else
+    centre_sq_kernel<false><<<W * n_slots, 256, 0, st>>>(d_idx, d_off, w0, n_slots, kstride, d_colsum_of, d_csg, d_SQ);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return e;
   dim3 grid((rpad + 31) / 32, W * n_slots);
-  if (fp4)
+  if (fp4 == 2)
+    centre_rows_fp4_dp4a_kernel<<<grid, 256, 0, st>>>(d_panel, rpad, kstride, d_kblocks, n_slots, d_csg, d_s);
+  else if (fp4)
     centre_rows_fp4_kernel<<<grid, 256, 0, st>>>(d_panel, rpad, kstride, d_kblocks, n_slots, d_csg, d_s);
   else
     centre_rows_kernel<<<grid, 256, 0, st>>>(d_panel, rpad, kstride, d_kblocks, n_slots, d_csg, d_s);

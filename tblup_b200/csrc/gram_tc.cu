@@ -38,15 +38,16 @@ constexpr int ACC_STRIDE4 = 240;
 constexpr int SF_COL = 480;
 constexpr int EPI_WARPS = 8;                     // two per TMEM lane quarter, each owning half of the tile's columns
 constexpr int NUM_THREADS = 64 + 32 * EPI_WARPS;
-constexpr int COLTERM_BYTES = 2 * BN * 8;         // fused scaling: two buffers of per-column integer terms
+constexpr int COLTERM_BYTES = 2 * BN * 8;         // fused scaling: two buffers of per-column terms (fp32; sized generously)
 constexpr int STAGING_BYTES = EPI_WARPS * 2048;   // per-warp transposition buffers of the coalescing epilogue
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*alignment slack*/ + 256 /*barriers*/ + COLTERM_BYTES +
                            STAGING_BYTES;
 
-// Fused scaling (mixed-precision path, one contiguous row set): besides the raw int32 cross-products the epilogue
-// writes the fp32 matrix the tensor-core Cholesky factors, A = G_tt + lambda I, straight from the accumulator:
-//   A_ab = (float)(N^2 C_ab - N s_a + (Q - N s_b)) * 2/den  (+ lambda on the diagonal),  identity padding,
-// the arithmetic of scale32_kernel (solve_mixed.cu) without re-reading C from HBM.
+// Fused scaling (mixed-precision path, one contiguous row set): besides the raw cross-products the epilogue writes
+// the fp32 matrix the tensor-core Cholesky factors, A = G_tt + lambda I, straight from the accumulator:
+//   A_ab = (2 N^2/den) C_ab - (2 N/den) s_a + (2/den)(Q - N s_b)  (+ lambda on the diagonal),  identity padding,
+// i.e. what scale32_kernel (solve_mixed.cu) computes, without re-reading C from HBM (coefficients from the exact
+// integers in fp64, evaluation in fp32: this matrix only feeds the 10-bit preconditioner).
 struct GramFuse {
   const TbScaleJob* jobs;   // [W] (one row set): s, SQ, N, n_t, ntp, lambda
   float* L32;               // [W][ntp_all][ntp_all]
@@ -211,8 +212,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       // ---- fused scaling: per-tile terms, prepared while the tile's MMAs run
       bool a_tile = false;
       int f_nt = 0, f_ntp = 0;
-      double f_NN = 0.0, f_rowterm = 0.0;
-      float f_inv = 0.f, f_lam = 0.f;
+      float f_scale = 0.f, f_rowterm = 0.f, f_lam = 0.f;
       uint32_t ct = 0;
       if (FUSE) {
         const TbScaleJob& jb = fz.jobs[w];
@@ -220,18 +220,21 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         f_nt = jb.n_t;
         a_tile = ti * BM < f_ntp && tj * BN < f_ntp;      // uniform over the four epilogue warps
         if (a_tile) {
+          // G_ab + [a = b] lambda = (2 N^2 / den) C_ab - (2 N / den) s_a + (2 / den) (Q - N s_b): the three
+          // coefficients are formed in fp64 from the exact integers and rounded once, so the fp32 evaluation below only
+          // combines O(1) quantities (absolute error ~1e-7 of the diagonal; the factorisation rounds to 10 bits, and
+          // the refinement in solve_mixed.cu works from the exact integers, not from this matrix)
           const long long N = jb.N, S = jb.SQ[0], Q = jb.SQ[1];
-          // every integer below stays under 2^53 (N <= 46 340, C <= 4 k), so the fp64 arithmetic is exact
-          f_NN = (double)(N * N);
-          f_inv = (float)(2.0 / (double)(2 * N * S - Q));
+          const double inv_d = 2.0 / (double)(2 * N * S - Q);
+          f_scale = (float)(inv_d * (double)(N * N));
           f_lam = (float)jb.lambda;
-          const uint32_t cw = colterm + fbuf * BN_I8 * 8;
+          const uint32_t cw = colterm + fbuf * BN_I8 * 4;
           for (int e = threadIdx.x - 64; e < BN; e += 32 * EPI_WARPS) {
             const int b = tj * BN + e;
-            const double term = b < f_nt ? (double)(Q - N * jb.s[b]) : 0.0;
-            asm volatile("st.shared.f64 [%0], %1;" ::"r"(cw + e * 8), "d"(term) : "memory");
+            const float term = b < f_nt ? (float)(inv_d * (double)(Q - N * jb.s[b])) : 0.f;
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(cw + e * 4), "f"(term) : "memory");
           }
-          f_rowterm = row < f_nt ? (double)(-N * jb.s[row]) : 0.0;
+          f_rowterm = row < f_nt ? (float)(inv_d * (double)(-N * jb.s[row])) : 0.f;
           ct = cw;
           fbuf ^= 1;
           // the buffer written two A-tiles ago is free again: every warp passed this barrier once since
@@ -253,9 +256,15 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_STRIDE + c * 32, v);
         tmem_ld_wait();
-        if (FP4) {                                     // fp32 accumulators holding exact integers
+        float vf[32];                                  // the cross-products as floats (exact: integers below 2^24)
 #pragma unroll
-          for (int e = 0; e < 32; ++e) v[e] = (uint32_t)__float2int_rn(__uint_as_float(v[e]));
+        for (int e = 0; e < 32; ++e) vf[e] = FP4 ? __uint_as_float(v[e]) : (FUSE ? (float)(int)v[e] : 0.f);
+        if (FP4) {
+          // fp32 accumulators -> integers: adding 2^23 leaves the integer in the low mantissa bits (values < 2^23;
+          // the int16 layout only needs 15 of them); the int32 layout goes through the converter
+#pragma unroll
+          for (int e = 0; e < 32; ++e)
+            v[e] = C16 ? (__float_as_uint(vf[e] + 8388608.f) & 0xffffu) : (uint32_t)__float2int_rn(vf[e]);
         }
         if (C16) {
           uint32_t pk[16];
@@ -284,19 +293,17 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         }
         if (FUSE && a_tile && col0 < f_ntp) {
           uint32_t o[32];
-          double cterm[32];
+          float cterm[32];
 #pragma unroll
-          for (int e = 0; e < 32; e += 2)
-            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];"
-                         : "=d"(cterm[e]), "=d"(cterm[e + 1])
-                         : "r"(ct + (c * 32 + e) * 8));
+          for (int e = 0; e < 32; e += 4)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(cterm[e]), "=f"(cterm[e + 1]), "=f"(cterm[e + 2]), "=f"(cterm[e + 3])
+                         : "r"(ct + (c * 32 + e) * 4));
 #pragma unroll
           for (int e = 0; e < 32; ++e) {
             const int b = col0 + e;
-            // exact integer numerator N^2 C - N s_a + (Q - N s_b) held in fp64, ONE rounding to fp32, one fp32
-            // multiply.  Columns b >= n_t only occur above the diagonal of a training row (never read).
-            const double num = fma((double)(int)v[e], f_NN, f_rowterm + cterm[e]);
-            float g = (float)num * f_inv;
+            // columns b >= n_t only occur above the diagonal of a training row (never read)
+            float g = fmaf(vf[e], f_scale, f_rowterm + cterm[e]);
             if (b == row) g += f_lam;
             if (row >= f_nt) g = b == row ? 1.f : 0.f;      // identity padding rows
             o[e] = __float_as_uint(g);

@@ -164,7 +164,8 @@ cudaError_t tb_launch_centre_terms(const int8_t* d_panel, int rpad, int kstride,
                                    const long long* d_off, int w0, int W, int n_slots, const int* d_kblocks,
                                    const int* const* d_colsum_of, /* [W*n_slots] device ptrs */
                                    int* d_csg /* [W*n_slots][kstride] scratch */, long long* d_s, long long* d_SQ,
-                                   cudaStream_t st, int fp4 = 0 /* panel rows hold nibbles; kstride counts markers */);
+                                   cudaStream_t st,
+                                   int fp4 = 0 /* 1: panel rows hold nibbles, kstride counts markers; 2: also split-byte sums + dp4a */);
 
 // gram_tc.cu / gram_simt.cu
 cudaError_t tb_gram_tc_init();
