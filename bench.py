@@ -358,6 +358,7 @@ def main():
                     else "fallback 1400 TFLOP/s sustained (B200_PROFILING.md)")
         c16 = bool(eng.info("last_c16"))
         fused = bool(eng.info("last_fused_scale"))
+        fp4 = bool(eng.info("last_fp4"))
         if precision == "mixed":
             upd_flops = chol_update_flops(ntp, 256) * n_mats
             upd_kernel = ("tf32_gemm_kernel<F16> (outer left-looking Cholesky update on the fp16 copy of the factor, "
@@ -410,16 +411,20 @@ def main():
                     "launches": int(solve_launches), "avg_launch_ms": solve_ms / max(1, solve_launches),
                     "share_of_step": solve_ms / ms_instrumented}
         gram_tops = gram_ops / (gram_ms * 1e-3) / 1e12 if gram_ms > 0 else None
-        gram_traffic = ncu.get("gram_fused_c16") if (fused and c16) else None
+        gram_traffic = ncu.get("gram_fp4_fused_c16" if fp4 else "gram_fused_c16") if (fused and c16) else None
+        gram_peak = (4 if fp4 else 2) * bf16
         rl_gram = {"bound": "tensor",
-                   "kernel": "gram_tc_kernel (tcgen05 kind::i8, M128 x N256 x K32, s32 in TMEM%s)"
+                   "kernel": ("gram_tc_kernel (tcgen05 kind::mxf4 on E2M1 dosages, block scales 2^0, M128 x N224 x K64, "
+                              "fp32 in TMEM holding exact integers%s)" if fp4 else
+                              "gram_tc_kernel (tcgen05 kind::i8, M128 x N256 x K32, s32 in TMEM%s)")
                              % ("; epilogue also writes the scaled fp32 matrix" if fused else ""),
-                   "achieved": gram_tops, "peak": 2 * bf16, "unit": "TOP/s",
-                   "frac": gram_tops / (2 * bf16) if gram_tops else None,
+                   "achieved": gram_tops, "peak": gram_peak, "unit": "TOP/s",
+                   "frac": gram_tops / gram_peak if gram_tops else None,
                    "traffic": gram_traffic["bytes_per_unit"] * P if gram_traffic else None,
                    "traffic_source": gram_traffic["source"] if gram_traffic else None,
                    "algorithmic_ops_per_launch": gram_ops / max(1, gram_launches),
-                   "peak_source": "2 x " + bf16_src + " (int8 dense = 2 x bf16; nominal 4 500 TOP/s)",
+                   "peak_source": ("4 x " + bf16_src + " (fp4 dense = 4 x bf16; nominal 9 000 TOP/s)") if fp4 else
+                                  ("2 x " + bf16_src + " (int8 dense = 2 x bf16; nominal 4 500 TOP/s)"),
                    "launches": int(gram_launches), "avg_launch_ms": gram_ms / max(1, gram_launches),
                    "share_of_step": gram_ms / ms_instrumented}
         ranked = sorted([("gram", rl_gram, gram_ms), ("solve", rl_solve, solve_ms), ("cholesky_update", rl_update, upd_ms)],
@@ -429,12 +434,13 @@ def main():
             "metric": METRIC, "value": evals / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
-            "dtype": ("s8 Gram (s32) + tf32/f16 Cholesky preconditioner + f64 refinement/solve" if precision == "mixed"
-                      else "s8 Gram (s32 accumulate) + f64 Cholesky/solve"), "data": "synthetic",
+            "dtype": ("%s Gram (exact integers) + tf32/f16 Cholesky preconditioner + f64 refinement/solve"
+                      % ("e2m1" if fp4 else "s8") if precision == "mixed"
+                      else "%s Gram (exact integers) + f64 Cholesky/solve" % ("e2m1" if fp4 else "s8")), "data": "synthetic",
             "config": {"workload": args.workload, "animals": n, "markers": m, "k": k, "pop_per_gpu": P, "folds": folds,
                        "h2": H2, "n_train": int(n_t), "n_valid": int(n_v), "individuals_per_wave": wave, "precision": precision,
                        "genotype_storage": args.storage, "cross_product_storage": "int16" if c16 else "int32",
-                       "scaling_fused_into_gram": fused, "genotype_bytes_resident": eng.resident_genotype_bytes(),
+                       "scaling_fused_into_gram": fused, "gram_operands": "e2m1 (fp4)" if fp4 else "int8", "genotype_bytes_resident": eng.resident_genotype_bytes(),
                        "l2": "inputs larger than L2 (each step streams >20 GB of per-genome panels and matrices)",
                        "parallelism": "replicated genotypes, population sharded, NCCL all-gather of fitness"},
             "e2e": {"value": evals / (ms_e2e * 1e-3), "unit": UNIT,

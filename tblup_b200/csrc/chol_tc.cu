@@ -314,7 +314,6 @@ __global__ void __launch_bounds__(256) chol_diag32_kernel(float* __restrict__ L3
   __shared__ float Ls[NB][NB + 1];
   __shared__ float Xs[NB][NB + 1];
   __shared__ float colbuf[2][NB];
-  __shared__ float part[4][NB];
   __shared__ int bad;
   const int job = blockIdx.x;
   float* D = L32 + ((size_t)job * ntp + (size_t)jb * NB) * ntp + jb * NB;
@@ -354,21 +353,20 @@ __global__ void __launch_bounds__(256) chol_diag32_kernel(float* __restrict__ L3
   }
   __syncthreads();
   {
-    const int c = tid & 63, h = tid >> 6;
-    for (int rr = 0; rr < NB; ++rr) {
+    // X = L^-1 by forward substitution, one column per 4 lanes (8 columns per warp): the partial sums of a column
+    // meet by shuffle and its history in Xs is private to the warp, so the 64 row steps need no block-wide barrier
+    const int warp = tid >> 5, lane = tid & 31;
+    const int c = warp * 8 + (lane >> 2), h = lane & 3;
+    for (int rr = warp * 8; rr < NB; ++rr) {
       float sacc = 0.f;
-      if (c <= rr) {
-        for (int pp = c + h; pp < rr; pp += 4) sacc = fmaf(Ls[rr][pp], Xs[pp][c], sacc);
-      }
-      part[h][c] = sacc;
-      __syncthreads();
-      if (h == 0 && c <= rr) {
-        const float tot = (part[0][c] + part[1][c]) + (part[2][c] + part[3][c]);
-        Xs[rr][c] = ((c == rr ? 1.f : 0.f) - tot) / Ls[rr][rr];
-      }
-      __syncthreads();
+      for (int pp = c + h; pp < rr; pp += 4) sacc = fmaf(Ls[rr][pp], Xs[pp][c], sacc);
+      sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
+      sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
+      if (h == 0 && rr >= c) Xs[rr][c] = ((c == rr ? 1.f : 0.f) - sacc) / Ls[rr][rr];
+      __syncwarp();
     }
   }
+  __syncthreads();
   float* Li = Linv32 + ((size_t)job * ntp + (size_t)jb * NB) * NB;
   for (int e = tid; e < NB * NB; e += 256) {
     const int rr = e >> 6, c = e & 63;
