@@ -39,6 +39,7 @@ NCU_TRAFFIC = {
     "solve_c32": {"bytes_per_unit": 164.06e6, "source": "profiles/r01p_solve_raw.csv"},
     "solve_c16": {"bytes_per_unit": 112.05e6, "source": "profiles/r01q_solve_raw.csv (1 000 matrices per launch)"},
     "gram_fused_c16": {"bytes_per_unit": 58.93e6, "source": "profiles/r01q_gram_raw.csv (1 000 genomes per launch)"},
+    "gram_fp4_fused_c16": {"bytes_per_unit": 48.43e6, "source": "profiles/r01r_gram_raw.csv (1 000 genomes per launch)"},
 }
 H2 = 0.4
 METRIC = "gblup_fitness_evals_per_sec"
