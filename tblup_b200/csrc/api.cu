@@ -151,8 +151,6 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
   bool mixed = c->precision == 0 && tb_solve_mixed_fits(max_ntp);
   for (int s = 0; s < n_slots; ++s) mixed = mixed && sv[s].rs->ntp == max_ntp;
   c->last_mixed = mixed ? 1 : 0;
-  bool contig_all = true;
-  for (int s = 0; s < n_slots; ++s) contig_all = contig_all && sv[s].rs->contiguous && sv[s].rs->n_t % 4 == 0;
   if (mixed) {
     per_ind = 0;
     for (int s = 0; s < n_slots; ++s)
@@ -348,6 +346,9 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
         mj.n_v = rs->n_v;
         mj.ntp = rs->ntp;
         mj.rpad = rpad;
+        mj.hole0 = rs->hole0;
+        mj.gap = rs->gap;
+        mj.valid_in_hole = rs->valid_in_hole ? 1 : 0;
         mj.lambda = lambda;
         c->dbg.M[job] = Mj;
         c->dbg.alpha[job] = aj;
@@ -415,7 +416,11 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
       }
       if (c->stop_after == TB_ST_CHOL_UPDATE || c->stop_after == TB_ST_CHOL_PANEL) continue;
       sp = span_begin(c, TB_ST_SOLVE);
-      TB_CUDA(c, tb_launch_solve_mixed(d_msolve, n_jobs, max_ntp, contig_all ? 1 : 0, c16 ? 1 : 0, st));
+      // contiguous kernels: every row set is a prefix of the universe, or (int16 layout) a prefix with one aligned hole
+      bool contig = true;
+      for (int s = 0; s < n_slots; ++s)
+        contig = contig && ((sv[s].rs->contiguous && sv[s].rs->n_t % 4 == 0) || (c16 && sv[s].rs->seg_ok));
+      TB_CUDA(c, tb_launch_solve_mixed(d_msolve, n_jobs, max_ntp, contig ? 1 : 0, c16 ? 1 : 0, st));
       span_end(c, sp);
       count(c, TB_ST_SOLVE, 1);
       continue;
@@ -680,6 +685,21 @@ int tb_set_rowset(tb_ctx* c, int slot, const int32_t* train, int n_t, const int3
   for (int i = 0; i < n_t; ++i) r.has_train[tpos[i] / TB_GRAM_BM] = 1;
   r.contiguous = true;
   for (int i = 0; i < n_t; ++i) r.contiguous = r.contiguous && tpos[i] == i;
+  {
+    int h0 = 0;
+    while (h0 < n_t && tpos[h0] == h0) ++h0;
+    r.hole0 = h0;
+    r.gap = h0 < n_t ? tpos[h0] - h0 : 0;
+    bool ok = h0 == n_t || r.gap > 0;
+    for (int i = h0; i < n_t && ok; ++i) ok = tpos[i] == i + r.gap;
+    r.seg_ok = ok && h0 % 8 == 0 && r.gap % 8 == 0 && n_t % 8 == 0;
+    r.valid_in_hole = r.seg_ok && r.gap > 0 && n_v == r.gap && n_v <= r.ntp;
+    for (int i = 0; i < n_v && r.valid_in_hole; ++i) r.valid_in_hole = vpos[i] == h0 + i;
+    if (!r.seg_ok) {
+      r.hole0 = n_t;
+      r.gap = 0;
+    }
+  }
   std::vector<double> yt(r.ntp, 0.0), ytc(r.ntp, 0.0), yv(n_v);
   double mean = 0.0;
   for (int i = 0; i < n_t; ++i) {

@@ -225,25 +225,36 @@ __device__ void apply_minv(const __half* __restrict__ L, const float* __restrict
 
 // (C alpha)_a for contiguous training animals from int16 cross-products: the lower triangle is streamed once by
 // rows and once by columns with 16-byte loads (eight entries), four loads in flight per thread.
-__device__ void sym_matvec16(const int16_t* __restrict__ C, int rpad, int n_t, const double* alpha, double* work,
-                             double* part2) {
+// The training animals may be "contiguous with one hole": compact index i sits at universe position i for i < h0 and
+// at i + gap beyond (k-fold cross-validation: the fold that is held out is a contiguous run of the training
+// animals, evaluator.py:455-483).  h0 and gap are multiples of 8, so an 8-entry group never straddles the hole;
+// gap = 0 (h0 = n_t) is the plain contiguous case.
+__device__ void sym_matvec16(const int16_t* __restrict__ C, int rpad, int n_t, int h0, int gap, const double* alpha,
+                             double* work, double* part2) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  auto U = [&](int i) { return i + (i >= h0 ? gap : 0); };          // compact index -> universe position
+  const int hg = h0 >> 3, gg = gap >> 3;
   // rows: a warp takes FOUR consecutive rows a .. a+3 (n_t is a multiple of 4) so that every alpha piece read from
   // shared memory serves four 16-byte loads of C (four independent global loads in flight per thread).
   for (int a = 4 * warp; a < n_t; a += 4 * (ST / 32)) {
-    const uint4* row = reinterpret_cast<const uint4*>(C + (size_t)a * rpad);
+    const int ua = U(a);                            // rows a .. a+3 are consecutive in the universe too
+    const uint4* row = reinterpret_cast<const uint4*>(C + (size_t)ua * rpad);
     const size_t rs = rpad / 8;
     const int full = (a + 1) / 8;                   // 8-entry groups at or left of the diagonal of ALL four rows
     double d[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int c = lane; c < full; c += 32) fma4x8s(d, row[c], row[rs + c], row[2 * rs + c], row[3 * rs + c], alpha + 8 * c);
+    for (int c = lane; c < full; c += 32) {
+      const int uc = c + (c >= hg ? gg : 0);
+      fma4x8s(d, row[uc], row[rs + uc], row[2 * rs + uc], row[3 * rs + uc], alpha + 8 * c);
+    }
     // the (at most 11) columns 8 full .. a + 3 that reach the diagonals: one lane per column, guarded per row
     {
       const int b = 8 * full + lane;
       if (lane < 12 && b <= a + 3) {
         const double z = alpha[b];
+        const int ub = U(b);
 #pragma unroll
         for (int rr = 0; rr < 4; ++rr)
-          if (b <= a + rr) d[rr] += (double)C[(size_t)(a + rr) * rpad + b] * z;
+          if (b <= a + rr) d[rr] += (double)C[(size_t)(ua + rr) * rpad + ub] * z;
       }
     }
 #pragma unroll
@@ -274,10 +285,10 @@ __device__ void sym_matvec16(const int16_t* __restrict__ C, int rpad, int n_t, c
       acc[7] += u2d(v.w >> 16) * w;
     };
     if (ca < n_t) {
-      const int16_t* colp = C + ca;
+      const int16_t* colp = C + U(ca);
       int b = ca + 1 + rg;                          // rows ca + 1 + rg, + 8, ...: every row below the diagonal once
       if (b < n_t && b <= ca + 7) {                 // crosses the 8 x 8 diagonal block: guard per column
-        const uint4 v = *reinterpret_cast<const uint4*>(colp + (size_t)b * rpad);
+        const uint4 v = *reinterpret_cast<const uint4*>(colp + (size_t)U(b) * rpad);
         const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
         const double w = alpha[b];
 #pragma unroll
@@ -286,16 +297,16 @@ __device__ void sym_matvec16(const int16_t* __restrict__ C, int rpad, int n_t, c
         b += 8;
       }
       for (; b + 24 < n_t; b += 32) {
-        const uint4 v0 = *reinterpret_cast<const uint4*>(colp + (size_t)b * rpad);
-        const uint4 v1 = *reinterpret_cast<const uint4*>(colp + (size_t)(b + 8) * rpad);
-        const uint4 v2 = *reinterpret_cast<const uint4*>(colp + (size_t)(b + 16) * rpad);
-        const uint4 v3 = *reinterpret_cast<const uint4*>(colp + (size_t)(b + 24) * rpad);
+        const uint4 v0 = *reinterpret_cast<const uint4*>(colp + (size_t)U(b) * rpad);
+        const uint4 v1 = *reinterpret_cast<const uint4*>(colp + (size_t)U(b + 8) * rpad);
+        const uint4 v2 = *reinterpret_cast<const uint4*>(colp + (size_t)U(b + 16) * rpad);
+        const uint4 v3 = *reinterpret_cast<const uint4*>(colp + (size_t)U(b + 24) * rpad);
         add8(v0, alpha[b]);
         add8(v1, alpha[b + 8]);
         add8(v2, alpha[b + 16]);
         add8(v3, alpha[b + 24]);
       }
-      for (; b < n_t; b += 8) add8(*reinterpret_cast<const uint4*>(colp + (size_t)b * rpad), alpha[b]);
+      for (; b < n_t; b += 8) add8(*reinterpret_cast<const uint4*>(colp + (size_t)U(b) * rpad), alpha[b]);
     }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
@@ -314,14 +325,83 @@ __device__ void sym_matvec16(const int16_t* __restrict__ C, int rpad, int n_t, c
   }
 }
 
+// Cross-products of the held-out animals (universe positions h0 .. h0 + gap - 1, the hole of the training set) with the
+// solution: out[v] = sum_b C(h0 + v, U(b)) alpha_b.  Training animals before the hole lie in the row of the held-out
+// animal (four rows per warp), those after it in its COLUMN of the lower triangle (the column pass of sym_matvec16
+// restricted to the hole's columns; no diagonal is crossed).
+__device__ void hole_predict16(const int16_t* __restrict__ C, int rpad, int n_t, int h0, int gap, const double* alpha,
+                               double* out, double* part2) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_v = gap;
+  for (int v = 4 * warp; v < n_v; v += 4 * (ST / 32)) {          // gap is a multiple of 8
+    const uint4* row = reinterpret_cast<const uint4*>(C + (size_t)(h0 + v) * rpad);
+    const size_t rs = rpad / 8;
+    double d[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int c = lane; c < (h0 >> 3); c += 32) fma4x8s(d, row[c], row[rs + c], row[2 * rs + c], row[3 * rs + c], alpha + 8 * c);
+#pragma unroll
+    for (int rr = 0; rr < 4; ++rr) {
+      const double t = warp_sum(d[rr]);
+      if (lane == 0) out[v + rr] = t;
+    }
+  }
+  __syncthreads();
+  const int cgl = lane & 7, rsub = lane >> 3, cblk = warp & 7, rsup = warp >> 3;
+  const int rg = rsup * 4 + rsub;
+  for (int v0 = 0; v0 < n_v; v0 += 512) {
+    const int cv = v0 + 64 * cblk + 8 * cgl;
+    double acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.0;
+    auto add8 = [&](const uint4 v, const double w) {
+      acc[0] += u2d(v.x & 0xffffu) * w;
+      acc[1] += u2d(v.x >> 16) * w;
+      acc[2] += u2d(v.y & 0xffffu) * w;
+      acc[3] += u2d(v.y >> 16) * w;
+      acc[4] += u2d(v.z & 0xffffu) * w;
+      acc[5] += u2d(v.z >> 16) * w;
+      acc[6] += u2d(v.w & 0xffffu) * w;
+      acc[7] += u2d(v.w >> 16) * w;
+    };
+    if (cv < n_v) {
+      const int16_t* colp = C + h0 + cv;
+      int b = h0 + rg;                                           // compact rows h0 .. n_t-1 = universe rows + gap
+      for (; b + 24 < n_t; b += 32) {
+        const uint4 x0 = *reinterpret_cast<const uint4*>(colp + (size_t)(b + gap) * rpad);
+        const uint4 x1 = *reinterpret_cast<const uint4*>(colp + (size_t)(b + 8 + gap) * rpad);
+        const uint4 x2 = *reinterpret_cast<const uint4*>(colp + (size_t)(b + 16 + gap) * rpad);
+        const uint4 x3 = *reinterpret_cast<const uint4*>(colp + (size_t)(b + 24 + gap) * rpad);
+        add8(x0, alpha[b]);
+        add8(x1, alpha[b + 8]);
+        add8(x2, alpha[b + 16]);
+        add8(x3, alpha[b + 24]);
+      }
+      for (; b < n_t; b += 8) add8(*reinterpret_cast<const uint4*>(colp + (size_t)(b + gap) * rpad), alpha[b]);
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+    }
+    if (rsub == 0) {
+      double* pr = part2 + rsup * 512 + 64 * cblk + 8 * cgl;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) pr[e] = acc[e];
+    }
+    __syncthreads();
+    const int v = v0 + tid;
+    if (v < n_v) out[v] += part2[tid] + part2[512 + tid];
+    __syncthreads();
+  }
+}
+
 // (C alpha)_a over the training animals into work[a]; CONTIG: training animal b sits at universe position b.
 // CT: element type of the stored cross-products (int32_t, or int16_t in C16 mode).
 template <bool CONTIG, typename CT>
-__device__ void sym_matvec(const CT* __restrict__ C, int rpad, int n_t, const int* tp, const double* alpha,
-                           double* work, double* part2) {
+__device__ void sym_matvec(const CT* __restrict__ C, int rpad, int n_t, int h0, int gap, const int* tp,
+                           const double* alpha, double* work, double* part2) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if constexpr (CONTIG && sizeof(CT) == 2) {
-    sym_matvec16(reinterpret_cast<const int16_t*>(C), rpad, n_t, alpha, work, part2);
+    sym_matvec16(reinterpret_cast<const int16_t*>(C), rpad, n_t, h0, gap, alpha, work, part2);
   } else if constexpr (CONTIG) {
     // rows: (C alpha)_a += sum_{b <= a} C[a][b] alpha_b, 16-byte loads, four in flight
     for (int a = warp; a < n_t; a += ST / 32) {
@@ -494,7 +574,7 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
     sa = block_sum(l0, red);
     ssa = block_sum(l1, red);
     if (sweeps == MAX_SWEEPS) break;
-    sym_matvec<CONTIG, CT>(C, rpad, n_t, tp, alpha, work, part2);      // work[a] = (C alpha)_a, a < n_t
+    sym_matvec<CONTIG, CT>(C, rpad, n_t, jb.hole0, jb.gap, tp, alpha, work, part2);      // work[a] = (C alpha)_a, a < n_t
     for (int a = tid; a < ntp; a += ST) {
       double rr = 0.0;
       if (a < n_t) {
@@ -542,13 +622,20 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
   // ---- predictions on the validation animals
   if constexpr (CONTIG && C16) {
     // four validation rows per warp share every alpha piece (see sym_matvec16); rows at/after n_t are plain rows of C
-      for (int v0i = 4 * warp; v0i < n_v; v0i += 4 * (ST / 32)) {
+      if (jb.gap > 0 && jb.valid_in_hole) {
+      // k-fold cross-validation: the validation animals are exactly the hole of the training set
+      __syncthreads();
+      hole_predict16(reinterpret_cast<const int16_t*>(C), rpad, n_t, jb.hole0, jb.gap, alpha, work, part2);
+      for (int v = tid; v < n_v; v += ST)
+        jb.pred[v] = coef * (Nd * Nd * work[v] - Nd * (double)jb.s[jb.hole0 + v] * sa - Nd * ssa + Qd * sa);
+    } else
+    for (int v0i = 4 * warp; v0i < n_v; v0i += 4 * (ST / 32)) {
       int pv[4];
       bool fast = true;
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) {
         pv[rr] = jb.vpos[min(v0i + rr, n_v - 1)];
-        fast = fast && pv[rr] >= n_t;
+        fast = fast && pv[rr] >= n_t && jb.gap == 0;
       }
       double d[4] = {0.0, 0.0, 0.0, 0.0};
       if (fast) {

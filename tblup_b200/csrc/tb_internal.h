@@ -44,6 +44,11 @@ struct TbRowSet {
   double* d_yv = nullptr;       // [n_v]
   std::vector<unsigned char> has_train;   // per 128-row universe block: contains a training animal
   bool contiguous = false;      // training animal b sits at universe position b
+  // "contiguous with one hole": training animal i sits at i for i < hole0 and at i + gap beyond (hole0, gap multiples
+  // of 8; gap = 0, hole0 = n_t when contiguous); valid_in_hole: the validation animals are exactly the hole, in order
+  bool seg_ok = false;
+  int hole0 = 0, gap = 0;
+  bool valid_in_hole = false;
 };
 
 // resident genotypes as the kernels see them: exactly one of x (int8 dosages, [m][ldn]) and x2 (2-bit packed,
@@ -240,6 +245,7 @@ struct TbSolveMixedJob {
   int* sweeps;             // refinement sweeps used (diagnostics)
   long long N;
   int n_t, n_v, ntp, rpad;
+  int hole0, gap, valid_in_hole;   // see TbRowSet (contiguous kernels only)
   double lambda;
 };
 cudaError_t tb_solve_mixed_init();

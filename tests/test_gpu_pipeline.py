@@ -331,3 +331,39 @@ def test_mixed_factor_across_several_panels():
                 assert abs(fit[job] - ref) < 1e-7, (wide, job, fit[job], ref)
     finally:
         eng.close()
+
+
+def test_cross_validation_folds_with_aligned_holes():
+    """k-fold row sets whose held-out fold is an 8-aligned contiguous run of the training animals take the
+    'contiguous with one hole' kernels (vectorised mat-vec, held-out predictions from row + column parts).
+    Against the oracle, and against the generic position-lookup kernels (int32 layout), for both branches."""
+    import random
+    from tblup_b200 import engine as E
+    n, m = 1100, 3000
+    x, y = O.synth_genotypes(n, m, h2=0.4, seed=31)
+    random.seed(31)
+    np.random.seed(31)
+    tr, va, te = O.ref_splits(n)
+    assert len(tr) == 704
+    folds = O.ref_make_fold_indices(list(tr), 8)              # 8 folds of 88 animals
+    eng, perm = _engine(x, y, tr, va, te, extra_sets=[(f[0], f[1]) for f in folds])
+    try:
+        rng = np.random.default_rng(32)
+        genomes = [rng.choice(m, size=k, replace=False) for k in (90, 1101, 2000)]
+        slots = list(range(1, 9))
+        for mode, omode in ((E.MODE_GBLUP, O.MODE_GBLUP), (E.MODE_SNPBLUP, O.MODE_SNPBLUP)):
+            eng.set_option("narrow_c", 1)
+            got = eng.evaluate(genomes, slots=slots, h2=0.4, mode=mode)
+            assert eng.info("last_c16") == 1
+            eng.set_option("narrow_c", 0)
+            generic = eng.evaluate(genomes, slots=slots, h2=0.4, mode=mode)
+            eng.set_option("narrow_c", 1)
+            want = np.array([[O.exact_fitness(g, f[0], f[1], x, y, 0.4, omode) for f in folds] for g in genomes])
+            assert np.abs(got - want).max() < 1e-7
+            assert np.abs(got - generic).max() < 1e-9
+        # base split and folds in one call (mixed contiguous / hole row sets)
+        both = eng.evaluate(genomes, slots=[0, 3], h2=0.4, mode=E.MODE_GBLUP)
+        assert abs(both[1, 0] - O.exact_fitness(genomes[1], tr, va, x, y, 0.4, O.MODE_GBLUP)) < 1e-7
+        assert abs(both[1, 1] - O.exact_fitness(genomes[1], folds[2][0], folds[2][1], x, y, 0.4, O.MODE_GBLUP)) < 1e-7
+    finally:
+        eng.close()
