@@ -148,7 +148,15 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     per_ind += (sv[s].m_elems + sv[s].linv_elems + rs->ntp + rs->n_v) * sizeof(double) + 1024;
   }
   has_train.resize(rpad / TB_GRAM_BM, 0);
-  bool mixed = c->precision == 0 && tb_solve_mixed_fits(max_ntp);
+  const int P = c->P;
+  int kmax = 0;
+  for (int i = 0; i < P; ++i) {
+    const int k = (int)(c->h_off[i + 1] - c->h_off[i]);
+    if (k <= 0) return fail(c, "tb_eval_staged: empty genome at position " + std::to_string(i));
+    kmax = std::max(kmax, k);
+  }
+  // the mixed path turns cross-products (<= 4 k) into floats through the 2^23 mantissa trick: 4 kmax < 2^23
+  bool mixed = c->precision == 0 && tb_solve_mixed_fits(max_ntp) && 4LL * kmax < (1LL << 23);
   for (int s = 0; s < n_slots; ++s) mixed = mixed && sv[s].rs->ntp == max_ntp;
   c->last_mixed = mixed ? 1 : 0;
   if (mixed) {
@@ -161,13 +169,6 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
   // one contiguous row set: the Gram epilogue writes the fp32 matrix itself (no separate scaling pass over C)
   const bool fuse_scale = mixed && n_slots == 1 && sv[0].rs->contiguous && c->n <= 46340 && c->fuse_scale;
   c->last_fused = fuse_scale ? 1 : 0;
-  const int P = c->P;
-  int kmax = 0;
-  for (int i = 0; i < P; ++i) {
-    const int k = (int)(c->h_off[i + 1] - c->h_off[i]);
-    if (k <= 0) return fail(c, "tb_eval_staged: empty genome at position " + std::to_string(i));
-    kmax = std::max(kmax, k);
-  }
   // E2M1 Gram: needs the packed resident matrix (its gather is written for it); every sum is an integer <= 4 kmax,
   // exact in the fp32 accumulators below 2^24
   const bool fp4 = c->gram_fp4 && c->d_x2 != nullptr && 4LL * kmax < (1LL << 24);

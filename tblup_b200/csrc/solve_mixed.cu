@@ -735,8 +735,7 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
 // fp32 copy of A = G_tt + lambda I (lower triangle, identity padding) for the tensor-core factorisation.
 // Block = 64 rows x 128 columns; a thread owns 4 consecutive columns (one 16-byte load of C, one 16-byte store) of
 // 8 rows, so the per-column setup (positions, column terms) is amortised over 8 rows and the 8 row loads are
-// independent.  fp32 output: exact int64 numerator, one fp64 multiply by 2/den (the exact operator lives in
-// solve_mixed_kernel, so no fp64 division is needed here).
+// independent.  (The exact operator lives in solve_mixed_kernel; this matrix only feeds the 10-bit preconditioner.)
 constexpr int S32_ROWS = 64;
 template <bool C16>
 __global__ void __launch_bounds__(256) scale32_kernel(const TbScaleJob* __restrict__ jobs, float* __restrict__ L32,
@@ -747,24 +746,26 @@ __global__ void __launch_bounds__(256) scale32_kernel(const TbScaleJob* __restri
   if (r0 >= ntp || c0 >= ntp || c0 > r0 + S32_ROWS - 1) return;
   const int c = c0 + (threadIdx.x & 31) * 4;
   if (c >= ntp) return;
+  // same evaluation as the fused Gram epilogue (gram_tc.cu): coefficients from the exact integers in fp64, rounded
+  // once; the fp32 combination below only handles O(1) quantities and no 64-bit integer -> float conversion
   const long long N = jb.N, S = jb.SQ[0], Q = jb.SQ[1];
-  const long long NN = N * N;
-  const float inv_den2 = (float)(2.0 / (double)(2 * N * S - Q)), lam = (float)jb.lambda;
+  const double inv_d = 2.0 / (double)(2 * N * S - Q);
+  const float scale = (float)(inv_d * (double)(N * N)), lam = (float)jb.lambda;
   int pc[4];
-  long long sc[4];
+  float sc[4];
   bool creal[4];
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     creal[i] = c + i < n_t;
     pc[i] = creal[i] ? jb.tpos[c + i] : 0;
-    sc[i] = creal[i] ? jb.s[pc[i]] : 0;
+    sc[i] = creal[i] ? (float)(inv_d * (double)(Q - N * jb.s[pc[i]])) : 0.f;
   }
   const bool run = creal[3] && pc[1] == pc[0] + 1 && pc[2] == pc[0] + 2 && pc[3] == pc[0] + 3 && (pc[0] & 3) == 0;
   float* out_base = L32 + (size_t)blockIdx.z * ntp_all * ntp_all;
   const int rbase = r0 + (threadIdx.x >> 5);
   // phase 1: positions, row terms and the integer cross-products of the 8 rows (independent loads)
   int pr[8];
-  long long sr[8];
+  float sr[8];
   int4 cv[8];
 #pragma unroll
   for (int h = 0; h < 8; ++h) {
@@ -774,10 +775,10 @@ __global__ void __launch_bounds__(256) scale32_kernel(const TbScaleJob* __restri
 #pragma unroll
   for (int h = 0; h < 8; ++h) {
     const int r = rbase + 8 * h;
-    sr[h] = 0;
+    sr[h] = 0.f;
     cv[h] = make_int4(0, 0, 0, 0);
     if (pr[h] >= 0 && c <= r) {
-      sr[h] = jb.s[pr[h]];
+      sr[h] = (float)(inv_d * (double)(-N * jb.s[pr[h]]));
       if (run && pc[3] < pr[h]) {
         if (C16) {
           const uint2 u = *reinterpret_cast<const uint2*>(reinterpret_cast<const int16_t*>(jb.C) + (size_t)pr[h] * rpad + pc[0]);
@@ -813,9 +814,9 @@ __global__ void __launch_bounds__(256) scale32_kernel(const TbScaleJob* __restri
       for (int i = 0; i < 4; ++i) {
         float g = 0.f;
         if (creal[i]) {
-          // exact int64 numerator (after the cancellation), ONE rounding to fp32, one fp32 multiply
-          const long long num = NN * (long long)cvv[i] - N * (sr[h] + sc[i]) + Q;
-          g = (float)num * inv_den2;
+          // cross-products are below 2^23: 0x4b000000 | c is the float 2^23 + c
+          const float cf = __uint_as_float(0x4b000000u | (unsigned)cvv[i]) - 8388608.f;
+          g = fmaf(cf, scale, sr[h] + sc[i]);
           if (r == c + i) g += lam;
         }
         out[i] = g;
