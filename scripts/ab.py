@@ -43,5 +43,6 @@ for i in range(5):
     eng.evaluate_staged([0], out_device_ptr=fit.data_ptr())
     for k, v in eng.stage_times().items():
         agg.setdefault(k, []).append(v[0])
+print("per-step ms:", [round(float(t), 1) for t in ts], "fallbacks", eng.info("last_fallbacks"))
 print("stage medians (ms):", {k: round(float(np.median(v)), 2) for k, v in agg.items()},
       "sum %.1f" % sum(float(np.median(v)) for v in agg.values()))

@@ -118,12 +118,15 @@ void mark_cb(void* p, int which, int end) {
   }
 }
 
+int fp64_fallback(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_rule, double* d_fit);
+
 struct SlotView {
   const TbRowSet* rs;
   size_t m_elems, linv_elems;
 };
 
-int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_rule, double* d_fit) {
+int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_rule, double* d_fit,
+              bool allow_fallback = true) {
   if (c->P <= 0) return fail(c, "tb_eval_staged: no genomes staged");
   if (n_slots <= 0 || n_slots > TB_MAX_SLOTS) return fail(c, "tb_eval_staged: bad n_slots");
   if (!(h2 > 0.0) || !(h2 <= 1.0)) return fail(c, "tb_eval_staged: heritability must be in (0, 1]");
@@ -159,7 +162,18 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
   bool mixed = c->precision == 0 && tb_solve_mixed_fits(max_ntp) && 4LL * kmax < (1LL << 23);
   for (int s = 0; s < n_slots; ++s) mixed = mixed && sv[s].rs->ntp == max_ntp;
   c->last_mixed = mixed ? 1 : 0;
+  if (allow_fallback) c->last_fallbacks = 0;
   if (mixed) {
+    const size_t need = (size_t)P * n_slots;
+    if (need > c->fail_cap) {
+      TB_CUDA(c, cudaStreamSynchronize(c->stream));
+      cudaFree(c->d_fail);
+      c->d_fail = nullptr;
+      c->fail_cap = 0;
+      TB_CUDA(c, cudaMalloc(&c->d_fail, need * sizeof(int)));
+      c->fail_cap = need;
+    }
+    TB_CUDA(c, cudaMemsetAsync(c->d_fail, 0, need * sizeof(int), c->stream));
     per_ind = 0;
     for (int s = 0; s < n_slots; ++s)
       per_ind += (size_t)max_ntp * max_ntp * (sizeof(float) + 2) + (size_t)max_ntp * TB_NB * sizeof(float) +
@@ -342,6 +356,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
         mj.pred = pj;
         mj.fitness = oj.fitness;
         mj.sweeps = d_sweeps + job;
+        mj.fail = mixed ? c->d_fail + (size_t)(w0 + w) * n_slots + s : nullptr;
         mj.N = sj.N;
         mj.n_t = rs->n_t;
         mj.n_v = rs->n_v;
@@ -418,10 +433,12 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
       if (c->stop_after == TB_ST_CHOL_UPDATE || c->stop_after == TB_ST_CHOL_PANEL) continue;
       sp = span_begin(c, TB_ST_SOLVE);
       // contiguous kernels: every row set is a prefix of the universe, or (int16 layout) a prefix with one aligned hole
-      bool contig = true;
-      for (int s = 0; s < n_slots; ++s)
+      bool contig = true, hole = false;
+      for (int s = 0; s < n_slots; ++s) {
         contig = contig && ((sv[s].rs->contiguous && sv[s].rs->n_t % 4 == 0) || (c16 && sv[s].rs->seg_ok));
-      TB_CUDA(c, tb_launch_solve_mixed(d_msolve, n_jobs, max_ntp, contig ? 1 : 0, c16 ? 1 : 0, st));
+        hole = hole || sv[s].rs->gap > 0;
+      }
+      TB_CUDA(c, tb_launch_solve_mixed(d_msolve, n_jobs, max_ntp, contig ? 1 : 0, c16 ? 1 : 0, hole ? 1 : 0, st));
       span_end(c, sp);
       count(c, TB_ST_SOLVE, 1);
       continue;
@@ -457,6 +474,79 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     span_end(c, sp);
     count(c, TB_ST_SOLVE, 1);
   }
+  if (mixed && allow_fallback && c->stop_after < 0) return fp64_fallback(c, slots, n_slots, h2, mode_rule, d_fit);
+  return 0;
+}
+
+// Jobs whose mixed-precision solve gave up (pivot breakdown of the low-precision factor or no convergence of the
+// refinement: lambda -> 0, i.e. h2 -> 1, makes A ill-conditioned) are evaluated again with the fp64 Cholesky, which
+// is what the reference's fp64 inverse (tblup/evaluator.py:282) can still handle.  One small D2H of the flags per
+// evaluation; in the normal case nothing else happens.
+int fp64_fallback(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_rule, double* d_fit) {
+  const int P = c->P;
+  std::vector<int> h_fail((size_t)P * n_slots);
+  TB_CUDA(c, cudaMemcpyAsync(h_fail.data(), c->d_fail, h_fail.size() * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  TB_CUDA(c, cudaStreamSynchronize(c->stream));
+  std::vector<int> redo;
+  int n_failed = 0;
+  for (int i = 0; i < P; ++i) {
+    bool any = false;
+    for (int s = 0; s < n_slots; ++s) {
+      any = any || h_fail[(size_t)i * n_slots + s] != 0;
+      n_failed += h_fail[(size_t)i * n_slots + s] != 0;
+    }
+    if (any) redo.push_back(i);
+  }
+  if (redo.empty()) return 0;
+  spans_collect(c);                                  // the recursive evaluation reuses the event pool
+  std::vector<long long> sub_off(redo.size() + 1, 0);
+  for (size_t j = 0; j < redo.size(); ++j) sub_off[j + 1] = sub_off[j] + (c->h_off[redo[j] + 1] - c->h_off[redo[j]]);
+  int* d_sub = nullptr;
+  double* d_subfit = nullptr;
+  TB_CUDA(c, cudaMalloc(&d_sub, (size_t)sub_off.back() * sizeof(int)));
+  if (cudaMalloc(&d_subfit, redo.size() * n_slots * sizeof(double)) != cudaSuccess) {
+    cudaFree(d_sub);
+    return fail(c, "fp64 fallback: out of memory", -2);
+  }
+  for (size_t j = 0; j < redo.size(); ++j)
+    cudaMemcpyAsync(d_sub + sub_off[j], c->d_idx + c->h_off[redo[j]],
+                    (size_t)(sub_off[j + 1] - sub_off[j]) * sizeof(int), cudaMemcpyDeviceToDevice, c->stream);
+  // evaluate the sub-batch as the staged batch, in fp64, then put everything back
+  std::vector<long long> keep_off;
+  keep_off.swap(c->h_off);
+  int* keep_idx = c->d_idx;
+  const size_t keep_cap = c->idx_cap;
+  const int keep_P = c->P, keep_prec = c->precision;
+  const int keep_c16 = c->last_c16, keep_fused = c->last_fused, keep_fp4 = c->last_fp4, keep_wave = c->last_wave;
+  c->h_off = sub_off;
+  c->d_idx = d_sub;
+  c->idx_cap = (size_t)sub_off.back();
+  c->P = (int)redo.size();
+  c->precision = 1;
+  int rc = eval_core(c, slots, n_slots, h2, mode_rule, d_subfit, false);
+  c->precision = keep_prec;
+  c->P = keep_P;
+  c->d_idx = keep_idx;
+  c->idx_cap = keep_cap;
+  c->h_off.swap(keep_off);
+  c->last_mixed = 1;
+  c->last_c16 = keep_c16;
+  c->last_fused = keep_fused;
+  c->last_fp4 = keep_fp4;
+  c->last_wave = keep_wave;
+  if (rc == 0) {
+    for (size_t j = 0; j < redo.size(); ++j)
+      for (int s = 0; s < n_slots; ++s)
+        if (h_fail[(size_t)redo[j] * n_slots + s])
+          cudaMemcpyAsync(d_fit + (size_t)redo[j] * n_slots + s, d_subfit + j * n_slots + s, sizeof(double),
+                          cudaMemcpyDeviceToDevice, c->stream);
+  }
+  cudaError_t se = cudaStreamSynchronize(c->stream);
+  cudaFree(d_sub);
+  cudaFree(d_subfit);
+  if (rc) return rc;
+  if (se != cudaSuccess) return fail(c, std::string("fp64 fallback: ") + cudaGetErrorString(se), -2);
+  c->last_fallbacks = n_failed;
   return 0;
 }
 
@@ -651,6 +741,7 @@ int tb_destroy(tb_ctx* c) {
   cudaFree(c->d_x2);
   cudaFree(c->d_colsum_all);
   cudaFree(c->d_idx);
+  cudaFree(c->d_fail);
   cudaFree(c->ws);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
@@ -955,6 +1046,7 @@ int tb_get_info(const tb_ctx* c, const char* name, long long* value) {
   else if (s == "wide_panel") *value = c->wide_panel;
   else if (s == "de_removed") *value = c->de.n_banned;
   else if (s == "last_fp4") *value = c->last_fp4;
+  else if (s == "last_fallbacks") *value = c->last_fallbacks;
   else if (s == "staged") *value = c->P;
   else return -1;
   return 0;

@@ -19,7 +19,7 @@ namespace {
 
 constexpr int NB = TB_NB;
 constexpr int ST = 512;
-constexpr int MAX_SWEEPS = 6;
+constexpr int MAX_SWEEPS = 5;
 constexpr int MIXED_SMEM_NTP = 4096;  // up to this many (padded) training animals alpha stays in shared memory
 constexpr double REL_TOL = 1e-8;     // stop when the PREDICTED remaining error is below 1e-8 of the solution
                                      // (fitness bar of BASELINE.json: 1e-6 absolute)
@@ -229,10 +229,12 @@ __device__ void apply_minv(const __half* __restrict__ L, const float* __restrict
 // at i + gap beyond (k-fold cross-validation: the fold that is held out is a contiguous run of the training
 // animals, evaluator.py:455-483).  h0 and gap are multiples of 8, so an 8-entry group never straddles the hole;
 // gap = 0 (h0 = n_t) is the plain contiguous case.
+// HOLE = false compiles the index mapping away (plain contiguous row sets pay nothing for it).
+template <bool HOLE>
 __device__ void sym_matvec16(const int16_t* __restrict__ C, int rpad, int n_t, int h0, int gap, const double* alpha,
                              double* work, double* part2) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  auto U = [&](int i) { return i + (i >= h0 ? gap : 0); };          // compact index -> universe position
+  auto U = [&](int i) { return HOLE ? i + (i >= h0 ? gap : 0) : i; };   // compact index -> universe position
   const int hg = h0 >> 3, gg = gap >> 3;
   // rows: a warp takes FOUR consecutive rows a .. a+3 (n_t is a multiple of 4) so that every alpha piece read from
   // shared memory serves four 16-byte loads of C (four independent global loads in flight per thread).
@@ -243,7 +245,7 @@ __device__ void sym_matvec16(const int16_t* __restrict__ C, int rpad, int n_t, i
     const int full = (a + 1) / 8;                   // 8-entry groups at or left of the diagonal of ALL four rows
     double d[4] = {0.0, 0.0, 0.0, 0.0};
     for (int c = lane; c < full; c += 32) {
-      const int uc = c + (c >= hg ? gg : 0);
+      const int uc = HOLE ? c + (c >= hg ? gg : 0) : c;
       fma4x8s(d, row[uc], row[rs + uc], row[2 * rs + uc], row[3 * rs + uc], alpha + 8 * c);
     }
     // the (at most 11) columns 8 full .. a + 3 that reach the diagonals: one lane per column, guarded per row
@@ -396,12 +398,12 @@ __device__ void hole_predict16(const int16_t* __restrict__ C, int rpad, int n_t,
 
 // (C alpha)_a over the training animals into work[a]; CONTIG: training animal b sits at universe position b.
 // CT: element type of the stored cross-products (int32_t, or int16_t in C16 mode).
-template <bool CONTIG, typename CT>
+template <bool CONTIG, bool HOLE, typename CT>
 __device__ void sym_matvec(const CT* __restrict__ C, int rpad, int n_t, int h0, int gap, const int* tp,
                            const double* alpha, double* work, double* part2) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if constexpr (CONTIG && sizeof(CT) == 2) {
-    sym_matvec16(reinterpret_cast<const int16_t*>(C), rpad, n_t, h0, gap, alpha, work, part2);
+    sym_matvec16<HOLE>(reinterpret_cast<const int16_t*>(C), rpad, n_t, h0, gap, alpha, work, part2);
   } else if constexpr (CONTIG) {
     // rows: (C alpha)_a += sum_{b <= a} C[a][b] alpha_b, 16-byte loads, four in flight
     for (int a = warp; a < n_t; a += ST / 32) {
@@ -523,7 +525,7 @@ __device__ void sym_matvec(const CT* __restrict__ C, int rpad, int n_t, int h0, 
   }
 }
 
-template <bool CONTIG, bool BIG, bool C16>
+template <bool CONTIG, bool BIG, bool C16, bool HOLE>
 __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJob* __restrict__ jobs) {
   using CT = typename std::conditional<C16, int16_t, int32_t>::type;
   extern __shared__ double msm[];
@@ -564,6 +566,7 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
   __syncthreads();
 
   int sweeps = 0;
+  bool solved = false;               // refinement reached the tolerance (else the host re-runs the job in fp64)
   double sa = 0.0, ssa = 0.0, prev_dmax = 1e300;
   for (;;) {
     double l0 = 0.0, l1 = 0.0;
@@ -574,7 +577,7 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
     sa = block_sum(l0, red);
     ssa = block_sum(l1, red);
     if (sweeps == MAX_SWEEPS) break;
-    sym_matvec<CONTIG, CT>(C, rpad, n_t, jb.hole0, jb.gap, tp, alpha, work, part2);      // work[a] = (C alpha)_a, a < n_t
+    sym_matvec<CONTIG, HOLE, CT>(C, rpad, n_t, jb.hole0, jb.gap, tp, alpha, work, part2);      // work[a] = (C alpha)_a, a < n_t
     for (int a = tid; a < ntp; a += ST) {
       double rr = 0.0;
       if (a < n_t) {
@@ -602,9 +605,12 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
     // contracts by 1e-2 .. 1e-3 for cond(A) up to a few hundred)
     const double rho = sweeps == 1 ? 0.05 : fmin(1.0, dmax / prev_dmax);
     const bool converged = !(dmax * rho > REL_TOL * amax);
-    const bool stalled = sweeps > 1 && dmax > 0.5 * prev_dmax;   // rounding floor of the residual reached
+    // corrections no longer shrink: either the rounding floor of the residual (then they are tiny) or a factor too
+    // poor to precondition (ill-conditioned matrix: lambda -> 0) -- only the first counts as solved
+    const bool stalled = sweeps > 1 && dmax > 0.5 * prev_dmax;
     prev_dmax = dmax;
     if (converged || stalled) {
+      solved = converged || dmax <= 1e-7 * amax;
       double m0 = 0.0, m1 = 0.0;
       for (int a = tid; a < n_t; a += ST) {
         m0 += alpha[a];
@@ -618,11 +624,12 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
   if (!big)
     for (int a = tid; a < ntp; a += ST) jb.alpha[a] = alpha[a];
   if (tid == 0 && jb.sweeps) *jb.sweeps = sweeps;
+  if (tid == 0 && jb.fail && (!solved || *jb.status != 0)) *jb.fail = 1;
 
   // ---- predictions on the validation animals
   if constexpr (CONTIG && C16) {
     // four validation rows per warp share every alpha piece (see sym_matvec16); rows at/after n_t are plain rows of C
-      if (jb.gap > 0 && jb.valid_in_hole) {
+      if (HOLE && jb.gap > 0 && jb.valid_in_hole) {
       // k-fold cross-validation: the validation animals are exactly the hole of the training set
       __syncthreads();
       hole_predict16(reinterpret_cast<const int16_t*>(C), rpad, n_t, jb.hole0, jb.gap, alpha, work, part2);
@@ -635,7 +642,7 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
 #pragma unroll
       for (int rr = 0; rr < 4; ++rr) {
         pv[rr] = jb.vpos[min(v0i + rr, n_v - 1)];
-        fast = fast && pv[rr] >= n_t && jb.gap == 0;
+        fast = fast && pv[rr] >= n_t && (!HOLE || jb.gap == 0);
       }
       double d[4] = {0.0, 0.0, 0.0, 0.0};
       if (fast) {
@@ -841,14 +848,16 @@ cudaError_t tb_solve_mixed_init() {
   auto set = [&](const void* fn) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, g_solve_mixed_smem_max);
   };
-  set((const void*)solve_mixed_kernel<true, false, false>);
-  set((const void*)solve_mixed_kernel<false, false, false>);
-  set((const void*)solve_mixed_kernel<true, true, false>);
-  set((const void*)solve_mixed_kernel<false, true, false>);
-  set((const void*)solve_mixed_kernel<true, false, true>);
-  set((const void*)solve_mixed_kernel<false, false, true>);
-  set((const void*)solve_mixed_kernel<true, true, true>);
-  set((const void*)solve_mixed_kernel<false, true, true>);
+  set((const void*)solve_mixed_kernel<true, false, false, false>);
+  set((const void*)solve_mixed_kernel<false, false, false, false>);
+  set((const void*)solve_mixed_kernel<true, true, false, false>);
+  set((const void*)solve_mixed_kernel<false, true, false, false>);
+  set((const void*)solve_mixed_kernel<true, false, true, false>);
+  set((const void*)solve_mixed_kernel<false, false, true, false>);
+  set((const void*)solve_mixed_kernel<true, true, true, false>);
+  set((const void*)solve_mixed_kernel<false, true, true, false>);
+  set((const void*)solve_mixed_kernel<true, false, true, true>);
+  set((const void*)solve_mixed_kernel<true, true, true, true>);
   return e;
 }
 
@@ -856,21 +865,27 @@ bool tb_solve_mixed_fits(int ntp) { return solve_mixed_smem_bytes(ntp) <= 220 * 
 
 // contiguous != 0: every job's training animal b sits at universe position b and n_t is a multiple of 4
 // (vectorised symmetric mat-vec); otherwise positions are looked up per element.
-cudaError_t tb_launch_solve_mixed(const TbSolveMixedJob* d_jobs, int n_jobs, int ntp, int contiguous, int c16,
+// hole != 0 (with contiguous and c16): some row set is contiguous with one aligned hole (see TbRowSet).
+cudaError_t tb_launch_solve_mixed(const TbSolveMixedJob* d_jobs, int n_jobs, int ntp, int contiguous, int c16, int hole,
                                   cudaStream_t st) {
   const int smem = solve_mixed_smem_bytes(ntp);
   if (smem > g_solve_mixed_smem_max) return cudaErrorInvalidConfiguration;
   const bool big = ntp > MIXED_SMEM_NTP;
+  if (hole && contiguous && c16) {
+    if (big) solve_mixed_kernel<true, true, true, true><<<n_jobs, ST, smem, st>>>(d_jobs);
+    else solve_mixed_kernel<true, false, true, true><<<n_jobs, ST, smem, st>>>(d_jobs);
+    return cudaGetLastError();
+  }
   const int which = (contiguous ? 4 : 0) | (big ? 2 : 0) | (c16 ? 1 : 0);
   switch (which) {
-    case 0: solve_mixed_kernel<false, false, false><<<n_jobs, ST, smem, st>>>(d_jobs); break;
-    case 1: solve_mixed_kernel<false, false, true><<<n_jobs, ST, smem, st>>>(d_jobs); break;
-    case 2: solve_mixed_kernel<false, true, false><<<n_jobs, ST, smem, st>>>(d_jobs); break;
-    case 3: solve_mixed_kernel<false, true, true><<<n_jobs, ST, smem, st>>>(d_jobs); break;
-    case 4: solve_mixed_kernel<true, false, false><<<n_jobs, ST, smem, st>>>(d_jobs); break;
-    case 5: solve_mixed_kernel<true, false, true><<<n_jobs, ST, smem, st>>>(d_jobs); break;
-    case 6: solve_mixed_kernel<true, true, false><<<n_jobs, ST, smem, st>>>(d_jobs); break;
-    default: solve_mixed_kernel<true, true, true><<<n_jobs, ST, smem, st>>>(d_jobs); break;
+    case 0: solve_mixed_kernel<false, false, false, false><<<n_jobs, ST, smem, st>>>(d_jobs); break;
+    case 1: solve_mixed_kernel<false, false, true, false><<<n_jobs, ST, smem, st>>>(d_jobs); break;
+    case 2: solve_mixed_kernel<false, true, false, false><<<n_jobs, ST, smem, st>>>(d_jobs); break;
+    case 3: solve_mixed_kernel<false, true, true, false><<<n_jobs, ST, smem, st>>>(d_jobs); break;
+    case 4: solve_mixed_kernel<true, false, false, false><<<n_jobs, ST, smem, st>>>(d_jobs); break;
+    case 5: solve_mixed_kernel<true, false, true, false><<<n_jobs, ST, smem, st>>>(d_jobs); break;
+    case 6: solve_mixed_kernel<true, true, false, false><<<n_jobs, ST, smem, st>>>(d_jobs); break;
+    default: solve_mixed_kernel<true, true, true, false><<<n_jobs, ST, smem, st>>>(d_jobs); break;
   }
   return cudaGetLastError();
 }

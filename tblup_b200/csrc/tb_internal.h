@@ -102,6 +102,9 @@ struct TbCtx {
   int last_fp4 = 0;
   int narrow_c = 1;               // 1: int16 cross-products when every genome of the batch has 4 k <= 32 767
   int last_c16 = 0;
+  int* d_fail = nullptr;          // [P * n_slots] per-job "mixed precision gave up" flags of the last evaluation
+  size_t fail_cap = 0;
+  int last_fallbacks = 0;         // jobs the last evaluation re-ran in fp64
   int last_fused = 0;
   int wide_panel = 1;             // 1: 256-wide panel solve through the inverse of the diagonal block (chol_tc.cu)
   int fuse_scale = 1;             // 1: Gram epilogue writes the fp32 matrix when the row set allows it
@@ -243,6 +246,7 @@ struct TbSolveMixedJob {
   double* pred;            // [n_v]
   double* fitness;
   int* sweeps;             // refinement sweeps used (diagnostics)
+  int* fail;               // set to 1 when the mixed-precision solve did not reach the tolerance (or a pivot failed)
   long long N;
   int n_t, n_v, ntp, rpad;
   int hole0, gap, valid_in_hole;   // see TbRowSet (contiguous kernels only)
@@ -250,7 +254,7 @@ struct TbSolveMixedJob {
 };
 cudaError_t tb_solve_mixed_init();
 bool tb_solve_mixed_fits(int ntp);
-cudaError_t tb_launch_solve_mixed(const TbSolveMixedJob* d_jobs, int n_jobs, int ntp, int contiguous, int c16,
+cudaError_t tb_launch_solve_mixed(const TbSolveMixedJob* d_jobs, int n_jobs, int ntp, int contiguous, int c16, int hole,
                                   cudaStream_t st);
 cudaError_t tb_launch_scale32(const TbScaleJob* d_jobs, int n_jobs, int ntp, float* L32, int c16, cudaStream_t st);
 cudaError_t tb_chol_tc_init();

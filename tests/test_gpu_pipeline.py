@@ -367,3 +367,32 @@ def test_cross_validation_folds_with_aligned_holes():
         assert abs(both[1, 1] - O.exact_fitness(genomes[1], folds[2][0], folds[2][1], x, y, 0.4, O.MODE_GBLUP)) < 1e-7
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("h2", [0.02, 0.9, 0.99, 0.999, 0.9999])
+def test_heritability_extremes_fall_back_to_fp64(h2):
+    """lambda = (1 - h2) / h2 -> 0 makes G_tt + lambda I ill-conditioned (singular G when k < n_t): the low-precision
+    factor breaks down or stops preconditioning.  Those jobs are evaluated again in fp64, so the fitness stays within
+    the bar for every heritability the reference accepts."""
+    from tblup_b200 import engine as E
+    g = load_golden("fit_mid")
+    x, y = g["x"], g["y"]
+    tr, va, te = g["train"], g["valid"], g["test"]
+    eng, perm = _engine(x, y, tr, va, te)
+    try:
+        rng = np.random.default_rng(1)
+        m = x.shape[1]
+        genomes = [rng.choice(m, size=k, replace=False) for k in (40, 255, 300, 401, 1500)]
+        total_fallbacks = 0
+        for mode, om in ((E.MODE_GBLUP, O.MODE_GBLUP), (E.MODE_SNPBLUP, O.MODE_SNPBLUP)):
+            got = eng.evaluate(genomes, slots=[0], h2=h2, mode=mode)[:, 0]
+            total_fallbacks += eng.info("last_fallbacks")
+            want = np.array([O.exact_fitness(gen, tr, va, x, y, h2, om) for gen in genomes])
+            # the fp64 solves of a matrix with cond ~ 1e6+ agree with the oracle's to ~cond * eps
+            assert np.all(np.isfinite(got)) and np.abs(got - want).max() < FIT_TOL, (h2, mode, got, want)
+        if h2 <= 0.9:
+            assert total_fallbacks == 0
+        if h2 >= 0.999:
+            assert total_fallbacks > 0
+    finally:
+        eng.close()
