@@ -303,76 +303,154 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 }
 
-// Diagonal block of the fp32 matrix: register-resident potrf + inverse (same scheme as chol_diag_kernel) in fp32
-// arithmetic -- the factor is rounded to TF32 (10 mantissa bits) on the way out, so fp32 (24 bits) math is ample,
-// and it halves the shared memory (more CTAs per SM) and avoids the long-latency fp64 sqrt/divide.  The rounded
-// factor is the one that gets inverted and stored, so the tensor-core operand truncation is a no-op and the
-// triangular solves in solve_mixed.cu use exactly the operator the factorisation built.
+// Diagonal block of the fp32 matrix (64 x 64): Cholesky factor + its inverse, in fp32 -- the factor is rounded to TF32
+// (10 mantissa bits) on the way out, so fp32 math is ample.  The rounded factor is the one that gets inverted and
+// stored, so the tensor-core operand truncation is a no-op and the triangular solves in solve_mixed.cu use exactly
+// the operator the factorisation built.
+// Recursive 2 x 2 blocking with WARP-LEVEL 32 x 32 kernels: a warp holds a 32 x 32 block one row (or column) per lane
+// in registers and exchanges pivot columns by shuffle, so the 64 dependent steps of the factorisation need no
+// block-wide barrier and ~5x fewer issued instructions than the previous thread-per-quarter-row scheme (the launch
+// was issue-bound: 97 us for 1 000 blocks).
+//   L11 = chol(A11)                      warp 0
+//   L21 = A21 L11^-T,  X11 = L11^-1      warps 1, 2
+//   A22 -= L21 L21^T                     all
+//   L22 = chol(A22)                      warp 0
+//   X22 = L22^-1,  P = L21 X11           warp 3, others
+//   X21 = -X22 P                         all
+constexpr int DLD = NB + 1;
+
+// a[c] = A[lane][c] (c <= lane valid) -> L[lane][c]; returns false on a non-positive pivot
+__device__ __forceinline__ bool warp_potrf32(float (&a)[32]) {
+  bool ok = true;
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    const float d = __shfl_sync(0xffffffffu, a[c], c);
+    ok = ok && d > 0.f;
+    const float l = a[c] * rsqrtf(d);                     // L[lane][c] for lane >= c
+    a[c] = l;
+#pragma unroll
+    for (int cc = c + 1; cc < 32; ++cc) a[cc] = fmaf(-l, __shfl_sync(0xffffffffu, l, cc), a[cc]);
+  }
+  return ok;
+}
+// row `lane` of B solved against the lower factor L (shared memory, leading dimension DLD): x L^T = b, in place
+__device__ __forceinline__ void warp_trsm32(float (&b)[32], const float* L) {
+#pragma unroll
+  for (int c = 0; c < 32; ++c) {
+    float s = b[c];
+#pragma unroll
+    for (int p = 0; p < c; ++p) s = fmaf(-b[p], L[c * DLD + p], s);
+    b[c] = s / L[c * DLD + c];
+  }
+}
+// column `lane` of X = L^-1: x[r] (zero for r < lane)
+__device__ __forceinline__ void warp_trinv32(float (&x)[32], const float* L, int lane) {
+#pragma unroll
+  for (int r = 0; r < 32; ++r) {
+    float s = r == lane ? 1.f : 0.f;
+#pragma unroll
+    for (int p = 0; p < r; ++p) s = fmaf(-L[r * DLD + p], x[p], s);
+    x[r] = r >= lane ? s / L[r * DLD + r] : 0.f;
+  }
+}
+
 __global__ void __launch_bounds__(256) chol_diag32_kernel(float* __restrict__ L32, float* __restrict__ Linv32,
                                                           __half* __restrict__ L16, int* __restrict__ status, int ntp,
                                                           int jb) {
-  __shared__ float Ls[NB][NB + 1];
-  __shared__ float Xs[NB][NB + 1];
-  __shared__ float colbuf[2][NB];
+  __shared__ float Ls[NB * DLD];
+  __shared__ float Xs[NB * DLD];
+  __shared__ float Ps[32 * 33];
   __shared__ int bad;
   const int job = blockIdx.x;
   float* D = L32 + ((size_t)job * ntp + (size_t)jb * NB) * ntp + jb * NB;
-  const int tid = threadIdx.x;
-  const int r = tid >> 2, q = tid & 3;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) bad = 0;
-  float a[16];
+  for (int e = tid; e < NB * 16; e += 256) {              // coalesced rows, 16 bytes per thread
+    const int r = e >> 4, c4 = (e & 15) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(D + (size_t)r * ntp + c4);
+    Ls[r * DLD + c4] = v.x;
+    Ls[r * DLD + c4 + 1] = v.y;
+    Ls[r * DLD + c4 + 2] = v.z;
+    Ls[r * DLD + c4 + 3] = v.w;
+  }
+  for (int e = tid; e < NB * NB; e += 256) Xs[(e >> 6) * DLD + (e & 63)] = 0.f;
+  __syncthreads();
+  float a[32];
+  if (warp == 0) {                                        // L11
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int c = q + 4 * i;
-    a[i] = c <= r ? D[(size_t)r * ntp + c] : 0.f;
+    for (int c = 0; c < 32; ++c) a[c] = Ls[lane * DLD + c];
+    if (!warp_potrf32(a)) bad = 1;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) Ls[lane * DLD + c] = c <= lane ? round_tf32(a[c]) : 0.f;
   }
   __syncthreads();
+  if (warp == 1) {                                        // L21 = A21 L11^-T
 #pragma unroll
-  for (int c = 0; c < NB; ++c) {
-    const int qc = c & 3, ic = c >> 2;
-    if (q == qc && r >= c) colbuf[c & 1][r] = a[ic];
+    for (int c = 0; c < 32; ++c) a[c] = Ls[(32 + lane) * DLD + c];
+    warp_trsm32(a, Ls);
+#pragma unroll
+    for (int c = 0; c < 32; ++c) Ls[(32 + lane) * DLD + c] = round_tf32(a[c]);
+  } else if (warp == 2) {                                 // X11 = L11^-1
+    warp_trinv32(a, Ls, lane);
+#pragma unroll
+    for (int r = 0; r < 32; ++r) Xs[r * DLD + lane] = a[r];
+  }
+  __syncthreads();
+  {                                                       // A22 -= L21 L21^T (lower part), 4 entries per thread
+    const int r = tid >> 3, c0 = (tid & 7) * 4;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int p = 0; p < 32; ++p) {
+      const float lr = Ls[(32 + r) * DLD + p];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(lr, Ls[(32 + c0 + j) * DLD + p], acc[j]);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      if (c0 + j <= r) Ls[(32 + r) * DLD + 32 + c0 + j] -= acc[j];
+  }
+  __syncthreads();
+  if (warp == 0) {                                        // L22
+#pragma unroll
+    for (int c = 0; c < 32; ++c) a[c] = Ls[(32 + lane) * DLD + 32 + c];
+    if (!warp_potrf32(a)) bad = 1;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) Ls[(32 + lane) * DLD + 32 + c] = c <= lane ? round_tf32(a[c]) : 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) Ls[lane * DLD + 32 + c] = 0.f;           // upper-right block of the factor
+  } else {                                                // P = L21 X11, meanwhile (224 threads, 32 x 32 outputs)
+    for (int e = tid - 32; e < 32 * 32; e += 224) {
+      const int r = e >> 5, c = e & 31;
+      float s = 0.f;
+      for (int p = c; p < 32; ++p) s = fmaf(Ls[(32 + r) * DLD + p], Xs[p * DLD + c], s);   // X11 is lower triangular
+      Ps[r * 33 + c] = s;
+    }
+  }
+  __syncthreads();
+  if (warp == 3) {                                        // X22 = L22^-1
+    warp_trinv32(a, Ls + 32 * DLD + 32, lane);
+#pragma unroll
+    for (int r = 0; r < 32; ++r) Xs[(32 + r) * DLD + 32 + lane] = a[r];
+  }
+  __syncthreads();
+  {                                                       // X21 = -X22 P
+    const int r = tid >> 3, c0 = (tid & 7) * 4;
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int p = 0; p <= r; ++p) {                        // X22 is lower triangular
+      const float xr = Xs[(32 + r) * DLD + 32 + p];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(xr, Ps[p * 33 + c0 + j], acc[j]);
+    }
     __syncthreads();
-    const float d = colbuf[c & 1][c];
-    if (!(d > 0.f) && tid == 0) bad = 1;
-    const float inv = rsqrtf(d);
-    if (r >= c) {
-      const float lr = colbuf[c & 1][r] * inv;
-      if (q == qc) a[ic] = lr;
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        const int cc = q + 4 * i;
-        if (cc > c && cc <= r) a[i] = fmaf(-lr, colbuf[c & 1][cc] * inv, a[i]);
-      }
-    }
-  }
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    const int c = q + 4 * i;
-    Ls[r][c] = c <= r ? round_tf32(a[i]) : 0.f;
-    Xs[r][c] = 0.f;
-  }
-  __syncthreads();
-  {
-    // X = L^-1 by forward substitution, one column per 4 lanes (8 columns per warp): the partial sums of a column
-    // meet by shuffle and its history in Xs is private to the warp, so the 64 row steps need no block-wide barrier
-    const int warp = tid >> 5, lane = tid & 31;
-    const int c = warp * 8 + (lane >> 2), h = lane & 3;
-    for (int rr = warp * 8; rr < NB; ++rr) {
-      float sacc = 0.f;
-      for (int pp = c + h; pp < rr; pp += 4) sacc = fmaf(Ls[rr][pp], Xs[pp][c], sacc);
-      sacc += __shfl_xor_sync(0xffffffffu, sacc, 1);
-      sacc += __shfl_xor_sync(0xffffffffu, sacc, 2);
-      if (h == 0 && rr >= c) Xs[rr][c] = ((c == rr ? 1.f : 0.f) - sacc) / Ls[rr][rr];
-      __syncwarp();
-    }
+    for (int j = 0; j < 4; ++j) Xs[(32 + r) * DLD + c0 + j] = -acc[j];
   }
   __syncthreads();
   float* Li = Linv32 + ((size_t)job * ntp + (size_t)jb * NB) * NB;
   for (int e = tid; e < NB * NB; e += 256) {
     const int rr = e >> 6, c = e & 63;
-    D[(size_t)rr * ntp + c] = Ls[rr][c];
-    if (L16) L16[((size_t)job * ntp + (size_t)jb * NB + rr) * ntp + jb * NB + c] = __float2half_rn(Ls[rr][c]);
-    Li[e] = round_tf32(Xs[rr][c]);
+    D[(size_t)rr * ntp + c] = Ls[rr * DLD + c];
+    if (L16) L16[((size_t)job * ntp + (size_t)jb * NB + rr) * ntp + jb * NB + c] = __float2half_rn(Ls[rr * DLD + c]);
+    Li[e] = round_tf32(Xs[rr * DLD + c]);
   }
   if (tid == 0 && bad) status[job] = 1;
 }
