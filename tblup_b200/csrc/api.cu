@@ -742,6 +742,7 @@ int tb_destroy(tb_ctx* c) {
   cudaFree(c->d_colsum_all);
   cudaFree(c->d_idx);
   cudaFree(c->d_fail);
+  cudaFree(c->d_fit_out);
   cudaFree(c->ws);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   delete c;
@@ -862,21 +863,26 @@ int tb_eval_staged(tb_ctx* c, const int32_t* slots, int n_slots, double h2, int 
   TB_CUDA(c, cudaSetDevice(c->device));
   const size_t n_out = (size_t)c->P * (size_t)std::max(n_slots, 0);
   double* d_fit = fitness_out;
-  double* d_tmp = nullptr;
   if (!out_is_device) {
-    TB_CUDA(c, cudaMalloc(&d_tmp, std::max<size_t>(n_out, 1) * sizeof(double)));
-    d_fit = d_tmp;
+    if (n_out > c->fit_cap) {                      // persistent device buffer for the host-output path
+      TB_CUDA(c, cudaStreamSynchronize(c->stream));
+      cudaFree(c->d_fit_out);
+      c->d_fit_out = nullptr;
+      c->fit_cap = 0;
+      TB_CUDA(c, cudaMalloc(&c->d_fit_out, std::max<size_t>(n_out, 1) * sizeof(double)));
+      c->fit_cap = n_out;
+    }
+    d_fit = c->d_fit_out;
   }
   int rc = eval_core(c, slots, n_slots, h2, mode_rule, d_fit);
   cudaError_t ce = cudaSuccess;
   if (rc == 0 && !out_is_device) {
     size_t sp = span_begin(c, TB_ST_D2H);
-    ce = cudaMemcpyAsync(fitness_out, d_tmp, n_out * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    ce = cudaMemcpyAsync(fitness_out, d_fit, n_out * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
     span_end(c, sp);
   }
   cudaError_t se = cudaStreamSynchronize(c->stream);
   spans_collect(c);
-  if (d_tmp) cudaFree(d_tmp);
   if (rc != 0) return rc;
   if (ce != cudaSuccess) return fail(c, std::string("D2H fitness: ") + cudaGetErrorString(ce), -2);
   if (se != cudaSuccess) return fail(c, std::string("device execution failed: ") + cudaGetErrorString(se), -2);

@@ -102,6 +102,8 @@ struct TbCtx {
   int last_fp4 = 0;
   int narrow_c = 1;               // 1: int16 cross-products when every genome of the batch has 4 k <= 32 767
   int last_c16 = 0;
+  double* d_fit_out = nullptr;    // device staging of the fitness vector for host-output calls
+  size_t fit_cap = 0;
   int* d_fail = nullptr;          // [P * n_slots] per-job "mixed precision gave up" flags of the last evaluation
   size_t fail_cap = 0;
   int last_fallbacks = 0;         // jobs the last evaluation re-ran in fp64
