@@ -827,18 +827,6 @@ int tb_stage_genomes(tb_ctx* c, const int32_t* idx_flat, const int64_t* idx_off,
   for (int i = 0; i < P; ++i)
     if (idx_off[i + 1] < idx_off[i]) return fail(c, "tb_stage_genomes: offsets must be non-decreasing");
   const size_t total = (size_t)idx_off[P];
-  {
-    // branch-free range check (vectorises): any index outside [0, m) sets the flag; the slow path names it
-    const unsigned um = (unsigned)c->m;
-    unsigned bad = 0;
-    for (size_t q = 0; q < total; ++q) bad |= (unsigned)((unsigned)idx_flat[q] >= um);
-    if (bad) {
-      for (size_t q = 0; q < total; ++q)
-        if (idx_flat[q] < 0 || idx_flat[q] >= c->m)
-          return fail(c, "tb_stage_genomes: marker index " + std::to_string(idx_flat[q]) + " out of range [0, " +
-                             std::to_string(c->m) + ")");
-    }
-  }
   TB_CUDA(c, cudaSetDevice(c->device));
   if (total > c->idx_cap) {
     TB_CUDA(c, cudaStreamSynchronize(c->stream));
@@ -848,9 +836,25 @@ int tb_stage_genomes(tb_ctx* c, const int32_t* idx_flat, const int64_t* idx_off,
     TB_CUDA(c, cudaMalloc(&c->d_idx, std::max<size_t>(total, 1) * sizeof(int)));
     c->idx_cap = total;
   }
+  // start the copy first, validate while it is in flight (pinned caller buffers make it truly asynchronous); a bad
+  // index invalidates the staged batch before anything can read it
   size_t sp = span_begin(c, TB_ST_H2D);
   TB_CUDA(c, cudaMemcpyAsync(c->d_idx, idx_flat, total * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   span_end(c, sp);
+  {
+    // branch-free range check (vectorises): any index outside [0, m) sets the flag; the slow path names it
+    const unsigned um = (unsigned)c->m;
+    unsigned bad = 0;
+    for (size_t q = 0; q < total; ++q) bad |= (unsigned)((unsigned)idx_flat[q] >= um);
+    if (bad) {
+      cudaStreamSynchronize(c->stream);
+      c->P = 0;
+      for (size_t q = 0; q < total; ++q)
+        if (idx_flat[q] < 0 || idx_flat[q] >= c->m)
+          return fail(c, "tb_stage_genomes: marker index " + std::to_string(idx_flat[q]) + " out of range [0, " +
+                             std::to_string(c->m) + ")");
+    }
+  }
   c->h_off.assign(idx_off, idx_off + P + 1);
   c->P = P;
   return 0;
