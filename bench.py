@@ -161,6 +161,18 @@ def chol_update_flops(ntp, nb=64):
     return tot
 
 
+def chol_update_bytes(ntp, ob=256):
+    """Algorithmic DRAM bytes of the outer Cholesky updates of one matrix in mixed precision: the fp32 block column
+    is read and written once (8 B per entry of the rows at and below the diagonal block) and the fp16 row operand
+    L[rows, 0:c0] is streamed once per block column (2 B per entry); the 256-row column operand stays in L2."""
+    tot = 0
+    for c0 in range(ob, ntp, ob):
+        w = min(ob, ntp - c0)
+        rows = ntp - c0
+        tot += rows * w * 8 + rows * c0 * 2
+    return tot
+
+
 def main():
     args = parse()
     wl = dict(WORKLOADS[args.workload])
@@ -382,6 +394,19 @@ def main():
                      "frac": (achieved / upd_peak) if achieved and upd_peak else None, "traffic": None,
                      "peak_source": upd_peak_src, "launches": int(upd_launches),
                      "avg_launch_ms": upd_ms / max(1, upd_launches), "share_of_step": upd_ms / ms_instrumented}
+        if precision == "mixed" and upd_ms > 0:
+            # with fp16 operands the update is HBM-bound (ncu: 79 % of the copy bandwidth, tensor pipe 46 % active):
+            # report it against the bandwidth roofline and keep the flop rate beside it
+            upd_bytes = chol_update_bytes(ntp, 256)
+            upd_gbs = upd_bytes * n_mats / (upd_ms * 1e-3) / 1e9
+            rl_update = {"bound": "hbm", "kernel": upd_kernel, "achieved": upd_gbs,
+                         "peak": peaks.get("hbm_gbs") or 6650.0, "unit": "GB/s",
+                         "frac": upd_gbs / (peaks.get("hbm_gbs") or 6650.0), "traffic": None,
+                         "algorithmic_bytes_per_matrix": upd_bytes,
+                         "peak_source": "hbm_gbs of MEASURED_PEAKS.json" if peaks.get("hbm_gbs") else "fallback 6650 GB/s",
+                         "tensor_tflops": achieved, "tensor_frac_of_bf16_sustained": achieved / upd_peak,
+                         "launches": int(upd_launches), "avg_launch_ms": upd_ms / max(1, upd_launches),
+                         "share_of_step": upd_ms / ms_instrumented}
         solve_ms, solve_launches = stage["solve"]
         csz = 2 if c16 else 4
         tri_c = n_t * (n_t + 1) / 2 * csz            # lower triangle of the stored cross-products
