@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <thread>
 
 namespace {
 
@@ -844,8 +845,25 @@ int tb_stage_genomes(tb_ctx* c, const int32_t* idx_flat, const int64_t* idx_off,
   {
     // branch-free range check (vectorises): any index outside [0, m) sets the flag; the slow path names it
     const unsigned um = (unsigned)c->m;
+    auto scan = [&](size_t lo, size_t hi) {
+      unsigned b = 0;
+      for (size_t q = lo; q < hi; ++q) b |= (unsigned)((unsigned)idx_flat[q] >= um);
+      return b;
+    };
     unsigned bad = 0;
-    for (size_t q = 0; q < total; ++q) bad |= (unsigned)((unsigned)idx_flat[q] >= um);
+    if (total >= ((size_t)1 << 20)) {               // a generation's worth of indices: four host threads
+      constexpr int NT = 4;
+      unsigned part[NT] = {0, 0, 0, 0};
+      std::thread th[NT - 1];
+      const size_t chunk = (total + NT - 1) / NT;
+      for (int t = 1; t < NT; ++t)
+        th[t - 1] = std::thread([&, t] { part[t] = scan(std::min(total, t * chunk), std::min(total, (t + 1) * chunk)); });
+      part[0] = scan(0, std::min(total, chunk));
+      for (int t = 1; t < NT; ++t) th[t - 1].join();
+      for (int t = 0; t < NT; ++t) bad |= part[t];
+    } else {
+      bad = scan(0, total);
+    }
     if (bad) {
       cudaStreamSynchronize(c->stream);
       c->P = 0;
