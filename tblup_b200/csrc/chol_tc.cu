@@ -514,8 +514,8 @@ __global__ void __launch_bounds__(256) trinv256_kernel(const float* __restrict__
       *reinterpret_cast<float4*>(dst + r * ld_dst + c4) = v;
     }
   };
-  for (int b = 0; b < 4; ++b) {
-    // the blocks above the diagonal of X are zero (the GEMM reads the full 256 x 256 operand)
+  // per block column b: zero blocks above the diagonal, X_bb = Linv_b
+  auto column_setup = [&](int b) {
     for (int i = 0; i < b; ++i)
       for (int e = tid; e < 64 * 16; e += 256)
         *reinterpret_cast<float4*>(Out + (size_t)(64 * i + (e >> 4)) * 256 + 64 * b + (e & 15) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -526,45 +526,97 @@ __global__ void __launch_bounds__(256) trinv256_kernel(const float* __restrict__
       *reinterpret_cast<float4*>(Out + (size_t)(64 * b + r) * 256 + 64 * b + c4) =
           *reinterpret_cast<const float4*>(Xs + b * 64 * XS_LD + r * XS_LD + c4);
     }
-    for (int i = b + 1; i < 4; ++i) {
-      float acc[4][4];
+  };
+  // The left operands form a fixed sequence (b, i, k): L_ik for k = b .. i-1, then Linv_i (written k = i), for
+  // i = b+1 .. 3, b = 0 .. 2.  Each one is fetched into registers while the previous product runs, so the global-load
+  // latency (the launch was bound by it: 16 dependent load -> barrier -> mma rounds) hides behind the tensor work.
+  auto operand = [&](int b, int i, int k, const float*& src, size_t& ld) {
+    if (k < i) {
+      src = Lj + (size_t)(64 * i) * ntp + 64 * k;
+      ld = (size_t)ntp;
+    } else {
+      src = Dj + (size_t)i * 64 * NB;
+      ld = NB;
+    }
+  };
+  float4 pre[4];
+  auto fetch = [&](int b, int i, int k) {
+    const float* src;
+    size_t ld;
+    operand(b, i, k, src, ld);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = tid + 256 * u;
+      pre[u] = *reinterpret_cast<const float4*>(src + (size_t)(e >> 4) * ld + (e & 15) * 4);
+    }
+  };
+  auto deposit = [&]() {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = tid + 256 * u;
+      *reinterpret_cast<float4*>(As + (e >> 4) * AS_LD + (e & 15) * 4) = pre[u];
+    }
+  };
+  int b = 0, i = 1, k = 0;
+  fetch(b, i, k);
+  float acc[4][4];
+  for (;;) {
+    if (i == b + 1 && k == b) column_setup(b);           // first operand of block column b
+    deposit();
+    __syncthreads();
+    int nb = b, ni = i, nk = k + 1;                       // successor in the sequence
+    if (nk > i) {
+      ni = i + 1;
+      nk = b;
+      if (ni > 3) {
+        nb = b + 1;
+        ni = nb + 1;
+        nk = nb;
+      }
+    }
+    const bool more = nb < 3;
+    if (more) fetch(nb, ni, nk);
+    if (k == b) {
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
         for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
-      for (int k = b; k < i; ++k) {
-        load_block(Lj + (size_t)(64 * i) * ntp + 64 * k, ntp, As, AS_LD);
-        __syncthreads();
-        block_mma(acc, As, Xs + k * 64 * XS_LD, warp, lane);
-        __syncthreads();
-      }
+    }
+    if (k < i) {
+      block_mma(acc, As, Xs + k * 64 * XS_LD, warp, lane);
+      if (k == i - 1) {                                   // S = sum_k L_ik X_kb complete: becomes the right operand
 #pragma unroll
-      for (int nt = 0; nt < 4; ++nt) {
-        *reinterpret_cast<float2*>(Ss + frow * XS_LD + fcol + 8 * nt) = make_float2(round_tf32(acc[nt][0]), round_tf32(acc[nt][1]));
-        *reinterpret_cast<float2*>(Ss + (frow + 8) * XS_LD + fcol + 8 * nt) = make_float2(round_tf32(acc[nt][2]), round_tf32(acc[nt][3]));
+        for (int nt = 0; nt < 4; ++nt) {
+          *reinterpret_cast<float2*>(Ss + frow * XS_LD + fcol + 8 * nt) = make_float2(round_tf32(acc[nt][0]), round_tf32(acc[nt][1]));
+          *reinterpret_cast<float2*>(Ss + (frow + 8) * XS_LD + fcol + 8 * nt) = make_float2(round_tf32(acc[nt][2]), round_tf32(acc[nt][3]));
+        }
       }
-      load_block(Dj + (size_t)i * 64 * NB, NB, As, AS_LD);
-      __syncthreads();
+    } else {                                              // X_ib = -Linv_i S
+      float acc2[4][4];
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
-      block_mma(acc, As, Ss, warp, lane);
+        for (int e = 0; e < 4; ++e) acc2[nt][e] = 0.f;
+      block_mma(acc2, As, Ss, warp, lane);
       float* Xi = Xs + i * 64 * XS_LD;
       float* Oi = Out + (size_t)(64 * i) * 256 + 64 * b;
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
-        const float2 lo = make_float2(round_tf32(-acc[nt][0]), round_tf32(-acc[nt][1]));
-        const float2 hi = make_float2(round_tf32(-acc[nt][2]), round_tf32(-acc[nt][3]));
+        const float2 lo = make_float2(round_tf32(-acc2[nt][0]), round_tf32(-acc2[nt][1]));
+        const float2 hi = make_float2(round_tf32(-acc2[nt][2]), round_tf32(-acc2[nt][3]));
         *reinterpret_cast<float2*>(Xi + frow * XS_LD + fcol + 8 * nt) = lo;
         *reinterpret_cast<float2*>(Xi + (frow + 8) * XS_LD + fcol + 8 * nt) = hi;
         *reinterpret_cast<float2*>(Oi + (size_t)frow * 256 + fcol + 8 * nt) = lo;
         *reinterpret_cast<float2*>(Oi + (size_t)(frow + 8) * 256 + fcol + 8 * nt) = hi;
       }
-      __syncthreads();
     }
     __syncthreads();
+    if (!more) break;
+    b = nb;
+    i = ni;
+    k = nk;
   }
+  column_setup(3);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
