@@ -26,6 +26,7 @@ fit = torch.empty(P, dtype=torch.float64, device="cuda")
 for _ in range(3):
     eng.evaluate_staged([0], out_device_ptr=fit.data_ptr())
 ts = []
+issue = []
 for i in range(steps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
@@ -33,6 +34,7 @@ for i in range(steps):
     e1.record(stream)
     torch.cuda.synchronize()
     ts.append(e0.elapsed_time(e1))
+    issue.append(eng.info("last_issue_us") / 1e3)
 ts = np.array(ts)
 print("pop %d %s %s: per-step ms median %.1f min %.1f max %.1f  -> %.0f evals/s (median)" % (
     P, prec, storage, np.median(ts), ts.min(), ts.max(), P / np.median(ts) * 1e3))
@@ -44,5 +46,6 @@ for i in range(5):
     for k, v in eng.stage_times().items():
         agg.setdefault(k, []).append(v[0])
 print("per-step ms:", [round(float(t), 1) for t in ts], "fallbacks", eng.info("last_fallbacks"))
+print("host issue ms per step:", [round(t, 2) for t in issue])
 print("stage medians (ms):", {k: round(float(np.median(v)), 2) for k, v in agg.items()},
       "sum %.1f" % sum(float(np.median(v)) for v in agg.values()))

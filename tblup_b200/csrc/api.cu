@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <chrono>
 #include <thread>
 
 namespace {
@@ -128,6 +129,7 @@ struct SlotView {
 
 int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_rule, double* d_fit,
               bool allow_fallback = true) {
+  const auto t_host0 = std::chrono::steady_clock::now();
   if (c->P <= 0) return fail(c, "tb_eval_staged: no genomes staged");
   if (n_slots <= 0 || n_slots > TB_MAX_SLOTS) return fail(c, "tb_eval_staged: bad n_slots");
   if (!(h2 > 0.0) || !(h2 <= 1.0)) return fail(c, "tb_eval_staged: heritability must be in (0, 1]");
@@ -196,10 +198,16 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
   per_ind += (size_t)rpad * kstride_max + (size_t)rpad * rpad * sizeof(int32_t) +
              (size_t)n_slots * (rpad + 2) * sizeof(long long) + (size_t)n_slots * kstride_max * sizeof(int) + 4096;
 
-  size_t free_b = 0, total_b = 0;
-  TB_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
-  size_t budget = c->ws_limit ? c->ws_limit : (size_t)((double)(free_b + c->ws_bytes) * 0.80);
   const size_t fixed = (size_t)128 * kstride_max + (size_t)P * n_slots * 512 + (size_t)128 * max_ntp * sizeof(float) + (1 << 20);
+  const int want = std::max(1, std::min(c->max_wave > 0 ? std::min(P, c->max_wave) : P, 1024));
+  size_t budget;
+  if (!c->ws_limit && fixed + per_ind * (size_t)want <= c->ws_bytes) {
+    budget = c->ws_bytes;                          // the arena already holds the whole batch: no driver query needed
+  } else {
+    size_t free_b = 0, total_b = 0;
+    TB_CUDA(c, cudaMemGetInfo(&free_b, &total_b));
+    budget = c->ws_limit ? c->ws_limit : (size_t)((double)(free_b + c->ws_bytes) * 0.80);
+  }
   if (budget < fixed + per_ind) budget = fixed + per_ind;
   long long Wll = (long long)((budget - fixed) / per_ind);
   int W = (int)std::min<long long>(Wll, P);
@@ -475,6 +483,9 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     span_end(c, sp);
     count(c, TB_ST_SOLVE, 1);
   }
+  // host time spent issuing the evaluation (everything above is asynchronous): diagnostics, "last_issue_us"
+  c->last_issue_us = (long long)std::chrono::duration_cast<std::chrono::microseconds>(
+                         std::chrono::steady_clock::now() - t_host0).count();
   if (mixed && allow_fallback && c->stop_after < 0) return fp64_fallback(c, slots, n_slots, h2, mode_rule, d_fit);
   return 0;
 }
@@ -1075,6 +1086,7 @@ int tb_get_info(const tb_ctx* c, const char* name, long long* value) {
   else if (s == "de_removed") *value = c->de.n_banned;
   else if (s == "last_fp4") *value = c->last_fp4;
   else if (s == "last_fallbacks") *value = c->last_fallbacks;
+  else if (s == "last_issue_us") *value = c->last_issue_us;
   else if (s == "staged") *value = c->P;
   else return -1;
   return 0;

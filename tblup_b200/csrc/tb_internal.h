@@ -106,6 +106,7 @@ struct TbCtx {
   size_t fit_cap = 0;
   int* d_fail = nullptr;          // [P * n_slots] per-job "mixed precision gave up" flags of the last evaluation
   size_t fail_cap = 0;
+  long long last_issue_us = 0;    // host microseconds the last evaluation took to issue (diagnostics)
   int last_fallbacks = 0;         // jobs the last evaluation re-ran in fp64
   int last_fused = 0;
   int wide_panel = 1;             // 1: 256-wide panel solve through the inverse of the diagonal block (chol_tc.cu)
