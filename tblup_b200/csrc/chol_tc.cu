@@ -619,6 +619,106 @@ __global__ void __launch_bounds__(256) trinv256_kernel(const float* __restrict__
   column_setup(3);
 }
 
+// acc (16 x 8 fragments, nt = 0..3) += As[64][AS_LD] * Bt[64][AS_LD]^T: both operands row-major [row][k]
+__device__ __forceinline__ void block_mma_nt(float (&acc)[4][4], const float* As, const float* Bt, int warp, int lane) {
+  const int g = lane >> 2, t = lane & 3;
+  const float* a_base = As + (16 * (warp & 3) + g) * AS_LD + t;
+  const float* b_base = Bt + (32 * (warp >> 2) + g) * AS_LD + t;
+#pragma unroll
+  for (int k = 0; k < 64; k += 8) {
+    uint32_t a[4];
+    a[0] = __float_as_uint(a_base[k]);
+    a[1] = __float_as_uint(a_base[8 * AS_LD + k]);
+    a[2] = __float_as_uint(a_base[k + 4]);
+    a[3] = __float_as_uint(a_base[8 * AS_LD + k + 4]);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      uint32_t b[2];
+      b[0] = __float_as_uint(b_base[8 * nt * AS_LD + k]);
+      b[1] = __float_as_uint(b_base[8 * nt * AS_LD + k + 4]);
+      mma_tf32_16x8x8(acc[nt], a, b);
+    }
+  }
+}
+
+// The narrow work of one inner step b inside the (up to) 256-row diagonal block, one CTA per job, after
+// chol_diag32_kernel(b):   L_ib = T_ib Linv_b^T for the blocks below (i > b), written as the fp32 / fp16 factor, and the
+// left-looking update of the NEXT block column, T_ij -= sum_{k <= b} L_ik L_jk^T (j = b + 1, i >= j).
+// Sixteen 64^3 products per diagonal block on mma.sync instead of six persistent tcgen05 launches whose fixed cost
+// (TMEM allocation, pipeline fill) dwarfed the 2 000 small tiles they covered.
+__global__ void __launch_bounds__(256) chol_narrow_kernel(float* __restrict__ L32, __half* __restrict__ L16,
+                                                          const float* __restrict__ Linv32, int ntp, int c0, int b,
+                                                          int nbk) {
+  __shared__ float As[64 * AS_LD];
+  __shared__ float Bs[64 * AS_LD];
+  const int job = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* base = L32 + ((size_t)job * ntp + c0) * ntp + c0;
+  __half* base16 = L16 ? L16 + ((size_t)job * ntp + c0) * ntp + c0 : nullptr;
+  const int g = lane >> 2, t = lane & 3;
+  const int frow = 16 * (warp & 3) + g, fcol = 32 * (warp >> 2) + 2 * t;
+  auto load_block = [&](const float* src, size_t ld_src, float* dst) {
+    for (int e = tid; e < 64 * 16; e += 256) {
+      const int r = e >> 4, c4 = (e & 15) * 4;
+      *reinterpret_cast<float4*>(dst + r * AS_LD + c4) = *reinterpret_cast<const float4*>(src + (size_t)r * ld_src + c4);
+    }
+  };
+  float acc[4][4];
+  auto clear = [&]() {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+  };
+  // (i) triangular solves of block column b
+  load_block(Linv32 + ((size_t)job * ntp + c0 + 64 * b) * NB, NB, Bs);
+  for (int i = b + 1; i < nbk; ++i) {
+    float* blk = base + (size_t)(64 * i) * ntp + 64 * b;
+    load_block(blk, ntp, As);
+    __syncthreads();
+    clear();
+    block_mma_nt(acc, As, Bs, warp, lane);
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      const float2 lo = make_float2(round_tf32(acc[nt][0]), round_tf32(acc[nt][1]));
+      const float2 hi = make_float2(round_tf32(acc[nt][2]), round_tf32(acc[nt][3]));
+      *reinterpret_cast<float2*>(blk + (size_t)frow * ntp + fcol + 8 * nt) = lo;
+      *reinterpret_cast<float2*>(blk + (size_t)(frow + 8) * ntp + fcol + 8 * nt) = hi;
+      if (base16) {
+        __half* h = base16 + (size_t)(64 * i) * ntp + 64 * b;
+        *reinterpret_cast<__half2*>(h + (size_t)frow * ntp + fcol + 8 * nt) = __floats2half2_rn(lo.x, lo.y);
+        *reinterpret_cast<__half2*>(h + (size_t)(frow + 8) * ntp + fcol + 8 * nt) = __floats2half2_rn(hi.x, hi.y);
+      }
+    }
+    __syncthreads();                 // the block just written is read again below; As is reused
+  }
+  // (ii) update of block column j = b + 1 with every finished column of the diagonal block
+  const int j = b + 1;
+  if (j >= nbk) return;
+  for (int i = j; i < nbk; ++i) {
+    clear();
+    for (int k = 0; k <= b; ++k) {
+      load_block(base + (size_t)(64 * i) * ntp + 64 * k, ntp, As);
+      load_block(base + (size_t)(64 * j) * ntp + 64 * k, ntp, Bs);
+      __syncthreads();
+      block_mma_nt(acc, As, Bs, warp, lane);
+      __syncthreads();
+    }
+    float* blk = base + (size_t)(64 * i) * ntp + 64 * j;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      float2* p0 = reinterpret_cast<float2*>(blk + (size_t)frow * ntp + fcol + 8 * nt);
+      float2* p1 = reinterpret_cast<float2*>(blk + (size_t)(frow + 8) * ntp + fcol + 8 * nt);
+      float2 v0 = *p0, v1 = *p1;
+      v0.x -= acc[nt][0];
+      v0.y -= acc[nt][1];
+      v1.x -= acc[nt][2];
+      v1.y -= acc[nt][3];
+      *p0 = v0;
+      *p1 = v1;
+    }
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -728,6 +828,22 @@ cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, float* Linv2
     // update / triangular-solve rounds; the narrow rounds then only cover the 256 rows of the diagonal block itself.
     const bool wide = Linv256 != nullptr && w == OB && c0 + w < ntp;
     const int narrow_end = wide ? c0 + w : ntp;
+    if (Linv256 != nullptr && narrow_end == c0 + w) {
+      // the narrow rounds only cover the diagonal block itself: potrf + inverse per 64-block, then one small
+      // mma.sync kernel per step for the solves below it and the update of the next block column
+      const int nbk = w / NB;
+      for (int b = 0; b < nbk; ++b) {
+        chol_diag32_kernel<<<n_jobs, 256, DIAG32_SMEM, st>>>(L32, Linv32, static_cast<__half*>(L16), status, ntp,
+                                                             (c0 + b * NB) / NB);
+        launches[1]++;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        if (b + 1 < nbk) {
+          chol_narrow_kernel<<<n_jobs, 256, 0, st>>>(L32, static_cast<__half*>(L16), Linv32, ntp, c0, b, nbk);
+          launches[1]++;
+          if ((e = cudaGetLastError()) != cudaSuccess) return e;
+        }
+      }
+    } else
     for (int cc = c0; cc < c0 + w; cc += NB) {
       if (cc > c0) {
         GemmParams p{};
