@@ -212,7 +212,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       // ---- fused scaling: per-tile terms, prepared while the tile's MMAs run
       bool a_tile = false;
       int f_nt = 0, f_ntp = 0;
-      float f_scale = 0.f, f_rowterm = 0.f, f_lam = 0.f;
+      float f_scale = 0.f, f_lam = 0.f;
+      float f_rowterm[4] = {0.f, 0.f, 0.f, 0.f};      // rows 16 hh + 8 rr + (lane >> 2) of this warp, index 2 hh + rr
       uint32_t ct = 0;
       if (FUSE) {
         const TbScaleJob& jb = fz.jobs[w];
@@ -234,7 +235,11 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
             const float term = b < f_nt ? (float)(inv_d * (double)(Q - N * jb.s[b])) : 0.f;
             asm volatile("st.shared.f32 [%0], %1;" ::"r"(cw + e * 4), "f"(term) : "memory");
           }
-          f_rowterm = row < f_nt ? (float)(inv_d * (double)(-N * jb.s[row])) : 0.f;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int grow = ti * BM + q * 32 + 16 * (i >> 1) + 8 * (i & 1) + (lane >> 2);
+            f_rowterm[i] = grow < f_nt ? (float)(inv_d * (double)(-N * jb.s[grow])) : 0.f;
+          }
           ct = cw;
           fbuf ^= 1;
           // the buffer written two A-tiles ago is free again: every warp passed this barrier once since
@@ -258,7 +263,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         tmem_ld_wait();
         float vf[32];                                  // the cross-products as floats (exact: integers below 2^24)
 #pragma unroll
-        for (int e = 0; e < 32; ++e) vf[e] = FP4 ? __uint_as_float(v[e]) : (FUSE ? (float)(int)v[e] : 0.f);
+        for (int e = 0; e < 32; ++e) vf[e] = FP4 ? __uint_as_float(v[e]) : 0.f;
         if (FP4) {
           // fp32 accumulators -> integers: adding 2^23 leaves the integer in the low mantissa bits (values < 2^23;
           // the int16 layout only needs 15 of them); the int32 layout goes through the converter
@@ -292,34 +297,41 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
           }
         }
         if (FUSE && a_tile && col0 < f_ntp) {
-          uint32_t o[32];
-          float cterm[32];
+          // second read of the chunk in the accumulator-fragment layout: four lanes own 32 contiguous bytes of a row,
+          // so the scaled matrix goes out with 8-byte stores of whole sectors and no shared-memory transposition
+          // (the staging traffic of this, the larger, output competed with the MMA operand reads)
+          const int t0 = lane & 3, t1 = lane >> 2;
 #pragma unroll
-          for (int e = 0; e < 32; e += 4)
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(cterm[e]), "=f"(cterm[e + 1]), "=f"(cterm[e + 2]), "=f"(cterm[e + 3])
-                         : "r"(ct + (c * 32 + e) * 4));
+          for (int hh = 0; hh < 2; ++hh) {
+            uint32_t w[16];
+            tmem_ld_16x256b_x4(tmem_base + (static_cast<uint32_t>(q * 32 + 16 * hh) << 16) + acc * ACC_STRIDE + c * 32, w);
+            tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const int b = col0 + e;
-            // columns b >= n_t only occur above the diagonal of a training row (never read)
-            float g = fmaf(vf[e], f_scale, f_rowterm + cterm[e]);
-            if (b == row) g += f_lam;
-            if (row >= f_nt) g = b == row ? 1.f : 0.f;      // identity padding rows
-            o[e] = __float_as_uint(g);
-          }
-          const int arow0 = ti * BM + q * 32;
+            for (int rr = 0; rr < 2; ++rr) {
+              const int rloc = 16 * hh + 8 * rr + t1;
+              const int grow = ti * BM + q * 32 + rloc;
+              if (grow >= f_ntp) continue;
+              const float rt = f_rowterm[2 * hh + rr];
+              float* drow = awarp + (size_t)rloc * fz.ntp_all + col0 + 2 * t0;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            stage_write16(stg, lane, o + 16 * h);
-            __syncwarp();
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const uint4 u = stage_read16(stg, lane, it);
-              if (arow0 + 8 * it + rl < f_ntp)
-                *reinterpret_cast<uint4*>(awarp + (size_t)(8 * it + rl) * fz.ntp_all + col0 + 16 * h + gl) = u;
+              for (int j = 0; j < 4; ++j) {
+                float c0f, c1f;
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(c0f), "=f"(c1f) : "r"(ct + (c * 32 + 8 * j + 2 * t0) * 4));
+                const uint32_t w0 = w[4 * j + 2 * rr], w1 = w[4 * j + 2 * rr + 1];
+                const float x0 = FP4 ? __uint_as_float(w0) : (float)(int)w0;
+                const float x1 = FP4 ? __uint_as_float(w1) : (float)(int)w1;
+                const int b0 = col0 + 8 * j + 2 * t0;
+                // columns b >= n_t only occur above the diagonal of a training row (never read)
+                float g0 = fmaf(x0, f_scale, rt + c0f), g1 = fmaf(x1, f_scale, rt + c1f);
+                if (b0 == grow) g0 += f_lam;
+                if (b0 + 1 == grow) g1 += f_lam;
+                if (grow >= f_nt) {                          // identity padding rows
+                  g0 = b0 == grow ? 1.f : 0.f;
+                  g1 = b0 + 1 == grow ? 1.f : 0.f;
+                }
+                *reinterpret_cast<float2*>(drow + 8 * j) = make_float2(g0, g1);
+              }
             }
-            __syncwarp();
           }
         }
       }

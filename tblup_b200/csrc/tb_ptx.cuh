@@ -127,6 +127,19 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
       : "r"(taddr)
       : "memory");
 }
+// 16 lanes x 32 consecutive 32-bit columns in the MMA-accumulator register layout (shape .16x256b, 4 repeats):
+// lane l = 4 r + p holds, for column group j = 0..3, v[4 j + {0,1}] = row r, columns 8 j + 2 p + {0,1} and
+// v[4 j + {2,3}] = row r + 8, same columns -- four lanes own 32 contiguous bytes of a row, so an 8-byte store per
+// lane writes whole sectors without a trip through shared memory.
+__device__ __forceinline__ void tmem_ld_16x256b_x4(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- coalescing epilogue stores ----------------------------------------------------------------
