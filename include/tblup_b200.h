@@ -112,11 +112,13 @@ int tb_debug_fetch(tb_ctx* ctx, int what, int job, void* out, size_t nbytes);
  * fp32 matrix itself), "wide_panel" (0/1, default 1: 256-wide Cholesky panel through the inverse of the diagonal
  * block), "narrow_c" (0/1, default 1: int16 storage of the cross-products when 4 k <= 32 767 for the whole batch),
  * "gram_fp4" (0/1, default 1: with packed resident genotypes the Gram runs on E2M1 operands, tcgen05 kind::mxf4 --
- * dosages 0/1/2 are exact in E2M1 and the fp32 accumulators hold the same integers; 0 = int8 operands) */
+ * dosages 0/1/2 are exact in E2M1 and the fp32 accumulators hold the same integers; 0 = int8 operands),
+ * "perm_rows" (0/1, default 1: a single scattered row set -- Monte-Carlo split, unaligned fold, custom splitter -- is
+ * turned into a prefix by permuting the panel rows at gather time, so it runs the contiguous kernels) */
 int tb_set_option(tb_ctx* ctx, const char* name, long long value);
 
 /* Facts about the last evaluation / the context: "last_c16", "last_fused_scale", "last_mixed", "last_wave",
- * "storage", "wide_panel", "de_removed" (size of the removed-marker set), "staged" (genomes staged), "last_fp4",
+ * "storage", "wide_panel", "de_removed" (size of the removed-marker set), "staged" (genomes staged), "last_fp4", "last_perm",
  * "last_fallbacks" (jobs of the last evaluation whose mixed-precision solve gave up -- pivot breakdown or no
  * convergence, h2 close to 1 -- and that were evaluated again with the fp64 Cholesky). */
 int tb_get_info(const tb_ctx* ctx, const char* name, long long* value);

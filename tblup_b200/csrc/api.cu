@@ -34,6 +34,8 @@ int fail(TbCtx* c, const std::string& msg, int code = -1) {
 void free_rowset(TbRowSet& r) {
   cudaFree(r.d_tpos);
   cudaFree(r.d_vpos);
+  cudaFree(r.d_rowmap);
+  cudaFree(r.d_ident);
   cudaFree(r.d_colsum_train);
   cudaFree(r.d_yt_raw);
   cudaFree(r.d_yt_ctr);
@@ -161,6 +163,20 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     if (k <= 0) return fail(c, "tb_eval_staged: empty genome at position " + std::to_string(i));
     kmax = std::max(kmax, k);
   }
+  // E2M1 Gram: needs the packed resident matrix (its gather is written for it); every sum is an integer <= 4 kmax,
+  // exact in the fp32 accumulators below 2^24
+  const bool fp4 = c->gram_fp4 && c->d_x2 != nullptr && 4LL * kmax < (1LL << 24);
+  c->last_fp4 = fp4 ? 1 : 0;
+  // a single scattered row set (Monte-Carlo split, unaligned fold, custom splitter): permute the panel rows at gather
+  // time -- training animals first, validation animals next -- and everything downstream sees a plain prefix
+  const bool use_perm = n_slots == 1 && c->perm_rows && fp4 && !sv[0].rs->contiguous && sv[0].rs->perm_ok;
+  c->last_perm = use_perm ? 1 : 0;
+  if (use_perm) {
+    const TbRowSet* rs = sv[0].rs;
+    rpad = tb_round_up(rs->n_t + rs->n_v, TB_GRAM_BM);
+    has_train.assign(rpad / TB_GRAM_BM, 0);
+    for (int blk = 0; blk * TB_GRAM_BM < rs->n_t; ++blk) has_train[blk] = 1;
+  }
   // the mixed path turns cross-products (<= 4 k) into floats through the 2^23 mantissa trick: 4 kmax < 2^23
   bool mixed = c->precision == 0 && tb_solve_mixed_fits(max_ntp) && 4LL * kmax < (1LL << 23);
   for (int s = 0; s < n_slots; ++s) mixed = mixed && sv[s].rs->ntp == max_ntp;
@@ -184,12 +200,8 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
                  (size_t)(max_ntp + sv[s].rs->n_v) * sizeof(double) + 1024;
   }
   // one contiguous row set: the Gram epilogue writes the fp32 matrix itself (no separate scaling pass over C)
-  const bool fuse_scale = mixed && n_slots == 1 && sv[0].rs->contiguous && c->n <= 46340 && c->fuse_scale;
+  const bool fuse_scale = mixed && n_slots == 1 && (sv[0].rs->contiguous || use_perm) && c->n <= 46340 && c->fuse_scale;
   c->last_fused = fuse_scale ? 1 : 0;
-  // E2M1 Gram: needs the packed resident matrix (its gather is written for it); every sum is an integer <= 4 kmax,
-  // exact in the fp32 accumulators below 2^24
-  const bool fp4 = c->gram_fp4 && c->d_x2 != nullptr && 4LL * kmax < (1LL << 24);
-  c->last_fp4 = fp4 ? 1 : 0;
   const int kq = fp4 ? TB_GRAM_BK_FP4 : TB_GRAM_BK;      // markers per k-block
   const int kstride_max = tb_round_up(kmax, kq);
   // every cross-product is at most 4 k: int16 storage is exact for the whole batch when 4 kmax <= 32 767
@@ -323,8 +335,8 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
                    : d_C + (size_t)w * rpad * rpad;
         sj.s = d_s + (size_t)cjob * rpad;
         sj.SQ = d_SQ + (size_t)cjob * 2;
-        sj.tpos = rs->d_tpos;
-        sj.vpos = rs->d_vpos;
+        sj.tpos = use_perm ? rs->d_ident : rs->d_tpos;
+        sj.vpos = use_perm ? rs->d_ident + rs->n_t : rs->d_vpos;
         sj.M = Mj;
         sj.N = gblup ? c->n : rs->n_t;
         sj.n_t = rs->n_t;
@@ -356,8 +368,8 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
         mj.C = sj.C;
         mj.s = sj.s;
         mj.SQ = sj.SQ;
-        mj.tpos = rs->d_tpos;
-        mj.vpos = rs->d_vpos;
+        mj.tpos = sj.tpos;
+        mj.vpos = sj.vpos;
         mj.y_t = oj.y_t;
         mj.y_v = oj.y_v;
         mj.status = d_status + job;
@@ -371,9 +383,9 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
         mj.n_v = rs->n_v;
         mj.ntp = rs->ntp;
         mj.rpad = rpad;
-        mj.hole0 = rs->hole0;
-        mj.gap = rs->gap;
-        mj.valid_in_hole = rs->valid_in_hole ? 1 : 0;
+        mj.hole0 = use_perm ? rs->n_t : rs->hole0;
+        mj.gap = use_perm ? 0 : rs->gap;
+        mj.valid_in_hole = (!use_perm && rs->valid_in_hole) ? 1 : 0;
         mj.lambda = lambda;
         c->dbg.M[job] = Mj;
         c->dbg.alpha[job] = aj;
@@ -396,7 +408,8 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
 
     sp = span_begin(c, TB_ST_GATHER);
     if (fp4)
-      TB_CUDA(c, tb_launch_gather_fp4(c->geno(), c->d_idx, d_off, w0, Wc, rpad, kstride_b, d_panel, st));
+      TB_CUDA(c, tb_launch_gather_fp4(c->geno(), c->d_idx, d_off, w0, Wc, rpad, kstride_b, d_panel, st,
+                                      use_perm ? sv[0].rs->d_rowmap : nullptr, use_perm ? sv[0].rs->rows_univ : 0));
     else
       TB_CUDA(c, tb_launch_gather(c->geno(), c->d_idx, d_off, w0, Wc, rpad, kstride, d_panel, st));
     span_end(c, sp);
@@ -444,8 +457,8 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
       // contiguous kernels: every row set is a prefix of the universe, or (int16 layout) a prefix with one aligned hole
       bool contig = true, hole = false;
       for (int s = 0; s < n_slots; ++s) {
-        contig = contig && ((sv[s].rs->contiguous && sv[s].rs->n_t % 4 == 0) || (c16 && sv[s].rs->seg_ok));
-        hole = hole || sv[s].rs->gap > 0;
+        contig = contig && (((sv[s].rs->contiguous || use_perm) && sv[s].rs->n_t % 4 == 0) || (c16 && sv[s].rs->seg_ok));
+        hole = hole || (!use_perm && sv[s].rs->gap > 0);
       }
       TB_CUDA(c, tb_launch_solve_mixed(d_msolve, n_jobs, max_ntp, contig ? 1 : 0, c16 ? 1 : 0, hole ? 1 : 0, st));
       span_end(c, sp);
@@ -805,6 +818,25 @@ int tb_set_rowset(tb_ctx* c, int slot, const int32_t* train, int n_t, const int3
       r.gap = 0;
     }
   }
+  std::vector<int> rowmap, ident;
+  r.rows_univ = maxpos + 1;
+  r.perm_ok = false;
+  if (!r.contiguous) {
+    // panel-row permutation: training animals first, validation animals next, nobody else
+    rowmap.assign(maxpos + 1, -1);
+    bool ok = n_t % 4 == 0;
+    for (int i = 0; i < n_t && ok; ++i) {
+      ok = rowmap[tpos[i]] < 0;
+      rowmap[tpos[i]] = i;
+    }
+    for (int i = 0; i < n_v && ok; ++i) {
+      ok = rowmap[vpos[i]] < 0;
+      rowmap[vpos[i]] = n_t + i;
+    }
+    r.perm_ok = ok;
+    ident.resize(n_t + n_v);
+    for (int i = 0; i < n_t + n_v; ++i) ident[i] = i;
+  }
   std::vector<double> yt(r.ntp, 0.0), ytc(r.ntp, 0.0), yv(n_v);
   double mean = 0.0;
   for (int i = 0; i < n_t; ++i) {
@@ -820,6 +852,12 @@ int tb_set_rowset(tb_ctx* c, int slot, const int32_t* train, int n_t, const int3
   TB_CUDA(c, cudaMalloc(&r.d_yt_raw, r.ntp * sizeof(double)));
   TB_CUDA(c, cudaMalloc(&r.d_yt_ctr, r.ntp * sizeof(double)));
   TB_CUDA(c, cudaMalloc(&r.d_yv, n_v * sizeof(double)));
+  if (r.perm_ok) {
+    TB_CUDA(c, cudaMalloc(&r.d_rowmap, rowmap.size() * sizeof(int)));
+    TB_CUDA(c, cudaMalloc(&r.d_ident, ident.size() * sizeof(int)));
+    TB_CUDA(c, cudaMemcpyAsync(r.d_rowmap, rowmap.data(), rowmap.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+    TB_CUDA(c, cudaMemcpyAsync(r.d_ident, ident.data(), ident.size() * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  }
   TB_CUDA(c, cudaMemcpyAsync(r.d_tpos, tpos.data(), n_t * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   TB_CUDA(c, cudaMemcpyAsync(r.d_vpos, vpos.data(), n_v * sizeof(int), cudaMemcpyHostToDevice, c->stream));
   TB_CUDA(c, cudaMemcpyAsync(r.d_yt_raw, yt.data(), r.ntp * sizeof(double), cudaMemcpyHostToDevice, c->stream));
@@ -1069,6 +1107,7 @@ int tb_set_option(tb_ctx* c, const char* name, long long value) {
   else if (s == "wide_panel") c->wide_panel = value != 0;
   else if (s == "narrow_c") c->narrow_c = value != 0;
   else if (s == "gram_fp4") c->gram_fp4 = value != 0;
+  else if (s == "perm_rows") c->perm_rows = value != 0;
   else if (s == "storage") return fail(c, "tb_set_option: storage is fixed at tb_create_ex");
   else return fail(c, "tb_set_option: unknown option '" + s + "'");
   return 0;
@@ -1085,6 +1124,7 @@ int tb_get_info(const tb_ctx* c, const char* name, long long* value) {
   else if (s == "wide_panel") *value = c->wide_panel;
   else if (s == "de_removed") *value = c->de.n_banned;
   else if (s == "last_fp4") *value = c->last_fp4;
+  else if (s == "last_perm") *value = c->last_perm;
   else if (s == "last_fallbacks") *value = c->last_fallbacks;
   else if (s == "last_issue_us") *value = c->last_issue_us;
   else if (s == "staged") *value = c->P;

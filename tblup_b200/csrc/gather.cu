@@ -128,7 +128,8 @@ __global__ void __launch_bounds__(256) gather_packed_kernel(const uint8_t* __res
 template <int MPL>
 __global__ void __launch_bounds__(256) gather_fp4_kernel(const uint8_t* __restrict__ x2, int ld4,
                                                          const int* __restrict__ idx, const long long* __restrict__ off,
-                                                         int w0, int rpad, int kstride_b, int8_t* __restrict__ panel) {
+                                                         int w0, int rpad, int kstride_b, int8_t* __restrict__ panel,
+                                                         const int* __restrict__ rowmap, int rows_univ) {
   constexpr int TM = 32 * MPL;
   extern __shared__ uint32_t ptile[];            // [TM][32]
   const int w = blockIdx.z;
@@ -158,21 +159,26 @@ __global__ void __launch_bounds__(256) gather_fp4_kernel(const uint8_t* __restri
   const int jl0 = lane * MPL;
   if (j0 + jl0 >= kpad) return;                  // kpad is a multiple of 256 >= MPL: whole lanes
   for (int c = warp; c < 32; c += 8) {
-    if (a0 + 16 * c >= rpad) break;
+    if (a0 + 16 * c >= (rowmap ? rows_univ : rpad)) break;
     uint32_t wv[MPL];
 #pragma unroll
     for (int t = 0; t < MPL; ++t) wv[t] = ptile[(jl0 + t) * 32 + ((c + lane) & 31)];
-    int8_t* dst = panel + ((size_t)w * rpad + a0 + 16 * c) * kstride_b + ((j0 + jl0) >> 1);
+    int8_t* dst0 = panel + (size_t)w * rpad * kstride_b + ((j0 + jl0) >> 1);
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
+      // panel row of this animal: its universe position, or wherever the row set's permutation sends it
+      int prow = a0 + 16 * c + i;
+      if (rowmap) prow = prow < rows_univ ? rowmap[prow] : -1;
+      if (prow < 0) continue;
+      int8_t* dst = dst0 + (size_t)prow * kstride_b;
       uint32_t lo = 0, hi = 0;
 #pragma unroll
       for (int t = 0; t < 8; ++t) {                // (bfe/bfi inline PTX was tried here: slower than shift + LOP3)
         lo |= ((wv[t] >> (2 * i)) & 3u) << (4 * t + 1);
         if (MPL == 16) hi |= ((wv[(t + 8) % MPL] >> (2 * i)) & 3u) << (4 * t + 1);
       }
-      if (MPL == 16) *reinterpret_cast<uint2*>(dst + (size_t)i * kstride_b) = make_uint2(lo, hi);
-      else *reinterpret_cast<uint32_t*>(dst + (size_t)i * kstride_b) = lo;
+      if (MPL == 16) *reinterpret_cast<uint2*>(dst) = make_uint2(lo, hi);
+      else *reinterpret_cast<uint32_t*>(dst) = lo;
     }
   }
 }
@@ -349,11 +355,12 @@ __global__ void __launch_bounds__(256) centre_rows_fp4_dp4a_kernel(const int8_t*
 cudaError_t tb_gather_init() { return cudaSuccess; }
 
 cudaError_t tb_launch_gather_fp4(const TbGeno& g, const int* d_idx, const long long* d_off, int w0, int W, int rpad,
-                                 int kstride_b, int8_t* d_panel, cudaStream_t st) {
+                                 int kstride_b, int8_t* d_panel, cudaStream_t st, const int* d_rowmap, int rows_univ) {
   if (!g.x2) return cudaErrorInvalidValue;       // written for the packed matrix
   // 256-marker tiles (32 KiB, more blocks in flight) measured 3.5 ms against 4.3 ms for 512-marker tiles (64 KiB)
-  dim3 grid((2 * kstride_b + 255) / 256, (rpad + 511) / 512, W);
-  gather_fp4_kernel<8><<<grid, 256, 256 * 128, st>>>(g.x2, g.ld4, d_idx, d_off, w0, rpad, kstride_b, d_panel);
+  dim3 grid((2 * kstride_b + 255) / 256, ((d_rowmap ? rows_univ : rpad) + 511) / 512, W);
+  gather_fp4_kernel<8><<<grid, 256, 256 * 128, st>>>(g.x2, g.ld4, d_idx, d_off, w0, rpad, kstride_b, d_panel, d_rowmap,
+                                                     rows_univ);
   return cudaGetLastError();
 }
 

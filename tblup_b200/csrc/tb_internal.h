@@ -49,6 +49,13 @@ struct TbRowSet {
   bool seg_ok = false;
   int hole0 = 0, gap = 0;
   bool valid_in_hole = false;
+  // any OTHER row set can still be made a prefix by permuting the panel rows at gather time (training animals first,
+  // then the validation animals; everyone else is dropped): d_rowmap[universe position] = panel row or -1,
+  // d_ident = 0, 1, 2, ... (the position lists in panel order).  Needs disjoint, duplicate-free index lists.
+  bool perm_ok = false;
+  int* d_rowmap = nullptr;
+  int* d_ident = nullptr;
+  int rows_univ = 0;            // universe rows the gather has to visit (1 + max position used)
 };
 
 // resident genotypes as the kernels see them: exactly one of x (int8 dosages, [m][ldn]) and x2 (2-bit packed,
@@ -98,6 +105,8 @@ struct TbCtx {
   int max_wave = 0;
   int precision = 0;              // 0: mixed (TF32 tensor-core Cholesky + fp64 refinement) when possible, 1: fp64
   int last_mixed = 0;
+  int perm_rows = 1;              // 1: a single scattered row set becomes a prefix through a row permutation at gather time
+  int last_perm = 0;
   int gram_fp4 = 1;               // 1: E2M1 Gram (kind::mxf4) when the genotypes are resident in packed form
   int last_fp4 = 0;
   int narrow_c = 1;               // 1: int16 cross-products when every genome of the batch has 4 k <= 32 767
@@ -168,8 +177,10 @@ cudaError_t tb_launch_unpack2_perm(const uint8_t* d_rows2, int n_rows, int strid
 cudaError_t tb_launch_gather(const TbGeno& g, const int* d_idx, const long long* d_off, int w0, int W,
                              int rpad, int kstride, int8_t* d_panel, cudaStream_t st);
 // fp4 panel: E2M1 nibbles, two markers per byte, kstride_b bytes per animal row (= padded k / 2), from packed genotypes
+// d_rowmap (nullable): panel row of every universe position (-1 = not gathered), rows_univ = positions to visit
 cudaError_t tb_launch_gather_fp4(const TbGeno& g, const int* d_idx, const long long* d_off, int w0, int W, int rpad,
-                                 int kstride_b, int8_t* d_panel, cudaStream_t st);
+                                 int kstride_b, int8_t* d_panel, cudaStream_t st, const int* d_rowmap = nullptr,
+                                 int rows_univ = 0);
 cudaError_t tb_gather_init();
 cudaError_t tb_launch_centre_terms(const int8_t* d_panel, int rpad, int kstride, const int* d_idx,
                                    const long long* d_off, int w0, int W, int n_slots, const int* d_kblocks,

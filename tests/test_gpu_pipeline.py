@@ -396,3 +396,43 @@ def test_heritability_extremes_fall_back_to_fp64(h2):
             assert total_fallbacks > 0
     finally:
         eng.close()
+
+
+def test_scattered_row_set_runs_as_a_prefix_after_row_permutation():
+    """A Monte-Carlo style split (evaluator.py:555-561: random 80/20 of training + validation) has scattered universe
+    positions.  The gather permutes the panel rows (training first, validation next), after which the contiguous
+    kernels -- fused scaling included -- apply.  Same fitness as the position-lookup kernels and as the oracle."""
+    from tblup_b200 import engine as E
+    g = load_golden("fit_mid")
+    x, y, h2 = g["x"], g["y"], float(g["h2"])
+    tr, va, te = g["train"], g["valid"], g["test"]
+    rng = np.random.default_rng(77)
+    pool = rng.permutation(np.concatenate([tr, va]))
+    mc_train, mc_valid = pool[:256], pool[256:]                 # 256 / 64, scattered over the universe prefix
+    eng, perm = _engine(x, y, tr, va, te, extra_sets=[(mc_train, mc_valid)])
+    try:
+        m = x.shape[1]
+        genomes = [rng.choice(m, size=k, replace=False) for k in (17, 320, 401, 1500)] + [rng.integers(0, m, size=600)]
+        for mode, omode in ((E.MODE_GBLUP, O.MODE_GBLUP), (E.MODE_SNPBLUP, O.MODE_SNPBLUP)):
+            eng.set_option("perm_rows", 1)
+            a = eng.evaluate(genomes, slots=[1], h2=h2, mode=mode)[:, 0]
+            assert eng.info("last_perm") == 1 and eng.info("last_fused_scale") == 1
+            eng.set_option("perm_rows", 0)
+            b = eng.evaluate(genomes, slots=[1], h2=h2, mode=mode)[:, 0]
+            assert eng.info("last_perm") == 0
+            eng.set_option("perm_rows", 1)
+            want = np.array([O.exact_fitness(gen, mc_train, mc_valid, x, y, h2, omode) for gen in genomes])
+            assert np.abs(a - want).max() < 1e-7 and np.abs(b - want).max() < 1e-7
+        # the contiguous base split is untouched, and several row sets in one call keep the shared-Gram path
+        base = eng.evaluate(genomes, slots=[0], h2=h2, mode=E.MODE_GBLUP)
+        assert eng.info("last_perm") == 0
+        both = eng.evaluate(genomes, slots=[0, 1], h2=h2, mode=E.MODE_GBLUP)
+        assert eng.info("last_perm") == 0 and np.abs(both[:, 0] - base[:, 0]).max() < 1e-12
+        # fp64 precision goes through the same permuted panel
+        eng.set_precision("fp64")
+        c = eng.evaluate(genomes, slots=[1], h2=h2, mode=E.MODE_GBLUP)[:, 0]
+        assert eng.info("last_perm") == 1
+        want = np.array([O.exact_fitness(gen, mc_train, mc_valid, x, y, h2, O.MODE_GBLUP) for gen in genomes])
+        assert np.abs(c - want).max() < 1e-9
+    finally:
+        eng.close()
