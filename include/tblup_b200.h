@@ -118,7 +118,7 @@ int tb_debug_fetch(tb_ctx* ctx, int what, int job, void* out, size_t nbytes);
 int tb_set_option(tb_ctx* ctx, const char* name, long long value);
 
 /* Facts about the last evaluation / the context: "last_c16", "last_fused_scale", "last_mixed", "last_wave",
- * "storage", "wide_panel", "de_removed" (size of the removed-marker set), "staged" (genomes staged), "last_fp4", "last_perm",
+ * "storage", "wide_panel", "de_removed" (size of the removed-marker set), "staged" (genomes staged), "last_fp4", "last_perm", "last_split",
  * "last_fallbacks" (jobs of the last evaluation whose mixed-precision solve gave up -- pivot breakdown or no
  * convergence, h2 close to 1 -- and that were evaluated again with the fp64 Cholesky). */
 int tb_get_info(const tb_ctx* ctx, const char* name, long long* value);

@@ -107,6 +107,9 @@ struct TbCtx {
   int last_mixed = 0;
   int perm_rows = 1;              // 1: a single scattered row set becomes a prefix through a row permutation at gather time
   int last_perm = 0;
+  int last_split = 0;             // the last multi-row-set evaluation ran one row set at a time (see eval_core)
+  double* d_split = nullptr;      // [P] fitness of one row set while splitting
+  size_t split_cap = 0;
   int gram_fp4 = 1;               // 1: E2M1 Gram (kind::mxf4) when the genotypes are resident in packed form
   int last_fp4 = 0;
   int narrow_c = 1;               // 1: int16 cross-products when every genome of the batch has 4 k <= 32 767

@@ -354,9 +354,14 @@ def test_cross_validation_folds_with_aligned_holes():
         for mode, omode in ((E.MODE_GBLUP, O.MODE_GBLUP), (E.MODE_SNPBLUP, O.MODE_SNPBLUP)):
             eng.set_option("narrow_c", 1)
             got = eng.evaluate(genomes, slots=slots, h2=0.4, mode=mode)
-            assert eng.info("last_c16") == 1
+            assert eng.info("last_c16") == 1 and eng.info("last_split") == 0      # one Gram per genome, hole kernels
             eng.set_option("narrow_c", 0)
             generic = eng.evaluate(genomes, slots=slots, h2=0.4, mode=mode)
+            assert eng.info("last_split") == 1       # int32 layout has no hole kernels: one permuted panel per fold
+            eng.set_option("perm_rows", 0)
+            lookup = eng.evaluate(genomes, slots=slots, h2=0.4, mode=mode)            # position-lookup kernels
+            assert eng.info("last_split") == 0 and np.abs(lookup - generic).max() < 1e-9
+            eng.set_option("perm_rows", 1)
             eng.set_option("narrow_c", 1)
             want = np.array([[O.exact_fitness(g, f[0], f[1], x, y, 0.4, omode) for f in folds] for g in genomes])
             assert np.abs(got - want).max() < 1e-7
@@ -423,11 +428,14 @@ def test_scattered_row_set_runs_as_a_prefix_after_row_permutation():
             eng.set_option("perm_rows", 1)
             want = np.array([O.exact_fitness(gen, mc_train, mc_valid, x, y, h2, omode) for gen in genomes])
             assert np.abs(a - want).max() < 1e-7 and np.abs(b - want).max() < 1e-7
-        # the contiguous base split is untouched, and several row sets in one call keep the shared-Gram path
+        # the contiguous base split is untouched; together with the scattered set the call is evaluated one row set at
+        # a time (a second Gram is far cheaper than position lookups in the refinement)
         base = eng.evaluate(genomes, slots=[0], h2=h2, mode=E.MODE_GBLUP)
         assert eng.info("last_perm") == 0
         both = eng.evaluate(genomes, slots=[0, 1], h2=h2, mode=E.MODE_GBLUP)
-        assert eng.info("last_perm") == 0 and np.abs(both[:, 0] - base[:, 0]).max() < 1e-12
+        assert eng.info("last_split") == 1 and np.abs(both[:, 0] - base[:, 0]).max() < 1e-12
+        assert np.abs(both[:, 1] - np.array([O.exact_fitness(gen, mc_train, mc_valid, x, y, h2, O.MODE_GBLUP)
+                                             for gen in genomes])).max() < 1e-7
         # fp64 precision goes through the same permuted panel
         eng.set_precision("fp64")
         c = eng.evaluate(genomes, slots=[1], h2=h2, mode=E.MODE_GBLUP)[:, 0]
