@@ -41,24 +41,27 @@ def as_dosage_int8(geno):
 def pack_genomes(genomes, n_markers):
     """Ragged list of index arrays -> (flat int32, offsets int64) with numpy fancy-indexing semantics
     (tblup/evaluator.py:275, :298): negative indices wrap, out-of-range raises IndexError, duplicates stay."""
-    lens = np.fromiter((len(g) for g in genomes), dtype=np.int64, count=len(genomes))
-    off = np.zeros(len(genomes) + 1, dtype=np.int64)
-    np.cumsum(lens, out=off[1:])
-    flat = np.empty(int(off[-1]), dtype=np.int64)
-    for i, g in enumerate(genomes):
+    arrs = []
+    for g in genomes:
         a = np.asarray(g)
-        if a.dtype.kind not in "iu":
+        if a.dtype.kind not in "iu":                 # the reference hands float arrays after union1d / setdiff1d
             ai = a.astype(np.int64)
             if not np.array_equal(ai, a):
                 raise IndexError("arrays used as indices must be of integer type")
             a = ai
-        flat[off[i]:off[i + 1]] = a
+        arrs.append(a.ravel())
+    lens = np.fromiter((a.size for a in arrs), dtype=np.int64, count=len(arrs))
+    off = np.zeros(len(arrs) + 1, dtype=np.int64)
+    np.cumsum(lens, out=off[1:])
+    flat = np.concatenate(arrs) if arrs else np.empty(0, dtype=np.int64)
     if flat.size:
-        if flat.max() >= n_markers or flat.min() < -n_markers:
+        lo, hi = int(flat.min()), int(flat.max())
+        if hi >= n_markers or lo < -n_markers:
             bad = flat[(flat >= n_markers) | (flat < -n_markers)][0]
             raise IndexError("index %d is out of bounds for axis 1 with size %d" % (bad, n_markers))
-        flat = np.where(flat < 0, flat + n_markers, flat)
-    return np.ascontiguousarray(flat.astype(np.int32)), off
+        if lo < 0:
+            flat = np.where(flat < 0, flat + n_markers, flat)
+    return np.ascontiguousarray(flat, dtype=np.int32), off
 
 
 class GblupEngine:
