@@ -159,6 +159,18 @@ int tb_de_evaluate(tb_ctx* ctx, const int32_t* slots, int n_slots, double h2, in
 int tb_de_step(tb_ctx* ctx, const int32_t* slots, int n_slots, double h2, int mode_rule, double F, double CR, int clip,
                const int32_t* abc, const int32_t* fixed, const uint8_t* mask, uint64_t seed, int32_t* take_out);
 int tb_de_get(tb_ctx* ctx, int what, int which, void* out, size_t nbytes);
+/* The same generation split in two, for a population whose keys are replicated on every GPU of a box and whose
+ * EVALUATION is sharded: tb_de_step_begin evolves the whole offspring population (same draws on every
+ * rank, so no key ever crosses NVLink) and scores the offspring [first, first + count); the caller all-gathers the
+ * offspring fitness in place (tb_de_device_ptr(ctx, 1) is the [P] device vector, e.g. ncclAllGather /
+ * torch.distributed.all_gather_into_tensor); tb_de_step_end applies the greedy selection to all P individuals.
+ * tb_de_evaluate_shard is the generation-0 counterpart (fills fit[first, first + count), tb_de_device_ptr(ctx, 0)). */
+int tb_de_step_begin(tb_ctx* ctx, const int32_t* slots, int n_slots, double h2, int mode_rule, double F, double CR,
+                     int clip, const int32_t* abc, const int32_t* fixed, const uint8_t* mask, uint64_t seed, int first,
+                     int count);
+int tb_de_step_end(tb_ctx* ctx, int32_t* take_out);
+int tb_de_evaluate_shard(tb_ctx* ctx, const int32_t* slots, int n_slots, double h2, int mode_rule, int first, int count);
+void* tb_de_device_ptr(tb_ctx* ctx, int what);
 /* SNP removal on the device (tblup/evaluator.py:569-633, SNPRemovalHandler).  The removed set lives next to the keys:
  * once it is non-empty, tb_de_evaluate / tb_de_step score every individual on setdiff1d(genome, removed)
  * (evaluator.py:617; an individual left with no marker gets fitness 0.0, :618-620) and tb_de_evaluate_testing scores

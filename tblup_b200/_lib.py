@@ -40,6 +40,11 @@ SYMBOLS = {
     "tb_de_evaluate": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int]),
     "tb_de_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int,
                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "tb_de_step_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_double, C.c_int,
+                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_int]),
+    "tb_de_step_end": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "tb_de_evaluate_shard": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int]),
+    "tb_de_device_ptr": (C.c_void_p, [C.c_void_p, C.c_int]),
     "tb_de_get": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t]),
     "tb_de_set_removed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "tb_de_ban_genome": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),

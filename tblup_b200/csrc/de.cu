@@ -353,19 +353,20 @@ int de_ensure_rows(TbCtx* c, int stride) {
 // rows [P][stride] with lens on the device -> the context's staged ragged batch (c->d_idx, c->h_off, c->P).
 // Only the P lengths visit the host (the offsets the wave scheduler plans with); an empty list is staged as one
 // arbitrary marker and its fitness overwritten afterwards (h_lens tells which).
-int de_stage_rows(TbCtx* c, int stride, std::vector<int>& h_lens) {
+int de_stage_rows(TbCtx* c, int stride, std::vector<int>& h_lens, int count = -1) {
   auto& d = c->de;
-  h_lens.resize(d.P);
-  TB_CUDA(c, cudaMemcpyAsync(h_lens.data(), d.lens, (size_t)d.P * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  if (count < 0) count = d.P;
+  h_lens.resize(count);
+  TB_CUDA(c, cudaMemcpyAsync(h_lens.data(), d.lens, (size_t)count * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
   TB_CUDA(c, cudaStreamSynchronize(c->stream));
-  c->h_off.resize(d.P + 1);
+  c->h_off.resize(count + 1);
   c->h_off[0] = 0;
-  for (int i = 0; i < d.P; ++i) c->h_off[i + 1] = c->h_off[i] + std::max(h_lens[i], 1);
-  c->P = d.P;
-  if (int rc = de_ensure_idx(c, (size_t)c->h_off[d.P])) return rc;
-  TB_CUDA(c, cudaMemcpyAsync(d.d_off, c->h_off.data(), (size_t)(d.P + 1) * sizeof(long long), cudaMemcpyHostToDevice,
+  for (int i = 0; i < count; ++i) c->h_off[i + 1] = c->h_off[i] + std::max(h_lens[i], 1);
+  c->P = count;
+  if (int rc = de_ensure_idx(c, (size_t)c->h_off[count])) return rc;
+  TB_CUDA(c, cudaMemcpyAsync(d.d_off, c->h_off.data(), (size_t)(count + 1) * sizeof(long long), cudaMemcpyHostToDevice,
                              c->stream));
-  dim3 grid((unsigned)std::min(64, (stride + 255) / 256), d.P);
+  dim3 grid((unsigned)std::min(64, (stride + 255) / 256), count);
   de_pack_rows_kernel<<<grid, 256, 0, c->stream>>>(d.rows, stride, d.d_off, c->d_idx);
   TB_CUDA(c, cudaGetLastError());
   c->launches += 1;
@@ -386,35 +387,42 @@ int de_ensure_raw(TbCtx* c, int n_slots) {
 
 // decode `src` keys into the context's staged-genome buffer (minus the banned markers, if any) and evaluate them;
 // result (mean over slots) -> dst
+// [first, first + count) of the individuals whose keys are in `src` (P x m): decode, drop banned markers, evaluate;
+// the mean over the row sets goes to dst[first ...].  count = P scores everybody; a smaller range is one rank's shard
+// of a population whose keys are replicated on every GPU.
 int de_decode_and_eval(TbCtx* c, const double* src, const int32_t* slots, int n_slots, double h2, int mode,
-                       double* dst) {
+                       double* dst, int first = 0, int count = -1) {
   auto& d = c->de;
+  if (count < 0) count = d.P - first;
+  if (count <= 0) return 0;
+  src += (size_t)first * c->m;
+  dst += first;
   std::vector<int> h_lens;
   if (d.n_banned == 0) {
-    if (int rc = de_ensure_idx(c, (size_t)d.P * d.k)) return rc;
-    de_decode_kernel<<<d.P, 1024, 0, c->stream>>>(src, c->m, d.k, c->d_idx, d.k);
+    if (int rc = de_ensure_idx(c, (size_t)count * d.k)) return rc;
+    de_decode_kernel<<<count, 1024, 0, c->stream>>>(src, c->m, d.k, c->d_idx, d.k);
     TB_CUDA(c, cudaGetLastError());
     c->launches += 1;
-    c->h_off.resize(d.P + 1);
-    for (int i = 0; i <= d.P; ++i) c->h_off[i] = (long long)i * d.k;
-    c->P = d.P;
+    c->h_off.resize(count + 1);
+    for (int i = 0; i <= count; ++i) c->h_off[i] = (long long)i * d.k;
+    c->P = count;
   } else {
     if (int rc = de_ensure_rows(c, d.k)) return rc;
-    de_decode_kernel<<<d.P, 1024, 0, c->stream>>>(src, c->m, d.k, d.rows, d.k);
+    de_decode_kernel<<<count, 1024, 0, c->stream>>>(src, c->m, d.k, d.rows, d.k);
     TB_CUDA(c, cudaGetLastError());
-    de_filter_banned_kernel<<<d.P, 1024, 0, c->stream>>>(d.rows, d.k, d.k, d.banned, d.lens);
+    de_filter_banned_kernel<<<count, 1024, 0, c->stream>>>(d.rows, d.k, d.k, d.banned, d.lens);
     TB_CUDA(c, cudaGetLastError());
     c->launches += 2;
-    if (int rc = de_stage_rows(c, d.k, h_lens)) return rc;
+    if (int rc = de_stage_rows(c, d.k, h_lens, count)) return rc;
   }
   if (int rc = de_ensure_raw(c, n_slots)) return rc;
   int rc = tb_internal_eval_device(c, slots, n_slots, h2, mode, d.raw_fit);
   if (rc) return rc;
-  de_mean_kernel<<<(d.P + 255) / 256, 256, 0, c->stream>>>(d.raw_fit, n_slots, d.P, dst);
+  de_mean_kernel<<<(count + 255) / 256, 256, 0, c->stream>>>(d.raw_fit, n_slots, count, dst);
   TB_CUDA(c, cudaGetLastError());
   c->launches += 1;
   if (d.n_banned) {
-    de_zero_empty_kernel<<<(d.P + 255) / 256, 256, 0, c->stream>>>(dst, d.lens, d.P);
+    de_zero_empty_kernel<<<(count + 255) / 256, 256, 0, c->stream>>>(dst, d.lens, count);
     TB_CUDA(c, cudaGetLastError());
     c->launches += 1;
   }
@@ -492,12 +500,14 @@ int tb_de_evaluate(tb_ctx* c, const int32_t* slots, int n_slots, double h2, int 
   return 0;
 }
 
-int tb_de_step(tb_ctx* c, const int32_t* slots, int n_slots, double h2, int mode_rule, double F, double CR, int clip,
-               const int32_t* abc, const int32_t* fixed, const uint8_t* mask, uint64_t seed, int32_t* take_out) {
+int tb_de_step_begin(tb_ctx* c, const int32_t* slots, int n_slots, double h2, int mode_rule, double F, double CR,
+                     int clip, const int32_t* abc, const int32_t* fixed, const uint8_t* mask, uint64_t seed, int first,
+                     int count) {
   if (!c) return -1;
   auto& d = c->de;
   if (!d.keys) return de_fail(c, "tb_de_step: call tb_de_init and tb_de_evaluate first");
   if ((abc == nullptr) != (fixed == nullptr)) return de_fail(c, "tb_de_step: pass both abc and fixed, or neither");
+  if (first < 0 || count < 0 || first + count > d.P) return de_fail(c, "tb_de_step_begin: shard out of range");
   TB_CUDA(c, cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
   const int P = d.P, m = c->m;
@@ -520,26 +530,69 @@ int tb_de_step(tb_ctx* c, const int32_t* slots, int n_slots, double h2, int mode
     TB_CUDA(c, cudaMemcpyAsync(d.mask, mask, (size_t)P * m, cudaMemcpyHostToDevice, st));
     d_mask = d.mask;
   }
+  // every rank evolves the WHOLE offspring population from the replicated parents (same draws, same keys: cheap,
+  // and no key ever crosses NVLink); only the evaluation is sharded
   dim3 grid((m + 255) / 256, P);
   de_evolve_kernel<<<grid, 256, 0, st>>>(d.keys, d.child, d.abc, d.fixed, d_mask, m, F, CR, clip, seed);
   TB_CUDA(c, cudaGetLastError());
   c->launches += 1;
-  int rc = de_decode_and_eval(c, d.child, slots, n_slots, h2, mode_rule, d.child_fit);
-  if (rc == 0) {
-    de_select_kernel<<<grid, 256, 0, st>>>(d.keys, d.child, d.fit, d.child_fit, m, d.take);
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess) {
-      de_commit_fitness_kernel<<<(P + 255) / 256, 256, 0, st>>>(d.fit, d.child_fit, d.take, P);
-      e = cudaGetLastError();
-    }
-    c->launches += 2;
-    if (e != cudaSuccess) rc = de_fail(c, std::string("selection launch: ") + cudaGetErrorString(e), -2);
-    if (rc == 0 && take_out) {
-      e = cudaMemcpyAsync(take_out, d.take, P * sizeof(int), cudaMemcpyDeviceToHost, st);
-      if (e != cudaSuccess) rc = de_fail(c, std::string("D2H take: ") + cudaGetErrorString(e), -2);
-    }
+  int rc = de_decode_and_eval(c, d.child, slots, n_slots, h2, mode_rule, d.child_fit, first, count);
+  cudaError_t se = cudaStreamSynchronize(st);
+  tb_internal_collect_spans(c);
+  if (rc) return rc;
+  if (se != cudaSuccess) return de_fail(c, std::string("device execution failed: ") + cudaGetErrorString(se), -2);
+  return 0;
+}
+
+int tb_de_step_end(tb_ctx* c, int32_t* take_out) {
+  if (!c) return -1;
+  auto& d = c->de;
+  if (!d.keys) return de_fail(c, "tb_de_step_end: no DE state");
+  TB_CUDA(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const int P = d.P, m = c->m;
+  int rc = 0;
+  dim3 grid((m + 255) / 256, P);
+  de_select_kernel<<<grid, 256, 0, st>>>(d.keys, d.child, d.fit, d.child_fit, m, d.take);
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) {
+    de_commit_fitness_kernel<<<(P + 255) / 256, 256, 0, st>>>(d.fit, d.child_fit, d.take, P);
+    e = cudaGetLastError();
+  }
+  c->launches += 2;
+  if (e != cudaSuccess) rc = de_fail(c, std::string("selection launch: ") + cudaGetErrorString(e), -2);
+  if (rc == 0 && take_out) {
+    e = cudaMemcpyAsync(take_out, d.take, P * sizeof(int), cudaMemcpyDeviceToHost, st);
+    if (e != cudaSuccess) rc = de_fail(c, std::string("D2H take: ") + cudaGetErrorString(e), -2);
   }
   cudaError_t se = cudaStreamSynchronize(st);
+  if (rc) return rc;
+  if (se != cudaSuccess) return de_fail(c, std::string("device execution failed: ") + cudaGetErrorString(se), -2);
+  return 0;
+}
+
+int tb_de_step(tb_ctx* c, const int32_t* slots, int n_slots, double h2, int mode_rule, double F, double CR, int clip,
+               const int32_t* abc, const int32_t* fixed, const uint8_t* mask, uint64_t seed, int32_t* take_out) {
+  if (!c) return -1;
+  int rc = tb_de_step_begin(c, slots, n_slots, h2, mode_rule, F, CR, clip, abc, fixed, mask, seed, 0, c->de.P);
+  if (rc) return rc;
+  return tb_de_step_end(c, take_out);
+}
+
+// Device pointers of the population / offspring fitness vectors [P] (what = 0 / 1), for collectives issued by the
+// caller between tb_de_step_begin and tb_de_step_end (all-gather of the shards' offspring fitness).
+void* tb_de_device_ptr(tb_ctx* c, int what) {
+  if (!c || !c->de.keys) return nullptr;
+  return what == 0 ? (void*)c->de.fit : what == 1 ? (void*)c->de.child_fit : nullptr;
+}
+
+int tb_de_evaluate_shard(tb_ctx* c, const int32_t* slots, int n_slots, double h2, int mode_rule, int first, int count) {
+  if (!c) return -1;
+  if (!c->de.keys) return de_fail(c, "tb_de_evaluate_shard: call tb_de_init first");
+  if (first < 0 || count < 0 || first + count > c->de.P) return de_fail(c, "tb_de_evaluate_shard: shard out of range");
+  TB_CUDA(c, cudaSetDevice(c->device));
+  int rc = de_decode_and_eval(c, c->de.keys, slots, n_slots, h2, mode_rule, c->de.fit, first, count);
+  cudaError_t se = cudaStreamSynchronize(c->stream);
   tb_internal_collect_spans(c);
   if (rc) return rc;
   if (se != cudaSuccess) return de_fail(c, std::string("device execution failed: ") + cudaGetErrorString(se), -2);

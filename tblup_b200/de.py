@@ -56,6 +56,55 @@ class DeviceDE:
         self.generation += 1
         return take.astype(bool)
 
+    # ---- population replicated on every GPU of the box, evaluation sharded over the ranks ---------------
+    class _DeviceVector:
+        """Zero-copy view of a device vector of the library for torch (CUDA array interface)."""
+
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (int(ptr), False), "version": 2}
+
+    def _shard(self, group=None):
+        import torch.distributed as dist
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        return self.P * rank // world, self.P * (rank + 1) // world
+
+    def _share(self, what, lo, hi, group=None):
+        """Every rank filled [lo, hi) of the fitness vector `what`; afterwards every rank holds all of it.  A sum of
+        vectors that are zero outside the own shard: P doubles over NCCL, exact (x + 0 = x, NaN stays NaN), and shards
+        may differ in size."""
+        import torch
+        import torch.distributed as dist
+        ptr = self.eng._lib.tb_de_device_ptr(self.eng._ctx, int(what))
+        v = torch.as_tensor(self._DeviceVector(ptr, self.P), device=torch.device("cuda", self.eng.device))
+        v[:lo] = 0.0
+        v[hi:] = 0.0
+        dist.all_reduce(v, group=group)
+        torch.cuda.synchronize(self.eng.device)
+
+    def evaluate_distributed(self, slots=(0,), h2=0.4, mode=MODE_AUTO, group=None):
+        """Generation 0 with the evaluation sharded over the ranks of ``group`` (keys must be identical on all ranks:
+        same host keys or same seed)."""
+        lo, hi = self._shard(group)
+        s = np.ascontiguousarray(np.asarray(slots, dtype=np.int32))
+        self.eng._check(self.eng._lib.tb_de_evaluate_shard(self.eng._ctx, s.ctypes.data, s.size, float(h2), int(mode),
+                                                           lo, hi - lo), "tb_de_evaluate_shard")
+        self._share(0, lo, hi, group)
+        return self.fitness()
+
+    def step_distributed(self, F, CR, slots=(0,), h2=0.4, mode=MODE_AUTO, clip=False, seed=0, group=None):
+        """One generation: every rank evolves all offspring (device draws from ``seed``: identical everywhere), scores
+        its shard, the offspring fitness is shared, every rank applies the same selection.  No key crosses NVLink."""
+        lo, hi = self._shard(group)
+        s = np.ascontiguousarray(np.asarray(slots, dtype=np.int32))
+        self.eng._check(self.eng._lib.tb_de_step_begin(self.eng._ctx, s.ctypes.data, s.size, float(h2), int(mode),
+                                                       float(F), float(CR), int(bool(clip)), None, None, None, int(seed),
+                                                       lo, hi - lo), "tb_de_step_begin")
+        self._share(1, lo, hi, group)
+        take = np.zeros(self.P, dtype=np.int32)
+        self.eng._check(self.eng._lib.tb_de_step_end(self.eng._ctx, take.ctypes.data), "tb_de_step_end")
+        self.generation += 1
+        return take.astype(bool)
+
     def run(self, generations, mutation=0.5, CR=0.8, slots=(0,), h2=0.4, mode=MODE_AUTO, clip=False, seed=0):
         """``generations`` device-driven generations with the reference's F schedule; returns best fitness per generation."""
         best = []

@@ -195,3 +195,22 @@ def test_maybe_remove_follows_the_handler_rule():
         assert de.fitness()[best] == 0.0
     finally:
         eng.close()
+
+
+def test_sharded_device_de_matches_single_gpu():
+    """Population replicated on every GPU, evaluation sharded over the ranks, one all-reduce of P doubles per generation:
+    scripts/de_multi_gpu.py asserts that every rank ends with the same population and that generation-0 fitness,
+    every selection and the final fitness equal the single-GPU run.  Needs two GPUs."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29531",
+                          os.path.join(root, "scripts", "de_multi_gpu.py"), "64", "3", "600", "4000", "700"],
+                         capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert "identical to the single-GPU run (generation-0 fitness, every selection, final fitness): True" in out.stdout
