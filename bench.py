@@ -337,6 +337,24 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
 
+    # parity gate run with every benchmark: 64 genomes of the timed batch through the default path and
+    # through the fp64 Cholesky path of the same library (two independent factorisations of the same exact integers)
+    parity = None
+    if rank == 0 and precision == "mixed":
+        n_par = min(64, P)
+        pf, po = batches[0]
+        sub_flat, sub_off = pf[:po[n_par]], po[:n_par + 1]
+        eng.stage(flat=sub_flat, off=sub_off)
+        f_mixed = eng.evaluate_staged(slots, h2=H2, mode=MODE_AUTO)
+        fallbacks = eng.info("last_fallbacks")
+        eng.set_precision("fp64")
+        f_fp64 = eng.evaluate_staged(slots, h2=H2, mode=MODE_AUTO)
+        eng.set_precision(args.precision)
+        parity = {"genomes": int(n_par), "folds": len(slots), "bar_abs": 1e-6,
+                  "max_abs_fitness_diff_default_vs_fp64_path": float(np.nanmax(np.abs(f_mixed - f_fp64))),
+                  "fp64_fallbacks_in_sample": int(fallbacks)}
+        eng.stage(flat=batches[0][0], off=batches[0][1])
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not wl.get("no_cpu"):
         sample = args.cpu_sample or cores
@@ -480,6 +498,7 @@ def main():
             "stage_ms_per_step": {s: v[0] / args.steps for s, v in stage.items()},
             "ms_per_step_instrumented": ms_instrumented / args.steps,
             "cpu_baseline": cpu_baseline,
+            "parity": parity,
         }
         print(json.dumps(line))
     eng.close()
