@@ -138,7 +138,9 @@ int tb_last_precision(const tb_ctx* ctx);
  * events bracket it); NULL restores the context's own stream. */
 int tb_set_stream(tb_ctx* ctx, void* cuda_stream);
 
-/* Peak probes for roofline denominators: which = 0 -> fp64 DMMA (mma.sync m8n8k4) TFLOP/s on this device. */
+/* Peak probes for roofline denominators (the Gram of tblup/utils.py:17 is reported against them): which = 0 -> fp64 DMMA
+ * (mma.sync m8n8k4) TFLOP/s; 1 -> tcgen05 kind::i8 TOP/s and 2 -> tcgen05 kind::mxf4 (E2M1) TOP/s, M128 x N256 MMAs
+ * issued back to back on shared-memory-resident operands, one CTA per SM (2 ops per multiply-accumulate). */
 int tb_microbench(tb_ctx* ctx, int which, double* out);
 
 /* ---- on-device differential evolution on random-key individuals (tblup/evolver.py:63-157 DE/rand/1 with binary

@@ -222,6 +222,42 @@ def exact_fitness(indices, train_indices, validation_indices, x_int, labels, h2,
     return fit
 
 
+def exact_fitness_rowsets(indices, rowsets, x_int, labels, h2, mode=None):
+    """``exact_fitness`` for several (train, valid) row sets of ONE genome, forming the integer Gram once over the
+    union of their rows (the k-fold evaluator recomputes the GRM per fold, tblup/evaluator.py:509-537; the values are
+    the same, this is only cheaper for the checker).  mode None = the reference's branch rule.  Returns one fitness
+    per row set."""
+    x_int = np.asarray(x_int)
+    labels = np.asarray(labels, dtype=np.float64).ravel()
+    if mode is None:
+        mode = ref_mode_for(len(indices), x_int.shape[0])
+    rows = np.unique(np.concatenate([np.concatenate([np.asarray(t), np.asarray(v)]) for t, v in rowsets]))
+    where = np.full(x_int.shape[0], -1, dtype=np.int64)
+    where[rows] = np.arange(rows.size)
+    c = exact_gram(x_int, indices, rows)
+    out = []
+    s_all = None
+    if mode == MODE_GBLUP:
+        s_all, S, Q, N = exact_centring_terms(x_int, indices, rows, np.arange(x_int.shape[0]))
+    lam = (1.0 - h2) / h2
+    for t, v in rowsets:
+        t, v = np.asarray(t), np.asarray(v)
+        if mode == MODE_GBLUP:
+            s = s_all
+        else:
+            s, S, Q, N = exact_centring_terms(x_int, indices, rows, t)
+        it, iv = where[t], where[v]
+        a = exact_grm_block(c[np.ix_(it, it)], s[it], s[it], S, Q, N)
+        g_vt = exact_grm_block(c[np.ix_(iv, it)], s[iv], s[it], S, Q, N)
+        a.flat[:: len(t) + 1] += lam
+        y_t = labels[t]
+        if mode == MODE_SNPBLUP:
+            y_t = y_t - y_t.mean()
+        alpha = cho_solve(cho_factor(a, lower=True), y_t)
+        out.append(pearson_abs(labels[v], g_vt @ alpha))
+    return out
+
+
 def exact_blup(indices, train_indices, validation_indices, x_int, labels, h2):
     """Exact pipeline with the reference's branch rule (tblup/evaluator.py:257)."""
     mode = ref_mode_for(len(indices), np.asarray(x_int).shape[0])

@@ -973,7 +973,6 @@ int tb_eval_staged(tb_ctx* c, const int32_t* slots, int n_slots, double h2, int 
     if (n_out > c->fit_cap) {                      // persistent device buffer for the host-output path
       TB_CUDA(c, cudaStreamSynchronize(c->stream));
       cudaFree(c->d_fit_out);
-  cudaFree(c->d_split);
       c->d_fit_out = nullptr;
       c->fit_cap = 0;
       TB_CUDA(c, cudaMalloc(&c->d_fit_out, std::max<size_t>(n_out, 1) * sizeof(double)));
@@ -1220,6 +1219,11 @@ int tb_microbench(tb_ctx* c, int which, double* out) {
   TB_CUDA(c, cudaSetDevice(c->device));
   if (which == 0) {
     TB_CUDA(c, tb_microbench_dmma(c->n_sm, c->stream, out));
+    c->launches += 4;
+    return 0;
+  }
+  if (which == 1 || which == 2) {
+    TB_CUDA(c, tb_microbench_umma(which, c->n_sm, c->stream, out));
     c->launches += 4;
     return 0;
   }

@@ -702,10 +702,15 @@ int tb_de_get(tb_ctx* c, int what, int which, void* out, size_t nbytes) {
       if (e != cudaSuccess || e2 != cudaSuccess) return de_fail(c, "tb_de_get: decode failed", -2);
       return 0;
     }
-    case 5: src = c->d_idx; need = (size_t)d.P * d.k * 4; break;                  // genomes of the last evaluated batch
+    case 5: {                                                                     // genomes of the last evaluated batch
+      // shard-local after tb_de_evaluate_shard / tb_de_step_begin: c->P genomes are staged, not d.P
+      if ((int)c->h_off.size() < c->P + 1 || c->P <= 0) return de_fail(c, "tb_de_get: no batch staged");
+      src = c->d_idx; need = (size_t)c->h_off[c->P] * 4; break;
+    }
     case 6: src = d.banned_list; need = (size_t)d.n_banned * 4; break;            // removed markers, ascending
-    case 7: src = d.lens; need = (size_t)d.P * 4; break;                          // list lengths of the last filtered batch
+    case 7: src = d.lens; need = (size_t)std::min(d.P, std::max(c->P, 0)) * 4; break;  // list lengths of the last filtered batch (staged genomes only)
     case 8: {                                                                     // flat lists of the last evaluated batch
+      if ((int)c->h_off.size() < c->P + 1 || c->P <= 0) return de_fail(c, "tb_de_get: no batch staged");
       src = c->d_idx; need = (size_t)c->h_off[c->P] * 4; break;
     }
     default: return de_fail(c, "tb_de_get: unknown item");

@@ -170,7 +170,8 @@ __global__ void __launch_bounds__(ST) solve_kernel(const TbSolveJob* __restrict_
       r = __longlong_as_double(0x7ff8000000000000LL);
     } else {
       r = sxy / (sqrt(sxx) * sqrt(syy));
-      r = fabs(fmax(fmin(r, 1.0), -1.0));
+      // fmin / fmax drop NaN operands: a non-finite r (syy = Inf) must not be clipped to 1
+      r = (fabs(r) < 1e300) ? fabs(fmax(fmin(r, 1.0), -1.0)) : __longlong_as_double(0x7ff8000000000000LL);
     }
     *jb.fitness = r;
   }

@@ -594,8 +594,9 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
       const double d = work[a];
       const double v = alpha[a] + d;
       alpha[a] = v;
-      dmax = fmax(dmax, fabs(d));
-      amax = fmax(amax, fabs(v));
+      // fmax drops NaN operands: map anything non-finite to +inf so that it cannot pass for "converged"
+      dmax = fmax(dmax, fabs(d) < 1e300 ? fabs(d) : __longlong_as_double(0x7ff0000000000000LL));
+      amax = fmax(amax, fabs(v) < 1e300 ? fabs(v) : __longlong_as_double(0x7ff0000000000000LL));
     }
     dmax = block_max(dmax, red);
     amax = block_max(amax, red);
@@ -604,7 +605,9 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
     // rho = dmax / prev_dmax the observed contraction (first sweep: assume rho <= 0.05, the TF32 factor
     // contracts by 1e-2 .. 1e-3 for cond(A) up to a few hundred)
     const double rho = sweeps == 1 ? 0.05 : fmin(1.0, dmax / prev_dmax);
-    const bool converged = !(dmax * rho > REL_TOL * amax);
+    const bool finite = dmax < 1e300 && amax < 1e300;   // an overflowing fp16 factor / Inf from apply_minv: not solved
+    if (!finite) break;                                 // solved stays false: the host re-runs the job in fp64
+    const bool converged = dmax * rho <= REL_TOL * amax;
     // corrections no longer shrink: either the rounding floor of the residual (then they are tiny) or a factor too
     // poor to precondition (ill-conditioned matrix: lambda -> 0) -- only the first counts as solved
     const bool stalled = sweeps > 1 && dmax > 0.5 * prev_dmax;
@@ -733,7 +736,7 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
       r = __longlong_as_double(0x7ff8000000000000LL);
     } else {
       r = sxy / (sqrt(sxx) * sqrt(syy));
-      r = fabs(fmax(fmin(r, 1.0), -1.0));
+      r = (fabs(r) < 1e300) ? fabs(fmax(fmin(r, 1.0), -1.0)) : __longlong_as_double(0x7ff8000000000000LL);
     }
     *jb.fitness = r;
   }

@@ -282,6 +282,7 @@ cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, float* Linv2
 
 // microbench.cu
 cudaError_t tb_microbench_dmma(int n_sm, cudaStream_t st, double* tflops);
+cudaError_t tb_microbench_umma(int which, int n_sm, cudaStream_t st, double* tops);
 
 // api.cu internals used by de.cu: evaluate the genomes already staged on the device (c->d_idx, c->h_off, c->P)
 // into a device buffer [P * n_slots] (asynchronous on c->stream), and fold the profiling spans after a sync.

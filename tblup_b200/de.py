@@ -152,15 +152,19 @@ class DeviceDE:
                                                              out.ctypes.data), "tb_de_evaluate_testing")
         return out
 
+    def _staged(self):
+        """Genomes of the last scored batch: P, or this rank's shard after a sharded evaluation."""
+        return int(self.eng.info("staged"))
+
     def last_lengths(self):
-        """Marker counts of the last batch scored with a non-empty removed set."""
-        return self._get(7, (self.P,), np.int32)
+        """Marker counts of the last batch scored with a non-empty removed set (shard-local after a sharded step)."""
+        return self._get(7, (min(self.P, self._staged()),), np.int32)
 
     def last_lists(self):
         """The ragged marker lists of the last scored batch (after removal / union), one array per individual."""
         off = np.asarray(self.eng.staged_offsets())
         flat = self._get(8, (int(off[-1]),), np.int32)
-        return [flat[off[i]:off[i + 1]] for i in range(self.P)]
+        return [flat[off[i]:off[i + 1]] for i in range(off.size - 1)]
 
     def _get(self, what, shape, dtype, which=0):
         out = np.empty(shape, dtype=dtype)
@@ -184,4 +188,5 @@ class DeviceDE:
         return self._get(4, (self.k,), np.int32, which=i)
 
     def last_genomes(self):
-        return self._get(5, (self.P, self.k), np.int32)
+        """Genomes of the last scored batch, (staged, k); only meaningful while no marker is removed (fixed length)."""
+        return self._get(5, (self._staged(), self.k), np.int32)

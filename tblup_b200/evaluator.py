@@ -248,6 +248,13 @@ class BlupParallelEvaluator(ParallelEvaluator):
         engines = self.consumers
         flat, off = pack_genomes(genomes, self.n_columns)
         if len(engines) == 1:
+            from . import dist as tdist
+            if tdist.rank_world()[1] > 1:
+                # one process per GPU (torchrun): every rank runs the same seeded main loop, scores its contiguous
+                # slice of the generation and the fitness vector is all-gathered (NCCL; gloo in the CPU tests)
+                return tdist.evaluate_sharded(
+                    lambda f, o: engines[0].evaluate_packed(np.ascontiguousarray(f), np.ascontiguousarray(o), slots,
+                                                            self.h2, MODE_AUTO), flat, off, len(slots))
             return engines[0].evaluate_packed(flat, off, slots, self.h2, MODE_AUTO)
         cuts = shard_bounds(np.diff(off), len(engines))
         out = np.empty((len(genomes), len(slots)))

@@ -8,18 +8,24 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_reference_arm_prints_one_contract_line():
-    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "tiny",
-                          "--steps", "1", "--warmup", "1", "--cpu-sample", "2"], capture_output=True, text=True,
-                         timeout=300, cwd=ROOT)
+import pytest
+
+
+@pytest.mark.parametrize("kind,workload", [("port", "tiny"), ("auto", "tiny"), ("auto", "tiny_3fold")])
+def test_reference_arm_prints_one_contract_line(kind, workload):
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", workload,
+                          "--steps", "1", "--warmup", "1", "--cpu-sample", "2", "--cpu-kind", kind],
+                         capture_output=True, text=True, timeout=300, cwd=ROOT)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [ln for ln in out.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["metric"] == "gblup_fitness_evals_per_sec" and d["unit"] == "evals/s"
     assert d["higher_is_better"] is True and d["value"] > 0 and d["steps"] == 1 and d["warmup"] == 1
-    assert d["config"]["workload"] == "tiny"
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1
+    assert d["config"]["workload"] == workload and d["config"]["pop_is"] == "per_gpu"
+    have_ref = os.path.isdir(os.path.join(ROOT, "oracle", "_ref", "tblup")) or os.path.isdir("/root/reference/tblup")
+    assert d["cpu_baseline"]["kind"] == ("reference" if kind == "auto" and have_ref else "port")
+    assert d["cpu_baseline"]["cores"] >= 1
     assert d["cpu_baseline"]["value"] == d["value"] == d["e2e"]["value"]
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
     assert d["gpu_launches"] == 0
