@@ -177,12 +177,16 @@ class BlupParallelEvaluator(ParallelEvaluator):
 
     @classmethod
     def _adhoc_engine(cls, data, labels, train_indices, validation_indices):
-        key = (id(data), id(labels))
-        entry = cls._adhoc.get(key)
-        if entry is None:
-            cls._adhoc.clear()           # one cached data set at a time
-            entry = {"engine": GblupEngine(data, labels, device=_devices_from_env()[0]), "rows": None}
-            cls._adhoc[key] = entry
+        # one cached data set at a time, recognised by IDENTITY of the arrays the caller holds; the entry keeps a
+        # reference to both, so their ids cannot be recycled for other arrays while the entry lives
+        entry = cls._adhoc.get("entry")
+        if entry is None or entry["data"] is not data or entry["labels"] is not labels:
+            if entry is not None:
+                entry["engine"].close()
+            cls._adhoc.clear()
+            entry = {"engine": GblupEngine(data, labels, device=_devices_from_env()[0]), "rows": None,
+                     "data": data, "labels": labels}
+            cls._adhoc["entry"] = entry
         rows = (hash(np.asarray(train_indices).tobytes()), hash(np.asarray(validation_indices).tobytes()))
         if entry["rows"] != rows:
             entry["engine"].set_rowset(0, train_indices, validation_indices)

@@ -236,6 +236,58 @@ def test_population_sharding_over_ranks_gloo():
     assert np.array_equal(got[0], want) and np.array_equal(got[1], want)
 
 
+def _dist_eval_worker(rank, world, port, geno, pheno, genomes, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import tblup_b200.evaluator as ev
+    ev.GblupEngine = OracleEngine
+    seeded(3)
+    e = ev.IntraGCVBlupParallelEvaluator(geno, pheno, 0.4, n_folds=3, snp_remover=ev.SNPRemovalHandler(10, 0.0, 0.4, False),
+                                         devices=[0])
+    pop = [Indv(g) for g in genomes]
+    with e:
+        e.evaluate(pop, pop, 0)
+        sizes = [c[0] for c in OracleEngine.instances[-1].calls]
+    q.put((rank, [p.fitness for p in pop], sizes))
+    dist.destroy_process_group()
+
+
+def test_evaluator_shards_over_torch_distributed_ranks_gloo(tmp_path):
+    """One process per GPU (torchrun): the evaluator class scores its slice and all-gathers -- every rank ends with the
+    whole generation's fitness, equal to a single-process run."""
+    import torch.multiprocessing as mp
+    g = load_golden("fit_small")
+    geno, pheno = tmp_path / "geno.npy", tmp_path / "pheno.npy"
+    np.save(geno, g["x"].astype(np.float64))
+    np.save(pheno, g["y"])
+    genomes = [np.asarray(x) for x in unpack(g["genomes_flat"], g["genomes_off"])]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_dist_eval_worker, args=(r, 2, port, str(geno), str(pheno), genomes, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {r: (f, s) for r, f, s in (q.get(timeout=180) for _ in procs)}
+    for p in procs:
+        p.join(timeout=60)
+    assert got[0][0] == got[1][0] and all(np.isfinite(got[0][0]))
+    assert got[0][1][0] + got[1][1][0] == len(genomes) and min(got[0][1][0], got[1][1][0]) >= 1
+    import tblup_b200.evaluator as ev
+    seeded(3)
+    e = ev.IntraGCVBlupParallelEvaluator(str(geno), str(pheno), 0.4, n_folds=3,
+                                         snp_remover=ev.SNPRemovalHandler(10, 0.0, 0.4, False), devices=[0])
+    saved = ev.GblupEngine
+    ev.GblupEngine = OracleEngine
+    try:
+        pop = [Indv(x) for x in genomes]
+        with e:
+            e.evaluate(pop, pop, 0)
+    finally:
+        ev.GblupEngine = saved
+    assert np.abs(np.array([p.fitness for p in pop]) - np.array(got[0][0])).max() < 1e-12
+
+
 @pytest.mark.skipif(not HAVE_REF, reason="reference checkout not present (GPU box)")
 @pytest.mark.parametrize("name", ["traj_gblup", "traj_intracv"])
 def test_reference_main_loop_drives_our_evaluator(name, tmp_path, monkeypatch):

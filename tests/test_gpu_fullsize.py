@@ -64,7 +64,7 @@ def test_mixed_agrees_with_fp64_and_waves_do_not_matter(big):
     eng.set_option("max_wave", 7)
     again = eng.evaluate_packed(flat, off, slots=[0], mode=E.MODE_AUTO)[:, 0]
     eng.set_option("max_wave", 0)
-    assert eng.last_wave() != 7 or True
+    assert eng.last_wave() == 7 or eng.last_wave() == 24
     assert np.array_equal(again, mix)
     test_fit = eng.evaluate_packed(flat[:off[4]], off[:5], slots=[1], mode=E.MODE_AUTO)[:, 0]     # 4 000 train -> 1 000 test
     assert np.all(np.isfinite(test_fit)) and np.all((test_fit >= 0) & (test_fit <= 1))
@@ -81,3 +81,85 @@ def test_two_genomes_against_the_reference_algorithm(big):
     xf = x.astype(np.float64)
     for gnm, f in zip(genomes, got):
         assert abs(O.ref_blup(gnm.astype(int), list(tr), list(va), xf, y, 0.4) - f) < 1e-6
+
+
+@pytest.mark.parametrize("k", [K, 50000])
+def test_fp4_gram_bit_exact_full_size(big, k):
+    """The DEFAULT Gram (tcgen05 kind::mxf4 on E2M1 nibbles) against the exact integer oracle at the headline k and at
+    k = 50 000 (config 4's subset size: sums up to 200 000, beyond int16, every k-block of the panel in use)."""
+    from oracle import gblup_oracle as O
+    eng, x, y, tr, va, te = big
+    rng = np.random.default_rng(11 + k)
+    idx = rng.choice(M, size=k, replace=False)
+    rows = 4000
+    got = eng.gram_debug(idx, rows, impl="fp4")
+    want = np.tril(O.exact_gram(x, idx, np.concatenate([tr, va])[:rows]))
+    assert np.array_equal(got.astype(np.int64), want)
+    assert got.max() > (32767 if k == 50000 else 0)
+
+
+def test_k50000_fitness_uses_int32_cross_products(big):
+    """k = 50 000: 4 k > 32 767, so the wave keeps int32 cross-products (fused scaling, mixed precision still on);
+    fitness against the exact oracle."""
+    from oracle import gblup_oracle as O
+    from tblup_b200 import engine as E
+    eng, x, y, tr, va, te = big
+    rng = np.random.default_rng(5)
+    genomes = [rng.permutation(M), rng.choice(M, size=40000, replace=False)]
+    eng.set_precision("mixed")
+    got = eng.evaluate(genomes, slots=[0], mode=E.MODE_AUTO)[:, 0]
+    assert eng.info("last_c16") == 0 and eng.info("last_fp4") == 1 and eng.last_precision() == "mixed"
+    want = [O.exact_blup(g, tr, va, x, y, 0.4) for g in genomes]
+    assert np.abs(got - np.array(want)).max() < 1e-6
+
+
+def test_config3_shape_ten_aligned_folds(big):
+    """BASELINE config 3: 10-fold intra-generation CV over the 3 200 training animals (2 880 train / 320 held out per
+    fold, tblup/evaluator.py:455-483, :509-537): one Gram per genome, ten factorisations; four genomes (both branches of
+    blup()) against the exact oracle, fold by fold."""
+    from oracle import gblup_oracle as O
+    from tblup_b200 import GblupEngine, engine as E
+    _, x, y, tr, va, te = big
+    folds = [(np.asarray(t), np.asarray(v)) for t, v in O.ref_make_fold_indices(list(tr), 10)]
+    assert [len(v) for _, v in folds] == [320] * 10
+    rng = np.random.default_rng(9)
+    genomes = [rng.choice(M, size=k, replace=False) for k in (K, K, 4800, 5000)]
+    with GblupEngine(x, y, perm=np.concatenate([tr, va, te])) as eng:
+        for f, (t, v) in enumerate(folds):
+            eng.set_rowset(f, t, v)
+        got = eng.evaluate(genomes, slots=list(range(10)), mode=E.MODE_AUTO)
+        assert eng.last_precision() == "mixed" and eng.info("last_split") == 0
+    want = np.array([O.exact_fitness_rowsets(g, folds, x, y, 0.4) for g in genomes])
+    assert got.shape == want.shape == (4, 10)
+    assert np.abs(got - want).max() < 1e-6
+
+
+def test_nan_semantics_on_device():
+    """scipy.stats.pearsonr conventions of tblup/evaluator.py:286,:314 on the GPU: a constant validation phenotype or a
+    genome of monomorphic markers (G = 0/0) gives NaN -- and NaN never wins the reference's selection
+    (tblup/selector.py:28: ``child.fitness > parent.fitness``)."""
+    from tblup_b200 import GblupEngine, engine as E, synth
+    n, m = 600, 3000
+    x, y = synth.synth_dataset(n, m, h2=0.4, seed=21)
+    x[:, :40] = 0                                   # monomorphic markers
+    tr, va, te = synth.split_indices(n, seed=21)
+    y_const = y.copy()
+    y_const[va] = 3.25
+    rng = np.random.default_rng(1)
+    ok_small, ok_big = rng.choice(np.arange(40, m), size=300, replace=False), rng.choice(np.arange(40, m), size=700, replace=False)
+    mono = np.arange(40)
+    mono_big = np.concatenate([np.arange(40)] * 16)          # 640 > n: the gblup branch on monomorphic columns
+    for precision in ("mixed", "fp64"):
+        with GblupEngine(x, y_const, perm=np.concatenate([tr, va, te])) as eng:
+            eng.set_precision(precision)
+            eng.set_rowset(0, tr, va)
+            f = eng.evaluate([ok_small, ok_big], slots=[0], mode=E.MODE_AUTO)[:, 0]
+            assert np.all(np.isnan(f)), f
+        with GblupEngine(x, y, perm=np.concatenate([tr, va, te])) as eng:
+            eng.set_precision(precision)
+            eng.set_rowset(0, tr, va)
+            f = eng.evaluate([ok_small, mono, ok_big, mono_big], slots=[0], mode=E.MODE_AUTO)[:, 0]
+            assert np.isfinite(f[0]) and np.isfinite(f[2]) and np.isnan(f[1]) and np.isnan(f[3]), f
+            # greedy selection exactly as tblup/selector.py:28 writes it
+            parent, child = 0.1, float(f[1])
+            assert not (child > parent)
