@@ -29,6 +29,12 @@ import sys
 import threading
 import time
 
+if "reference" in sys.argv[1:]:
+    # the reference's deployment: one single-threaded BLAS per worker process (generate_sbs.py:25 exports
+    # OMP_NUM_THREADS=1).  Its workers are FORKED from this process, so the limit must be in place before numpy loads.
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = "1"
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -204,7 +210,16 @@ class ReferenceArm:
         self.ev.training_indices, self.ev.validation_indices = [int(i) for i in train], [int(i) for i in valid]
         if folds > 1:
             self.ev.fold_indices = self.ev.make_fold_indices(self.ev.training_indices, folds)
+        # the workers are forked: they inherit this process's BLAS thread setting, not the environment
+        self._blas_limit = None
+        try:
+            from threadpoolctl import threadpool_limits
+            self._blas_limit = threadpool_limits(limits=1)
+        except Exception:
+            pass
         self.ev.__enter__()
+        if self._blas_limit is not None:
+            self._blas_limit.restore_original_limits()
         self.what = ("reference %s with its own %d-process worker pool (tblup/evaluator.py), 1 BLAS thread per worker"
                      % (type(self.ev).__name__, cores))
 

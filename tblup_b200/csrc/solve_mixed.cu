@@ -100,233 +100,6 @@ __device__ __forceinline__ double dot8h(const uint4 l, const double* z) {
          ((double)f2.x * z2.x + (double)f2.y * z2.y) + ((double)f3.x * z3.x + (double)f3.y * z3.y);
 }
 
-// work <- (L L^T)^-1 work, in place.  L is the fp16 copy of the TF32 factor (identical 10-bit mantissa, half the
-// bytes of fp32).  All global loads are 16 bytes with four independent loads in flight per thread (the kernel is
-// bound by how many bytes one CTA keeps in flight, not by arithmetic); accumulation in fp64.
-__device__ void apply_minv(const __half* __restrict__ L, const float* __restrict__ Linv, int ntp, double* work,
-                           double* rvec, double* part) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nb = ntp / NB;
-  for (int b = 0; b < nb; ++b) {                      // forward: L z = work
-    const int kc = b * NB;
-    {
-      // each warp owns rows kc + 4 warp .. + 3 and streams them together (z is read from smem once for all four)
-      const uint4* r0 = reinterpret_cast<const uint4*>(L + (size_t)(kc + 4 * warp) * ntp);
-      const size_t rs = ntp / 8;
-      double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-      for (int c = lane; c < kc / 8; c += 32) {
-        const uint4 l0 = r0[c], l1 = r0[rs + c], l2 = r0[2 * rs + c], l3 = r0[3 * rs + c];
-        const double* z = work + 8 * c;
-        s0 += dot8h(l0, z);
-        s1 += dot8h(l1, z);
-        s2 += dot8h(l2, z);
-        s3 += dot8h(l3, z);
-      }
-      s0 = warp_sum(s0);
-      s1 = warp_sum(s1);
-      s2 = warp_sum(s2);
-      s3 = warp_sum(s3);
-      if (lane == 0) {
-        rvec[4 * warp + 0] = work[kc + 4 * warp + 0] - s0;
-        rvec[4 * warp + 1] = work[kc + 4 * warp + 1] - s1;
-        rvec[4 * warp + 2] = work[kc + 4 * warp + 2] - s2;
-        rvec[4 * warp + 3] = work[kc + 4 * warp + 3] - s3;
-      }
-    }
-    __syncthreads();
-    {
-      const int i = tid >> 3, sub = tid & 7;
-      const float4* li = reinterpret_cast<const float4*>(Linv + ((size_t)kc + i) * NB + sub * 8);
-      const double s_ = dot4(li[0], rvec + sub * 8) + dot4(li[1], rvec + sub * 8 + 4);
-      double s = s_;
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      if (sub == 0) work[kc + i] = s;
-    }
-    __syncthreads();
-  }
-  for (int b = nb - 1; b >= 0; --b) {                 // backward: L^T d = z
-    const int kc = b * NB;
-    {
-      // thread = 8 consecutive columns (one 16-byte load) x one of 64 row groups
-      const int cq = tid & 7, rg = tid >> 3;
-      double a[8];
-#pragma unroll
-      for (int e = 0; e < 8; ++e) a[e] = 0.0;
-      const __half* base = L + kc + 8 * cq;
-      auto acc8 = [&](const uint4 l, const double w) {
-        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&l.x));
-        const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
-        const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&l.z));
-        const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&l.w));
-        a[0] += (double)f0.x * w;
-        a[1] += (double)f0.y * w;
-        a[2] += (double)f1.x * w;
-        a[3] += (double)f1.y * w;
-        a[4] += (double)f2.x * w;
-        a[5] += (double)f2.y * w;
-        a[6] += (double)f3.x * w;
-        a[7] += (double)f3.y * w;
-      };
-      int i = kc + NB + rg;
-      for (; i + 192 < ntp; i += 256) {
-        const uint4 l0 = *reinterpret_cast<const uint4*>(base + (size_t)i * ntp);
-        const uint4 l1 = *reinterpret_cast<const uint4*>(base + (size_t)(i + 64) * ntp);
-        const uint4 l2 = *reinterpret_cast<const uint4*>(base + (size_t)(i + 128) * ntp);
-        const uint4 l3 = *reinterpret_cast<const uint4*>(base + (size_t)(i + 192) * ntp);
-        acc8(l0, work[i]);
-        acc8(l1, work[i + 64]);
-        acc8(l2, work[i + 128]);
-        acc8(l3, work[i + 192]);
-      }
-      for (; i < ntp; i += 64) acc8(*reinterpret_cast<const uint4*>(base + (size_t)i * ntp), work[i]);
-      // the four row groups of a warp (lanes differing in bits 3, 4) are combined by shuffle, one smem row per warp
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        a[e] += __shfl_xor_sync(0xffffffffu, a[e], 8);
-        a[e] += __shfl_xor_sync(0xffffffffu, a[e], 16);
-      }
-      if (lane < 8) {
-        double* pr = part + warp * NB + 8 * cq;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) pr[e] = a[e];
-      }
-    }
-    __syncthreads();
-    if (tid < NB) {
-      double s = 0.0;
-#pragma unroll
-      for (int gI = 0; gI < ST / 32; ++gI) s += part[gI * NB + tid];
-      rvec[tid] = work[kc + tid] - s;
-    }
-    __syncthreads();
-    {
-      const int i = tid & 63, grp = tid >> 6;
-      const float* li = Linv + (size_t)kc * NB;
-      double s = 0.0;
-#pragma unroll
-      for (int pp = 0; pp < 8; ++pp) {
-        const int q = grp * 8 + pp;
-        s += (double)li[q * NB + i] * rvec[q];
-      }
-      part[grp * NB + i] = s;
-    }
-    __syncthreads();
-    if (tid < NB) {
-      double s = 0.0;
-#pragma unroll
-      for (int gI = 0; gI < 8; ++gI) s += part[gI * NB + tid];
-      work[kc + tid] = s;
-    }
-    __syncthreads();
-  }
-}
-
-// (C alpha)_a for contiguous training animals from int16 cross-products: the lower triangle is streamed once by
-// rows and once by columns with 16-byte loads (eight entries), four loads in flight per thread.
-// The training animals may be "contiguous with one hole": compact index i sits at universe position i for i < h0 and
-// at i + gap beyond (k-fold cross-validation: the fold that is held out is a contiguous run of the training
-// animals, evaluator.py:455-483).  h0 and gap are multiples of 8, so an 8-entry group never straddles the hole;
-// gap = 0 (h0 = n_t) is the plain contiguous case.
-// HOLE = false compiles the index mapping away (plain contiguous row sets pay nothing for it).
-template <bool HOLE>
-__device__ void sym_matvec16(const int16_t* __restrict__ C, int rpad, int n_t, int h0, int gap, const double* alpha,
-                             double* work, double* part2) {
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  auto U = [&](int i) { return HOLE ? i + (i >= h0 ? gap : 0) : i; };   // compact index -> universe position
-  const int hg = h0 >> 3, gg = gap >> 3;
-  // rows: a warp takes FOUR consecutive rows a .. a+3 (n_t is a multiple of 4) so that every alpha piece read from
-  // shared memory serves four 16-byte loads of C (four independent global loads in flight per thread).
-  for (int a = 4 * warp; a < n_t; a += 4 * (ST / 32)) {
-    const int ua = U(a);                            // rows a .. a+3 are consecutive in the universe too
-    const uint4* row = reinterpret_cast<const uint4*>(C + (size_t)ua * rpad);
-    const size_t rs = rpad / 8;
-    const int full = (a + 1) / 8;                   // 8-entry groups at or left of the diagonal of ALL four rows
-    double d[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int c = lane; c < full; c += 32) {
-      const int uc = HOLE ? c + (c >= hg ? gg : 0) : c;
-      fma4x8s(d, row[uc], row[rs + uc], row[2 * rs + uc], row[3 * rs + uc], alpha + 8 * c);
-    }
-    // the (at most 11) columns 8 full .. a + 3 that reach the diagonals: one lane per column, guarded per row
-    {
-      const int b = 8 * full + lane;
-      if (lane < 12 && b <= a + 3) {
-        const double z = alpha[b];
-        const int ub = U(b);
-#pragma unroll
-        for (int rr = 0; rr < 4; ++rr)
-          if (b <= a + rr) d[rr] += (double)C[(size_t)(ua + rr) * rpad + ub] * z;
-      }
-    }
-#pragma unroll
-    for (int rr = 0; rr < 4; ++rr) {
-      const double t = warp_sum(d[rr]);
-      if (lane == 0) work[a + rr] = t;
-    }
-  }
-  __syncthreads();
-  // columns: thread = 8 consecutive columns x one of 8 row groups (rows b = rg mod 8); the four row groups inside a
-  // warp are combined by shuffles, the two halves of the CTA through part2.  A thread starts at its first row
-  // below the diagonal of its own columns: at most one guarded load, nothing above the diagonal is read.
-  const int cgl = lane & 7, rsub = lane >> 3, cblk = warp & 7, rsup = warp >> 3;
-  const int rg = rsup * 4 + rsub;
-  for (int a0 = 0; a0 < n_t; a0 += 512) {
-    const int ca = a0 + 64 * cblk + 8 * cgl;
-    double acc[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[e] = 0.0;
-    auto add8 = [&](const uint4 v, const double w) {
-      acc[0] += u2d(v.x & 0xffffu) * w;
-      acc[1] += u2d(v.x >> 16) * w;
-      acc[2] += u2d(v.y & 0xffffu) * w;
-      acc[3] += u2d(v.y >> 16) * w;
-      acc[4] += u2d(v.z & 0xffffu) * w;
-      acc[5] += u2d(v.z >> 16) * w;
-      acc[6] += u2d(v.w & 0xffffu) * w;
-      acc[7] += u2d(v.w >> 16) * w;
-    };
-    if (ca < n_t) {
-      const int16_t* colp = C + U(ca);
-      int b = ca + 1 + rg;                          // rows ca + 1 + rg, + 8, ...: every row below the diagonal once
-      if (b < n_t && b <= ca + 7) {                 // crosses the 8 x 8 diagonal block: guard per column
-        const uint4 v = *reinterpret_cast<const uint4*>(colp + (size_t)U(b) * rpad);
-        const uint32_t wv[4] = {v.x, v.y, v.z, v.w};
-        const double w = alpha[b];
-#pragma unroll
-        for (int e = 0; e < 8; ++e)
-          if (b > ca + e) acc[e] += u2d((wv[e >> 1] >> (16 * (e & 1))) & 0xffffu) * w;
-        b += 8;
-      }
-      for (; b + 24 < n_t; b += 32) {
-        const uint4 v0 = *reinterpret_cast<const uint4*>(colp + (size_t)U(b) * rpad);
-        const uint4 v1 = *reinterpret_cast<const uint4*>(colp + (size_t)U(b + 8) * rpad);
-        const uint4 v2 = *reinterpret_cast<const uint4*>(colp + (size_t)U(b + 16) * rpad);
-        const uint4 v3 = *reinterpret_cast<const uint4*>(colp + (size_t)U(b + 24) * rpad);
-        add8(v0, alpha[b]);
-        add8(v1, alpha[b + 8]);
-        add8(v2, alpha[b + 16]);
-        add8(v3, alpha[b + 24]);
-      }
-      for (; b < n_t; b += 8) add8(*reinterpret_cast<const uint4*>(colp + (size_t)U(b) * rpad), alpha[b]);
-    }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
-      acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
-    }
-    if (rsub == 0) {
-      double* pr = part2 + rsup * 512 + 64 * cblk + 8 * cgl;
-#pragma unroll
-      for (int e = 0; e < 8; ++e) pr[e] = acc[e];
-    }
-    __syncthreads();
-    const int a = a0 + tid;
-    if (a < n_t) work[a] += part2[tid] + part2[512 + tid];
-    __syncthreads();
-  }
-}
-
 // Cross-products of the held-out animals (universe positions h0 .. h0 + gap - 1, the hole of the training set) with the
 // solution: out[v] = sum_b C(h0 + v, U(b)) alpha_b.  Training animals before the hole lie in the row of the held-out
 // animal (four rows per warp), those after it in its COLUMN of the lower triangle (the column pass of sym_matvec16
@@ -396,6 +169,240 @@ __device__ void hole_predict16(const int16_t* __restrict__ C, int rpad, int n_t,
   }
 }
 
+
+// ---- fp32 application of the preconditioner -----------------------------------------------------------------------
+// wf <- (L L^T)^-1 wf in place, entirely in fp32 (fp16 factor widened pairwise, FFMA accumulation).  The factor is a
+// 10-bit preconditioner (it contracts the error ~300x per sweep); applying it with fp32 rounding (~1e-6 relative)
+// changes nothing about what the refinement converges to -- the residual is formed in fp64 from the exact integers --
+// and frees the fp64 / conversion pipes and half of the shared-memory reads of the solution vector (r01 ncu: XU 33 %,
+// fp64 26 %, LSU wavefronts 66 % busy with one fp64 value per factor entry).
+__device__ __forceinline__ float dot8hf(const uint4 l, const float4 z0, const float4 z1) {
+  const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&l.x));
+  const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
+  const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&l.z));
+  const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&l.w));
+  return ((f0.x * z0.x + f0.y * z0.y) + (f1.x * z0.z + f1.y * z0.w)) + ((f2.x * z1.x + f2.y * z1.y) + (f3.x * z1.z + f3.y * z1.w));
+}
+__device__ __forceinline__ float warp_sumf(float v) {
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+__device__ void apply_minv_f32(const __half* __restrict__ L, const float* __restrict__ Linv, int ntp, float* wf,
+                               float* rvec, float* part) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nb = ntp / NB;
+  for (int b = 0; b < nb; ++b) {                      // forward: L z = wf
+    const int kc = b * NB;
+    {
+      const uint4* r0 = reinterpret_cast<const uint4*>(L + (size_t)(kc + 4 * warp) * ntp);
+      const size_t rs = ntp / 8;
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      for (int c = lane; c < kc / 8; c += 32) {
+        const uint4 l0 = r0[c], l1 = r0[rs + c], l2 = r0[2 * rs + c], l3 = r0[3 * rs + c];
+        const float4 z0 = *reinterpret_cast<const float4*>(wf + 8 * c), z1 = *reinterpret_cast<const float4*>(wf + 8 * c + 4);
+        s0 += dot8hf(l0, z0, z1);
+        s1 += dot8hf(l1, z0, z1);
+        s2 += dot8hf(l2, z0, z1);
+        s3 += dot8hf(l3, z0, z1);
+      }
+      s0 = warp_sumf(s0);
+      s1 = warp_sumf(s1);
+      s2 = warp_sumf(s2);
+      s3 = warp_sumf(s3);
+      if (lane == 0) {
+        rvec[4 * warp + 0] = wf[kc + 4 * warp + 0] - s0;
+        rvec[4 * warp + 1] = wf[kc + 4 * warp + 1] - s1;
+        rvec[4 * warp + 2] = wf[kc + 4 * warp + 2] - s2;
+        rvec[4 * warp + 3] = wf[kc + 4 * warp + 3] - s3;
+      }
+    }
+    __syncthreads();
+    {
+      const int i = tid >> 3, sub = tid & 7;
+      const float4* li = reinterpret_cast<const float4*>(Linv + ((size_t)kc + i) * NB + sub * 8);
+      const float4 a0 = li[0], a1 = li[1];
+      const float4 z0 = *reinterpret_cast<const float4*>(rvec + sub * 8), z1 = *reinterpret_cast<const float4*>(rvec + sub * 8 + 4);
+      float sv = (a0.x * z0.x + a0.y * z0.y) + (a0.z * z0.z + a0.w * z0.w) + (a1.x * z1.x + a1.y * z1.y) + (a1.z * z1.z + a1.w * z1.w);
+      sv += __shfl_xor_sync(0xffffffffu, sv, 1);
+      sv += __shfl_xor_sync(0xffffffffu, sv, 2);
+      sv += __shfl_xor_sync(0xffffffffu, sv, 4);
+      if (sub == 0) wf[kc + i] = sv;
+    }
+    __syncthreads();
+  }
+  for (int b = nb - 1; b >= 0; --b) {                 // backward: L^T d = z
+    const int kc = b * NB;
+    {
+      const int cq = tid & 7, rg = tid >> 3;           // thread = 8 consecutive columns x one of 64 row groups
+      float a[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) a[e] = 0.f;
+      const __half* base = L + kc + 8 * cq;
+      auto acc8 = [&](const uint4 l, const float w) {
+        const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&l.x));
+        const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&l.y));
+        const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&l.z));
+        const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&l.w));
+        a[0] = fmaf(f0.x, w, a[0]);
+        a[1] = fmaf(f0.y, w, a[1]);
+        a[2] = fmaf(f1.x, w, a[2]);
+        a[3] = fmaf(f1.y, w, a[3]);
+        a[4] = fmaf(f2.x, w, a[4]);
+        a[5] = fmaf(f2.y, w, a[5]);
+        a[6] = fmaf(f3.x, w, a[6]);
+        a[7] = fmaf(f3.y, w, a[7]);
+      };
+      int i = kc + NB + rg;
+      for (; i + 448 < ntp; i += 512) {                // eight independent 16-byte loads in flight
+        uint4 l[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) l[u] = *reinterpret_cast<const uint4*>(base + (size_t)(i + 64 * u) * ntp);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc8(l[u], wf[i + 64 * u]);
+      }
+      for (; i < ntp; i += 64) acc8(*reinterpret_cast<const uint4*>(base + (size_t)i * ntp), wf[i]);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        a[e] += __shfl_xor_sync(0xffffffffu, a[e], 8);
+        a[e] += __shfl_xor_sync(0xffffffffu, a[e], 16);
+      }
+      if (lane < 8) {
+        float* pr = part + warp * NB + 8 * cq;
+        *reinterpret_cast<float4*>(pr) = make_float4(a[0], a[1], a[2], a[3]);
+        *reinterpret_cast<float4*>(pr + 4) = make_float4(a[4], a[5], a[6], a[7]);
+      }
+    }
+    __syncthreads();
+    if (tid < NB) {
+      float sv = 0.f;
+#pragma unroll
+      for (int gI = 0; gI < ST / 32; ++gI) sv += part[gI * NB + tid];
+      rvec[tid] = wf[kc + tid] - sv;
+    }
+    __syncthreads();
+    {
+      const int i = tid & 63, grp = tid >> 6;
+      const float* li = Linv + (size_t)kc * NB;
+      float sv = 0.f;
+#pragma unroll
+      for (int pp = 0; pp < 8; ++pp) {
+        const int q = grp * 8 + pp;
+        sv = fmaf(li[q * NB + i], rvec[q], sv);
+      }
+      part[grp * NB + i] = sv;
+    }
+    __syncthreads();
+    if (tid < NB) {
+      float sv = 0.f;
+#pragma unroll
+      for (int gI = 0; gI < 8; ++gI) sv += part[gI * NB + tid];
+      wf[kc + tid] = sv;
+    }
+    __syncthreads();
+  }
+}
+
+// ---- symmetric mat-vec in ONE pass over the lower triangle --------------------------------------------------------
+// out[a] = (C alpha)_a for contiguous training animals from int16 cross-products.  Every 16-byte load of C feeds BOTH
+// the row dot product (out[r] += C[r][c] alpha[c]) and the column update (out[c] += C[r][c] alpha[r]), so the
+// triangle crosses HBM once per sweep instead of twice (r01: "by rows, then by columns").
+// Work unit = 128 rows x one 128-column strip, taken by a warp from a shared counter (largest strips first).  A lane
+// owns 4 consecutive columns of the strip (8-byte loads, eight rows in flight): their alpha entries and the 8 column accumulators stay in registers down
+// the unit; the row partials of four rows are reduced across the warp by a transposing butterfly (6 shuffles per four
+// rows) and added to out[] with shared-memory atomics, as are the column sums at the end of the unit (about 40
+// warp-level atomics per 16 K entries of C).  The same "prefix with one aligned hole" index mapping as before.
+template <bool HOLE>
+__device__ void sym_matvec16_1p(const int16_t* __restrict__ C, int rpad, int n_t, int h0, int gap, const double* alpha,
+                                double* out, int* counter) {
+  const int tid = threadIdx.x, lane = tid & 31;
+  auto U = [&](int i) { return HOLE ? i + (i >= h0 ? gap : 0) : i; };   // compact index -> universe position
+  for (int a = tid; a < n_t; a += ST) out[a] = 0.0;
+  if (tid == 0) *counter = 0;
+  __syncthreads();
+  constexpr int SW = 128, RU = 128;                  // strip width (4 columns per lane), rows per unit
+  const int n_strips = (n_t + SW - 1) / SW;
+  int total = 0;
+  for (int s = 0; s < n_strips; ++s) total += (n_t - SW * s + RU - 1) / RU;
+  for (;;) {
+    int u = 0;
+    if (lane == 0) u = atomicAdd(counter, 1);
+    u = __shfl_sync(0xffffffffu, u, 0);
+    if (u >= total) break;
+    int s = 0;
+    for (;; ++s) {
+      const int cnt = (n_t - SW * s + RU - 1) / RU;
+      if (u < cnt) break;
+      u -= cnt;
+    }
+    const int c0 = SW * s + 4 * lane;                // this lane's first column (compact index)
+    const int r0 = SW * s + RU * u, r1 = min(n_t, r0 + RU);
+    const bool col_ok = c0 < n_t;                     // n_t is a multiple of 4: a lane's four columns are all in or all out
+    double ac[4], al[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      ac[e] = 0.0;
+      al[e] = col_ok ? alpha[c0 + e] : 0.0;
+    }
+    const int16_t* colp = C + U(c0);
+    const bool diag_unit = u == 0;                    // SW == RU: only a strip's first unit reaches its diagonal
+    for (int r = r0; r < r1; r += 8) {                // eight rows (8-byte loads) in flight; n_t % 4 == 0
+      uint2 v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        v[q] = make_uint2(0u, 0u);
+        if (col_ok && r + q < r1 && (!diag_unit || c0 <= r + q))
+          v[q] = *reinterpret_cast<const uint2*>(colp + (size_t)U(r + q) * rpad);
+      }
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (r + 4 * h >= r1) break;
+        double p[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int rr = r + 4 * h + q;
+          const double ar = alpha[rr];
+          const uint32_t w0 = v[4 * h + q].x, w1 = v[4 * h + q].y;
+          const double cc[4] = {u2d(w0 & 0xffffu), u2d(w0 >> 16), u2d(w1 & 0xffffu), u2d(w1 >> 16)};
+          double pr = 0.0;
+          if (!diag_unit || c0 + 3 < rr) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              pr += cc[e] * al[e];
+              ac[e] += cc[e] * ar;
+            }
+          } else if (c0 <= rr) {                      // the 4-column group that holds the diagonal of row rr
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (c0 + e <= rr) pr += cc[e] * al[e];   // the diagonal entry counts once (in the row part)
+              if (c0 + e < rr) ac[e] += cc[e] * ar;
+            }
+          }
+          p[q] = pr;
+        }
+        // transposing butterfly: afterwards lane 8 q (q = 0..3) holds the sum over the warp of p[q]
+        const bool hi16 = lane & 16, hi8 = lane & 8;
+        double x0 = hi16 ? p[2] : p[0], x1 = hi16 ? p[3] : p[1];
+        const double s0 = hi16 ? p[0] : p[2], s1 = hi16 ? p[1] : p[3];
+        x0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+        x1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+        double yv = hi8 ? x1 : x0;
+        const double sy = hi8 ? x0 : x1;
+        yv += __shfl_xor_sync(0xffffffffu, sy, 8);
+        yv += __shfl_xor_sync(0xffffffffu, yv, 4);
+        yv += __shfl_xor_sync(0xffffffffu, yv, 2);
+        yv += __shfl_xor_sync(0xffffffffu, yv, 1);
+        if ((lane & 7) == 0) atomicAdd(out + r + 4 * h + 2 * (lane >> 4) + ((lane >> 3) & 1), yv);
+      }
+    }
+    if (col_ok) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) atomicAdd(out + c0 + e, ac[e]);
+    }
+  }
+  __syncthreads();
+}
+
 // (C alpha)_a over the training animals into work[a]; CONTIG: training animal b sits at universe position b.
 // CT: element type of the stored cross-products (int32_t, or int16_t in C16 mode).
 template <bool CONTIG, bool HOLE, typename CT>
@@ -403,7 +410,8 @@ __device__ void sym_matvec(const CT* __restrict__ C, int rpad, int n_t, int h0, 
                            const double* alpha, double* work, double* part2) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if constexpr (CONTIG && sizeof(CT) == 2) {
-    sym_matvec16<HOLE>(reinterpret_cast<const int16_t*>(C), rpad, n_t, h0, gap, alpha, work, part2);
+    sym_matvec16_1p<HOLE>(reinterpret_cast<const int16_t*>(C), rpad, n_t, h0, gap, alpha, work,
+                          reinterpret_cast<int*>(part2));
   } else if constexpr (CONTIG) {
     // rows: (C alpha)_a += sum_{b <= a} C[a][b] alpha_b, 16-byte loads, four in flight
     for (int a = warp; a < n_t; a += ST / 32) {
@@ -535,22 +543,25 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
   // the job's global output vector and the positions are read from the row set (both stay L1/L2 resident)
   // (BIG is a template parameter so that each instantiation knows the address space of alpha / tp statically)
   constexpr bool big = BIG;
-  double* work = msm;                // [ntp]
-  double* rvec = work + ntp;         // [NB]
-  double* part = rvec + NB;          // [ST/32][NB]
-  double* part2 = part + (ST / 32) * NB;   // [4][512]
+  double* work = msm;                // [ntp]   (C alpha) / residual in fp64
+  double* part2 = work + ntp;        // [4][512] scratch of the column passes (its first word: work counter)
   double* red = part2 + 4 * 512;     // [ST/32]
   double* alpha;                     // [ntp]
   const int* tp;                     // [n_t]
   int* tp_w = nullptr;
+  float* wf;                         // [ntp]   right-hand side / result of the fp32 preconditioner application
   if constexpr (BIG) {
     alpha = jb.alpha;
     tp = jb.tpos;
+    wf = reinterpret_cast<float*>(red + ST / 32);
   } else {
     alpha = red + ST / 32;
-    tp_w = reinterpret_cast<int*>(red + ST / 32 + ntp);
+    tp_w = reinterpret_cast<int*>(alpha + ntp);
     tp = tp_w;
+    wf = reinterpret_cast<float*>(tp_w + ntp);
   }
+  float* rvec = wf + ntp;            // [NB]
+  float* part = rvec + NB;           // [ST/32][NB]
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const double Nd = (double)jb.N, Sd = (double)jb.SQ[0], Qd = (double)jb.SQ[1];
   const double coef = 2.0 / (2.0 * Nd * Sd - Qd);
@@ -558,11 +569,11 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
 
   for (int a = tid; a < ntp; a += ST) {
     if (tp_w) tp_w[a] = a < n_t ? jb.tpos[a] : 0;
-    work[a] = jb.y_t[a];
+    wf[a] = (float)jb.y_t[a];
   }
   __syncthreads();
-  apply_minv(static_cast<const __half*>(jb.L16), jb.Linv32, ntp, work, rvec, part);
-  for (int a = tid; a < ntp; a += ST) alpha[a] = work[a];
+  apply_minv_f32(static_cast<const __half*>(jb.L16), jb.Linv32, ntp, wf, rvec, part);
+  for (int a = tid; a < ntp; a += ST) alpha[a] = (double)wf[a];
   __syncthreads();
 
   int sweeps = 0;
@@ -585,13 +596,13 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
                           coef * (Nd * Nd * work[a] - Nd * (double)jb.s[tp[a]] * sa - Nd * ssa + Qd * sa);
         rr = jb.y_t[a] - Aa;
       }
-      work[a] = rr;
+      wf[a] = (float)rr;
     }
     __syncthreads();
-    apply_minv(static_cast<const __half*>(jb.L16), jb.Linv32, ntp, work, rvec, part);
+    apply_minv_f32(static_cast<const __half*>(jb.L16), jb.Linv32, ntp, wf, rvec, part);
     double dmax = 0.0, amax = 0.0;
     for (int a = tid; a < ntp; a += ST) {
-      const double d = work[a];
+      const double d = (double)wf[a];
       const double v = alpha[a] + d;
       alpha[a] = v;
       // fmax drops NaN operands: map anything non-finite to +inf so that it cannot pass for "converged"
@@ -841,7 +852,7 @@ int g_solve_mixed_smem_max = 0;
 }  // namespace
 
 static inline int solve_mixed_smem_bytes(int ntp) {
-  const int fixed = (ntp + NB + (ST / 32) * NB + 4 * 512 + ST / 32) * (int)sizeof(double);
+  const int fixed = (ntp + 4 * 512 + ST / 32) * (int)sizeof(double) + (ntp + NB + (ST / 32) * NB) * (int)sizeof(float);
   return ntp > MIXED_SMEM_NTP ? fixed : fixed + ntp * (int)(sizeof(double) + sizeof(int));
 }
 
