@@ -764,7 +764,7 @@ def SOLVE_BYTES(sweeps, tri_h, tri_c, valid_bytes):
     return (1 + sweeps) * 2 * tri_h + sweeps * SOLVE_C_PASSES * tri_c + valid_bytes
 
 
-SOLVE_C_PASSES = 2     # by rows, then by columns (solve_mixed.cu sym_matvec16)
+SOLVE_C_PASSES = 1     # every 16-byte load feeds the row dot product and the column update (solve_mixed.cu sym_matvec16_1p)
 
 
 if __name__ == "__main__":

@@ -186,6 +186,21 @@ int tb_de_set_removed(tb_ctx* ctx, const int32_t* markers, int n);
 int tb_de_ban_genome(tb_ctx* ctx, int which, int32_t* n_removed_out);
 int tb_de_evaluate_testing(tb_ctx* ctx, int slot, double h2, int mode_rule, double* fitness_out);
 
+/* ---- knockout local search (tblup/local.py:50-76, KnockoutLocalSearch.search) ------------------------------------
+ * The reference walks the markers of the best genome in order and calls evaluator.blup(genome[mask], training_indices,
+ * validation_indices, data, labels, h2) once per marker (local.py:65-66), keeping the marker out when the fitness
+ * improves (`fitness > best_fitness`, local.py:68): len(genome) sequential single evaluations.
+ * tb_knockout runs the same greedy sequence as speculative batches through the ordinary pipeline (candidate lists are
+ * built on the device; a batch is rescored from the first accepted drop on, so every decision is the reference's):
+ * genome [k] marker indices (duplicates allowed), row set `slot`, start_fitness = fitness of the whole genome;
+ * keep_out [k] receives 1 for markers that stay and 0 for knocked-out ones (the reference's `mask`),
+ * best_fitness_out the final fitness; n_evals_out (nullable) the evaluations the greedy sequence consumed (= what the
+ * reference would have run), n_batches_out (nullable) the batched pipeline passes it took.
+ * tb_knockout_scan: fitness_out[i] = blup(genome without its i-th entry) for every i (no greedy dependence). */
+int tb_knockout(tb_ctx* ctx, const int32_t* genome, int k, int slot, double h2, int mode_rule, double start_fitness,
+                uint8_t* keep_out, double* best_fitness_out, int32_t* n_evals_out, int32_t* n_batches_out);
+int tb_knockout_scan(tb_ctx* ctx, const int32_t* genome, int k, int slot, double h2, int mode_rule, double* fitness_out);
+
 #ifdef __cplusplus
 }
 #endif

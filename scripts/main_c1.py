@@ -62,6 +62,8 @@ def run_pair(n=1000, m=10000, features=1500, pop=50, gens=10, seed=0, extra=(), 
         rows = list(csv.reader(open(os.path.join(d, stem + "_results.csv"))))
         arch = json.load(open(os.path.join(d, stem + "_archive.json")))
         out[name] = {"rows": rows, "archive": arch, "seconds": time.time() - t0}
+        loc = os.path.join(d, stem + "_local.json")
+        out[name]["local"] = json.load(open(loc)) if os.path.isfile(loc) else None
         if verbose:
             print("%-9s %.1f s, %d result rows, archive keys %s" % (name, out[name]["seconds"], len(rows), sorted(arch)))
     a, b = out["reference"], out["b200"]
@@ -78,7 +80,11 @@ def run_pair(n=1000, m=10000, features=1500, pop=50, gens=10, seed=0, extra=(), 
         a["archive"][g].get("genome") == b["archive"][g].get("genome") for g in a["archive"])
     fit_gap = max((abs(a["archive"][g]["fitness"] - b["archive"][g]["fitness"]) for g in a["archive"]
                    if g in b["archive"] and "fitness" in a["archive"][g]), default=0.0)
-    out["verdict"] = {"csv_identical": same_rows, "csv_max_abs_diff": worst, "panels_identical": panels_equal,
+    local_equal = None
+    if a["local"] is not None or b["local"] is not None:
+        la, lb = a["local"] or {}, b["local"] or {}
+        local_equal = la.get("genome") == lb.get("genome") and abs(la.get("fitness", 0) - lb.get("fitness", 1)) < 1e-6
+    out["verdict"] = {"local_search_identical": local_equal, "csv_identical": same_rows, "csv_max_abs_diff": worst, "panels_identical": panels_equal,
                       "archive_fitness_max_abs_diff": fit_gap, "generations": gens, "pop": pop, "features": features,
                       "animals": n, "markers": m, "seed": seed, "extra": list(extra),
                       "reference_seconds": a["seconds"], "b200_seconds": b["seconds"]}

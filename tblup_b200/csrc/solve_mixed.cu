@@ -314,10 +314,18 @@ __device__ void apply_minv_f32(const __half* __restrict__ L, const float* __rest
 // warp-level atomics per 16 K entries of C).  The same "prefix with one aligned hole" index mapping as before.
 template <bool HOLE>
 __device__ void sym_matvec16_1p(const int16_t* __restrict__ C, int rpad, int n_t, int h0, int gap, const double* alpha,
-                                double* out, int* counter) {
+                                double amax, double* out, int* counter) {
   const int tid = threadIdx.x, lane = tid & 31;
   auto U = [&](int i) { return HOLE ? i + (i >= h0 ? gap : 0) : i; };   // compact index -> universe position
-  for (int a = tid; a < n_t; a += ST) out[a] = 0.0;
+  // The partial sums of many warps meet in out[]: they are accumulated as 64-bit FIXED-POINT integers, so the result
+  // does not depend on the order in which the warps arrive (bit-identical from run to run and for any wave size).
+  // |sum_b C_ab alpha_b| <= 32768 n_t amax =: bound < 2^ex; one quantum = 2^(ex - 62) <= bound 2^-61 -- finer than the
+  // rounding of the fp64 dot product it replaces (~ n_t 2^-53 of the same bound).
+  unsigned long long* outq = reinterpret_cast<unsigned long long*>(out);
+  const double bound = 32768.0 * (double)n_t * fmax(amax, 1e-290);
+  const int ex = ((__double2hiint(bound) >> 20) & 0x7ff) - 1022;
+  const double scale = __hiloint2double((62 - ex + 1023) << 20, 0), inv_scale = __hiloint2double((ex - 62 + 1023) << 20, 0);
+  for (int a = tid; a < n_t; a += ST) outq[a] = 0ull;
   if (tid == 0) *counter = 0;
   __syncthreads();
   constexpr int SW = 128, RU = 128;                  // strip width (4 columns per lane), rows per unit
@@ -392,14 +400,17 @@ __device__ void sym_matvec16_1p(const int16_t* __restrict__ C, int rpad, int n_t
         yv += __shfl_xor_sync(0xffffffffu, yv, 4);
         yv += __shfl_xor_sync(0xffffffffu, yv, 2);
         yv += __shfl_xor_sync(0xffffffffu, yv, 1);
-        if ((lane & 7) == 0) atomicAdd(out + r + 4 * h + 2 * (lane >> 4) + ((lane >> 3) & 1), yv);
+        if ((lane & 7) == 0)
+          atomicAdd(outq + r + 4 * h + 2 * (lane >> 4) + ((lane >> 3) & 1), (unsigned long long)__double2ll_rn(yv * scale));
       }
     }
     if (col_ok) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) atomicAdd(out + c0 + e, ac[e]);
+      for (int e = 0; e < 4; ++e) atomicAdd(outq + c0 + e, (unsigned long long)__double2ll_rn(ac[e] * scale));
     }
   }
+  __syncthreads();
+  for (int a = tid; a < n_t; a += ST) out[a] = (double)(long long)outq[a] * inv_scale;
   __syncthreads();
 }
 
@@ -407,10 +418,10 @@ __device__ void sym_matvec16_1p(const int16_t* __restrict__ C, int rpad, int n_t
 // CT: element type of the stored cross-products (int32_t, or int16_t in C16 mode).
 template <bool CONTIG, bool HOLE, typename CT>
 __device__ void sym_matvec(const CT* __restrict__ C, int rpad, int n_t, int h0, int gap, const int* tp,
-                           const double* alpha, double* work, double* part2) {
+                           const double* alpha, double amax, double* work, double* part2) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if constexpr (CONTIG && sizeof(CT) == 2) {
-    sym_matvec16_1p<HOLE>(reinterpret_cast<const int16_t*>(C), rpad, n_t, h0, gap, alpha, work,
+    sym_matvec16_1p<HOLE>(reinterpret_cast<const int16_t*>(C), rpad, n_t, h0, gap, alpha, amax, work,
                           reinterpret_cast<int*>(part2));
   } else if constexpr (CONTIG) {
     // rows: (C alpha)_a += sum_{b <= a} C[a][b] alpha_b, 16-byte loads, four in flight
@@ -580,15 +591,18 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
   bool solved = false;               // refinement reached the tolerance (else the host re-runs the job in fp64)
   double sa = 0.0, ssa = 0.0, prev_dmax = 1e300;
   for (;;) {
-    double l0 = 0.0, l1 = 0.0;
+    double l0 = 0.0, l1 = 0.0, l2 = 0.0;
     for (int a = tid; a < n_t; a += ST) {
       l0 += alpha[a];
       l1 += (double)jb.s[tp[a]] * alpha[a];
+      l2 = fmax(l2, fabs(alpha[a]) < 1e300 ? fabs(alpha[a]) : __longlong_as_double(0x7ff0000000000000LL));
     }
     sa = block_sum(l0, red);
     ssa = block_sum(l1, red);
+    const double amax_now = block_max(l2, red);
     if (sweeps == MAX_SWEEPS) break;
-    sym_matvec<CONTIG, HOLE, CT>(C, rpad, n_t, jb.hole0, jb.gap, tp, alpha, work, part2);      // work[a] = (C alpha)_a, a < n_t
+    if (!(amax_now < 1e300)) break;                     // non-finite first solve (overflowing factor): leave it to fp64
+    sym_matvec<CONTIG, HOLE, CT>(C, rpad, n_t, jb.hole0, jb.gap, tp, alpha, amax_now, work, part2);      // work[a] = (C alpha)_a, a < n_t
     for (int a = tid; a < ntp; a += ST) {
       double rr = 0.0;
       if (a < n_t) {

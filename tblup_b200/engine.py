@@ -170,6 +170,26 @@ class GblupEngine:
         self._n_staged = P
         return out
 
+    # -- knockout local search (tblup/local.py:50-76) -------------------------------------------
+    def knockout(self, genome, start_fitness, slot=0, h2=0.4, mode=MODE_AUTO):
+        """Greedy knockout of the reference's ``KnockoutLocalSearch.search``: returns (keep mask, best fitness,
+        evaluations consumed, batched passes)."""
+        flat, _ = pack_genomes([genome], self.m)
+        keep = np.ones(flat.size, dtype=np.uint8)
+        best, n_ev, n_b = C.c_double(0.0), C.c_int32(0), C.c_int32(0)
+        self._check(self._lib.tb_knockout(self._ctx, flat.ctypes.data, flat.size, int(slot), float(h2), int(mode),
+                                          float(start_fitness), keep.ctypes.data, C.byref(best), C.byref(n_ev),
+                                          C.byref(n_b)), "tb_knockout")
+        return keep.astype(bool), float(best.value), int(n_ev.value), int(n_b.value)
+
+    def knockout_scan(self, genome, slot=0, h2=0.4, mode=MODE_AUTO):
+        """Fitness of every leave-one-out list of ``genome`` (one batched pass per 1 024 markers)."""
+        flat, _ = pack_genomes([genome], self.m)
+        out = np.empty(flat.size, dtype=np.float64)
+        self._check(self._lib.tb_knockout_scan(self._ctx, flat.ctypes.data, flat.size, int(slot), float(h2), int(mode),
+                                               out.ctypes.data), "tb_knockout_scan")
+        return out
+
     # -- diagnostics ---------------------------------------------------------------------------
     def gram_debug(self, indices, rows, impl="tc"):
         flat, _ = pack_genomes([indices], self.m)

@@ -38,4 +38,19 @@ def install(tblup_module=None):
                 setattr(ours, n, saved[n])
 
     tblup_module.get_evaluator = get_evaluator
+    # knockout local search (main.py:7,42-45 imports tblup.local.get_local_search when it runs): the batched device
+    # search; the class also derives from the reference's so isinstance checks keep holding
+    from . import local as ours_local
+    ref_local = getattr(tblup_module, "local", None)
+    if ref_local is not None and hasattr(ref_local, "KnockoutLocalSearch"):
+        hybrid_ko = type("KnockoutLocalSearch", (ours_local.KnockoutLocalSearch, ref_local.KnockoutLocalSearch),
+                         {"__module__": __name__})
+
+        def get_local_search(args, population):
+            if args.local_search == args.LOCAL_SEARCH_KNOCKOUT:
+                return hybrid_ko(population)
+            raise NotImplementedError("Local search method {} not implemented.".format(args.local_search))
+
+        ref_local.get_local_search = get_local_search
+        tblup_module.get_local_search = get_local_search
     return get_evaluator

@@ -123,3 +123,22 @@ def test_removal_restatement_matches_reference_handler():
         for g, i in zip(to_eval, idx):
             assert np.array_equal(g, D.filtered_genome(pop[i].genome, want_removed))
         assert np.array_equal(h.combine_with_removed(pop[2].genome), D.testing_genome(pop[2].genome, want_removed))
+
+
+@pytest.mark.parametrize("name", ["ko_small", "ko_removed"])
+def test_knockout_restatement_matches_reference_search(name):
+    """oracle.knockout_oracle.ref_knockout against the live reference's KnockoutLocalSearch.search() recorded by
+    tests/golden/make_golden_ko.py: same knocked-out markers, same final fitness, same per-step candidate fitness --
+    with the reference-faithful blup and with the exact-integer one."""
+    from oracle import knockout_oracle as K
+    g = load_golden(name)
+    x, y, h2 = g["x"], g["y"], float(g["h2"])
+    xf = x.astype(np.float64)
+    for c in range(int(g["n_cases"])):
+        genome = np.union1d(g["genome%d" % c], g["removed"]).astype(int)     # combine_with_removed (local.py:55)
+        for blup, data, tol in ((O.ref_blup, xf, 1e-12), (O.exact_blup, x, 1e-9)):
+            keep, best, trace = K.ref_knockout(genome, float(g["start_fitness%d" % c]), list(g["train"]), list(g["valid"]),
+                                               data, y, h2, blup=blup)
+            assert np.array_equal(genome[keep], g["kept%d" % c])
+            assert abs(best - float(g["best_fitness%d" % c])) < tol
+            assert np.abs(trace - g["trace%d" % c]).max() < tol
