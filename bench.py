@@ -191,7 +191,9 @@ class ReferenceArm:
             np.asscalar = lambda a: a.item()
         _single_thread_blas()
         import tblup
-        self.tmp, gp, pp = _write_dataset(x, y, as_float=True)
+        # float64 as the reference expects (snp_blup subtracts in place, evaluator.py:306-309); a matrix beyond ~16 GB of
+        # float64 (config 4: 80 GB) is handed over as int8, which only the gblup branch accepts
+        self.tmp, gp, pp = _write_dataset(x, y, as_float=x.size * 8 <= (16 << 30))
         # every worker np.load()s the float64 matrix privately (evaluator.py:215): bound the pool by host memory
         try:
             import psutil

@@ -73,6 +73,10 @@ int tb_create(const int8_t* geno, int n, int m, const double* y, const int32_t* 
 int tb_create_ex(const void* geno, int layout, int storage, int n, int m, const double* y, const int32_t* perm,
                  int device, tb_ctx** out);
 int tb_destroy(tb_ctx* ctx);
+/* A context on another GPU of the same box holding the same data set, filled by a device-to-device copy of the resident
+ * matrix and column sums (NVLink peer copy) instead of a second host ingest -- the reference has every worker np.load()
+ * the matrix again (tblup/evaluator.py:215-216).  Row sets are defined on the clone with tb_set_rowset as usual. */
+int tb_clone(const tb_ctx* src, int device, tb_ctx** out);
 /* resident genotype bytes and storage kind (TB_STORE_*) of a context */
 int tb_storage_info(const tb_ctx* ctx, int* storage, uint64_t* bytes);
 

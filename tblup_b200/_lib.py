@@ -21,6 +21,7 @@ SYMBOLS = {
                                C.POINTER(C.c_void_p)]),
     "tb_storage_info": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "tb_destroy": (C.c_int, [C.c_void_p]),
+    "tb_clone": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "tb_set_rowset": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "tb_stage_genomes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "tb_eval_staged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_int]),

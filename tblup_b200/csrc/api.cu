@@ -704,16 +704,31 @@ int tb_create_ex(const void* geno_any, int layout, int storage, int n, int m, co
     }
     for (int p0 = 0; p0 < n && !cuda_bad && !bad_value; p0 += chunk) {
       const int rows = std::min(chunk, n - p0);
-      unsigned char maxv = 0;
-      for (int r = 0; r < rows; ++r) {
-        const int8_t* src = geno + (size_t)p[p0 + r] * m;
-        int8_t* dst = h_stage + (size_t)r * m;
-        for (int j = 0; j < m; ++j) {
-          const int8_t v = src[j];
-          dst[j] = v;
-          maxv = std::max(maxv, (unsigned char)v);   // negative values map to >= 128
+      // copy + validate the chunk with several host threads (the byte loop was the whole cost of creating a context at
+      // config 4's 10 GB; rows are independent)
+      const int nt = (int)std::max<size_t>(1, std::min<size_t>(16, std::min<size_t>(std::thread::hardware_concurrency(),
+                                                                                  ((size_t)rows * m) >> 22)));
+      std::vector<unsigned char> tmax(nt, 0);
+      auto work = [&](int t) {
+        unsigned char mx = 0;
+        for (int r = t; r < rows; r += nt) {
+          const int8_t* src = geno + (size_t)p[p0 + r] * m;
+          int8_t* dst = h_stage + (size_t)r * m;
+          memcpy(dst, src, (size_t)m);
+          unsigned char rowmax = 0;
+          for (int j = 0; j < m; ++j) rowmax = std::max(rowmax, (unsigned char)src[j]);   // negative values map to >= 128
+          mx = std::max(mx, rowmax);
         }
+        tmax[t] = mx;
+      };
+      {
+        std::vector<std::thread> th;
+        for (int t = 1; t < nt; ++t) th.emplace_back(work, t);
+        work(0);
+        for (auto& x : th) x.join();
       }
+      unsigned char maxv = 0;
+      for (int t = 0; t < nt; ++t) maxv = std::max(maxv, tmax[t]);
       if (maxv > 2) {
         bad_value = true;
         break;
@@ -784,6 +799,80 @@ int tb_create_ex(const void* geno_any, int layout, int storage, int n, int m, co
       chk(tb_solve_init(), "solve kernel init") ||
       chk(tb_chol_tc_init(), "tensor-core cholesky init") || chk(tb_solve_mixed_init(), "mixed solve init") ||
       chk(tb_gather_init(), "gather init"))
+    return bail("");
+  *out = c;
+  return 0;
+}
+
+// A second context on another GPU of the box without a second ingest: the resident genotype matrix (already validated,
+// permuted, transposed and packed) and the column sums are copied device to device (NVLink / NVSwitch peer copy).
+// Row sets are not copied -- the caller defines them with tb_set_rowset as on any context.
+int tb_clone(const tb_ctx* src, int device, tb_ctx** out) {
+  if (!out) return -1;
+  *out = nullptr;
+  if (!src) {
+    g_create_err = "tb_clone: null source context";
+    return -1;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    g_create_err = "tb_clone: bad device ordinal";
+    return -1;
+  }
+  cudaDeviceProp prop;
+  cudaGetDeviceProperties(&prop, device);
+  if (prop.major != 10) {
+    g_create_err = "tb_clone: target device is not sm_100";
+    return -3;
+  }
+  cudaSetDevice(src->device);
+  cudaStreamSynchronize(src->stream);
+  TbCtx* c = new TbCtx();
+  auto bail = [&](const std::string& msg) {
+    g_create_err = msg.empty() ? c->err : msg;
+    tb_destroy(c);
+    return -2;
+  };
+  c->device = device;
+  c->n = src->n;
+  c->m = src->m;
+  c->ldn = src->ldn;
+  c->storage = src->storage;
+  c->n_sm = prop.multiProcessorCount;
+  c->y_univ = src->y_univ;
+  c->pos_of = src->pos_of;
+  if (cudaSetDevice(device) != cudaSuccess) return bail("cudaSetDevice failed");
+  auto chk = [&](cudaError_t ce, const char* what) {
+    if (ce == cudaSuccess) return false;
+    c->err = std::string(what) + ": " + cudaGetErrorString(ce);
+    return true;
+  };
+  if (device != src->device) {
+    int can = 0;
+    cudaDeviceCanAccessPeer(&can, device, src->device);
+    if (can) {
+      cudaError_t pe = cudaDeviceEnablePeerAccess(src->device, 0);
+      if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled) (void)pe;
+      cudaGetLastError();     // "already enabled" is not an error
+    }
+  }
+  if (chk(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking), "cudaStreamCreate")) return bail("");
+  c->stream = c->own_stream;
+  const size_t bytes = (size_t)c->m * (size_t)(c->storage == TB_STORE_PACKED2 ? c->ldn / 4 : c->ldn);
+  void* dst = nullptr;
+  if (chk(cudaMalloc(&dst, bytes), "cudaMalloc genotypes")) return bail("");
+  const void* from = c->storage == TB_STORE_PACKED2 ? (const void*)src->d_x2 : (const void*)src->d_x;
+  if (c->storage == TB_STORE_PACKED2) c->d_x2 = static_cast<uint8_t*>(dst);
+  else c->d_x = static_cast<int8_t*>(dst);
+  if (chk(cudaMalloc(&c->d_colsum_all, (size_t)c->m * sizeof(int)), "cudaMalloc colsum")) return bail("");
+  if (chk(cudaMemcpyPeerAsync(dst, device, from, src->device, bytes, c->stream), "peer copy genotypes")) return bail("");
+  if (chk(cudaMemcpyPeerAsync(c->d_colsum_all, device, src->d_colsum_all, src->device, (size_t)c->m * sizeof(int), c->stream),
+          "peer copy colsum"))
+    return bail("");
+  if (chk(cudaStreamSynchronize(c->stream), "peer copy")) return bail("");
+  if (chk(tb_gram_tc_init(), "gram kernel init") || chk(tb_chol_init(), "cholesky kernel init") ||
+      chk(tb_solve_init(), "solve kernel init") || chk(tb_chol_tc_init(), "tensor-core cholesky init") ||
+      chk(tb_solve_mixed_init(), "mixed solve init") || chk(tb_gather_init(), "gather init"))
     return bail("");
   *out = c;
   return 0;

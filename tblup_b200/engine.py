@@ -100,6 +100,19 @@ class GblupEngine:
         self._n_staged = 0
 
     # -- lifetime ------------------------------------------------------------------------------
+    def clone(self, device):
+        """The same data set on another GPU of the box: device-to-device copy of the resident matrix (tb_clone), no
+        second host ingest.  Row sets have to be defined on the clone."""
+        other = object.__new__(GblupEngine)
+        other._lib = self._lib
+        other._ctx = C.c_void_p()
+        rc = self._lib.tb_clone(self._ctx, int(device), C.byref(other._ctx))
+        if rc != 0:
+            other._ctx = C.c_void_p()
+            raise RuntimeError("tb_clone failed (%d): %s" % (rc, self._lib.tb_last_error(None).decode()))
+        other.n, other.m, other.storage, other.device, other._n_staged = self.n, self.m, self.storage, int(device), 0
+        return other
+
     def close(self):
         if getattr(self, "_ctx", None) is not None and self._ctx:
             self._lib.tb_destroy(self._ctx)

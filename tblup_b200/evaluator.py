@@ -161,8 +161,13 @@ class BlupParallelEvaluator(ParallelEvaluator):
         order = np.concatenate((self.training_indices, self.validation_indices, self.testing_indices)).astype(np.int64)
         if len(np.unique(order)) != self.n_samples:      # a custom splitter may not cover every animal
             order = np.concatenate((order, np.setdiff1d(np.arange(self.n_samples), order)))
+        # one ingest (validate, permute, transpose, pack) on the first device; the other GPUs of the box receive the
+        # resident matrix by a device-to-device copy (the reference has every worker np.load() the file, :215-216)
         for device in self.devices:
-            self.consumers.append(GblupEngine(geno, pheno, perm=order, device=device, storage=self.storage))
+            if self.consumers and hasattr(self.consumers[0], "clone"):
+                self.consumers.append(self.consumers[0].clone(device))
+            else:
+                self.consumers.append(GblupEngine(geno, pheno, perm=order, device=device, storage=self.storage))
         self._define_rowsets()
         return self
 

@@ -144,3 +144,25 @@ def test_fp4_and_int8_gram_give_identical_fitness(engines):
     nt = len(g["train"])
     assert np.array_equal(np.tril(ca)[:, :nt], np.tril(cb)[:, :nt])
     assert np.array_equal(a, b)
+
+
+def test_clone_holds_the_same_resident_data():
+    """tb_clone: a second context filled by a device-to-device copy (same GPU here; tests/test_gpu_large.py covers two
+    GPUs) gives bit-identical cross-products and fitness."""
+    from tblup_b200 import GblupEngine, engine as E, synth
+    n, m = 500, 3000
+    x, y = synth.synth_dataset(n, m, h2=0.4, seed=51)
+    tr, va, te = synth.split_indices(n, seed=51)
+    rng = np.random.default_rng(51)
+    genomes = [rng.choice(m, size=kk, replace=False) for kk in (100, 501, 900)]
+    for storage in ("packed2", "int8"):
+        with GblupEngine(x, y, perm=np.concatenate([tr, va, te]), storage=storage) as a:
+            a.set_rowset(0, tr, va)
+            with a.clone(0) as b:
+                b.set_rowset(0, tr, va)
+                assert b.resident_genotype_bytes() == a.resident_genotype_bytes()
+                impl = "fp4" if storage == "packed2" else "tc"
+                assert np.array_equal(a.gram_debug(genomes[1], 400, impl=impl), b.gram_debug(genomes[1], 400, impl=impl))
+                fa = a.evaluate(genomes, slots=[0], mode=E.MODE_AUTO)
+                fb = b.evaluate(genomes, slots=[0], mode=E.MODE_AUTO)
+                assert np.array_equal(fa, fb)
