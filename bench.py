@@ -29,7 +29,7 @@ import sys
 import threading
 import time
 
-if "reference" in sys.argv[1:]:
+if "reference" in sys.argv[1:] and "c4_" not in " ".join(sys.argv[1:]):
     # the reference's deployment: one single-threaded BLAS per worker process (generate_sbs.py:25 exports
     # OMP_NUM_THREADS=1).  Its workers are FORKED from this process, so the limit must be in place before numpy loads.
     for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
@@ -48,9 +48,9 @@ WORKLOADS = {
     "c3_5000x50000_k5001_pop1000_10fold": dict(n=5000, m=50000, k=5001, pop=1000, folds=10),
     # config 4 (large-n regime): 20 000 x 500 000, k = 50 000; BASELINE states pop = 500 (on 8 GPUs: 63 per GPU)
     "c4_20000x500000_k50000_pop500": dict(n=20000, m=500000, k=50000, pop=500, folds=1, fast_synth=True,
-                                          parity_genomes=2, cpu_sample=2, cpu_threads_per_worker=0),
+                                          parity_genomes=2, cpu_sample=1),
     "c4_20000x500000_k50000_pop32": dict(n=20000, m=500000, k=50000, pop=32, folds=1, fast_synth=True,
-                                         parity_genomes=2, cpu_sample=2, cpu_threads_per_worker=0),
+                                         parity_genomes=2, cpu_sample=1),
     "tiny": dict(n=300, m=2000, k=400, pop=16, folds=1),
     "tiny_3fold": dict(n=300, m=2000, k=400, pop=16, folds=3),
 }
@@ -195,13 +195,18 @@ class ReferenceArm:
         # float64 (config 4: 80 GB) is handed over as int8, which only the gblup branch accepts
         self.tmp, gp, pp = _write_dataset(x, y, as_float=x.size * 8 <= (16 << 30))
         # every worker np.load()s the float64 matrix privately (evaluator.py:215): bound the pool by host memory
+        want = cores
         try:
             import psutil
             avail = psutil.virtual_memory().available
-            cores = max(1, min(cores, int(0.6 * avail / max(1, x.size * 8))))
+            # per worker: its private copy of the matrix + the float64 gather, centred copy and GRM of one evaluation
+            per_worker = x.size * (8 if x.size * 8 <= (16 << 30) else 1) + 3 * 8 * x.shape[0] * max(x.shape[0], 1)
+            cores = max(1, min(cores, int(0.6 * avail / max(1, per_worker))))
         except Exception:
             pass
         self.cores = cores
+        # when memory allows fewer workers than cores, each worker's BLAS gets the idle cores (stated in `sample`)
+        self.blas_threads = max(1, want // cores)
         random.seed(0)
         np.random.seed(0)
         if folds == 1:
@@ -216,14 +221,14 @@ class ReferenceArm:
         self._blas_limit = None
         try:
             from threadpoolctl import threadpool_limits
-            self._blas_limit = threadpool_limits(limits=1)
+            self._blas_limit = threadpool_limits(limits=self.blas_threads)
         except Exception:
             pass
         self.ev.__enter__()
         if self._blas_limit is not None:
             self._blas_limit.restore_original_limits()
-        self.what = ("reference %s with its own %d-process worker pool (tblup/evaluator.py), 1 BLAS thread per worker"
-                     % (type(self.ev).__name__, cores))
+        self.what = ("reference %s with its own %d-process worker pool (tblup/evaluator.py), %d BLAS thread(s) per worker"
+                     % (type(self.ev).__name__, cores, self.blas_threads))
 
     def step(self, genomes):
         pop = [_Indv(np.asarray(g).astype(int)) for g in genomes]
