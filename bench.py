@@ -87,6 +87,7 @@ def parse():
     ap.add_argument("--storage", default="packed2", choices=["int8", "packed2"],
                     help="resident genotype format: int8 dosages, or 2 bits per dosage (bit-identical results)")
     ap.add_argument("--cpu-sample", type=int, default=0, help="individuals in the CPU sample (default: one per core)")
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value (A/B experiments), e.g. fuse_in_gram=1")
     ap.add_argument("--cpu-kind", default="auto", choices=["auto", "reference", "port"],
                     help="CPU arm: the staged reference's own evaluator + worker pool (oracle/_ref), or the oracle port")
     return ap.parse_args()
@@ -179,7 +180,7 @@ def _single_thread_blas():
 class ReferenceArm:
     kind = "reference"
 
-    def __init__(self, x, y, train, valid, cores, folds=1):
+    def __init__(self, x, y, train, valid, cores, folds=1, max_workers=0):
         import random
         from oracle import stage_ref
         ref = stage_ref.ref_path()
@@ -196,6 +197,8 @@ class ReferenceArm:
         self.tmp, gp, pp = _write_dataset(x, y, as_float=x.size * 8 <= (16 << 30))
         # every worker np.load()s the float64 matrix privately (evaluator.py:215): bound the pool by host memory
         want = cores
+        if max_workers:
+            cores = max(1, min(cores, max_workers))     # no more workers than genomes in the sample
         try:
             import psutil
             avail = psutil.virtual_memory().available
@@ -254,7 +257,7 @@ def _port_worker(job):
 class PortArm:
     kind = "port"
 
-    def __init__(self, x, y, train, valid, cores, folds=1):
+    def __init__(self, x, y, train, valid, cores, folds=1, max_workers=0):
         import multiprocessing as mp
         from oracle import gblup_oracle as O
         _single_thread_blas()
@@ -277,10 +280,10 @@ class PortArm:
         self.tmp.cleanup()
 
 
-def make_cpu_arm(kind, x, y, train, valid, cores, folds):
+def make_cpu_arm(kind, x, y, train, valid, cores, folds, max_workers=0):
     if kind in ("auto", "reference"):
         try:
-            return ReferenceArm(x, y, train, valid, cores, folds)
+            return ReferenceArm(x, y, train, valid, cores, folds, max_workers)
         except Exception as exc:
             if kind == "reference":
                 raise
@@ -365,7 +368,7 @@ def reference_main(args, wl, rank, cores):
     x, y = (synth.synth_dataset_fast if wl.get("fast_synth") else synth.synth_dataset)(n, m, h2=H2, seed=0)
     train, valid, test = synth.split_indices(n, seed=0)
     sample = args.cpu_sample or wl.get("cpu_sample") or cores
-    arm = make_cpu_arm(args.cpu_kind, x, y, train, valid, cores, folds)
+    arm = make_cpu_arm(args.cpu_kind, x, y, train, valid, cores, folds, max_workers=sample)
     try:
         flat, off = synth.random_genomes(sample * (args.steps + args.warmup), m, k, seed=100)
         gens = [flat[off[i]:off[i + 1]] for i in range(off.size - 1)]
@@ -437,6 +440,9 @@ def main():
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
     eng.set_precision(args.precision)
+    for kv in args.opt:
+        name, val = kv.split("=")
+        eng.set_option(name, int(val))
     S = len(slots)
     slots_np = np.asarray(slots, dtype=np.int32)
 
@@ -592,7 +598,7 @@ def main():
         pf, po = prim["pinned"][prim["last_batch"]]
         flat, off = pf.numpy(), po.numpy()
         gens = [flat[off[i]:off[i + 1]] for i in range(min(sample, p_primary))]
-        arm = make_cpu_arm(args.cpu_kind, x, y, train, valid, cores, folds)
+        arm = make_cpu_arm(args.cpu_kind, x, y, train, valid, cores, folds, max_workers=len(gens))
         try:
             dt, cpu_fit = arm.step(gens)
         finally:

@@ -229,7 +229,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     TB_CUDA(c, cudaMemsetAsync(c->d_fail, 0, need * sizeof(int), c->stream));
     per_ind = 0;
     for (int s = 0; s < n_slots; ++s)
-      per_ind += (size_t)max_ntp * max_ntp * (sizeof(float) + 2) + (size_t)max_ntp * TB_NB * sizeof(float) +
+      per_ind += (size_t)max_ntp * max_ntp * (sizeof(float) + 2) + (size_t)max_ntp * (TB_NB + 2) * sizeof(float) + 256 +
                  (size_t)256 * 256 * sizeof(float) +
                  (size_t)(max_ntp + sv[s].rs->n_v) * sizeof(double) + 1024;
   }
@@ -315,7 +315,13 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     float* d_Linv32 = nullptr;
     unsigned short* d_L16 = nullptr;
     float* d_Linv256 = nullptr;
+    float* d_terms = nullptr;
+    float2* d_coef = nullptr;
     if (mixed) {
+      if (fuse_scale) {
+        d_terms = ar.take<float>((size_t)n_jobs * 2 * max_ntp);
+        d_coef = ar.take<float2>(n_jobs);
+      }
       if (c->wide_panel) d_Linv256 = ar.take<float>((size_t)n_jobs * 256 * 256);
       d_L32 = ar.take<float>(((size_t)n_jobs * max_ntp + 128) * max_ntp);
       d_Linv32 = ar.take<float>((size_t)n_jobs * max_ntp * TB_NB);
@@ -459,8 +465,10 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     sp = span_begin(c, TB_ST_GRAM);
     {
       std::string e;
+      // (the Gram no longer writes the scaled matrix: with fuse_scale the Cholesky updates form it from C on the fly)
       cudaError_t ce = tb_launch_gram_tc(d_panel, Wc, rpad, kstride_b, d_kb, d_tiles, n_tiles, d_C, c->n_sm, st, &e,
-                                         fuse_scale ? d_scale : nullptr, d_L32, max_ntp, c16 ? 1 : 0, fp4 ? 1 : 0);
+                                         (fuse_scale && c->fuse_in_gram) ? d_scale : nullptr, d_L32, max_ntp, c16 ? 1 : 0,
+                                         fp4 ? 1 : 0);
       if (ce != cudaSuccess) return fail(c, "gram launch: " + (e.empty() ? std::string(cudaGetErrorString(ce)) : e), -2);
     }
     span_end(c, sp);
@@ -468,11 +476,26 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     if (c->stop_after == TB_ST_GRAM) continue;
 
     if (mixed) {
-      if (!fuse_scale) {
+      const bool from_c = fuse_scale && !c->fuse_in_gram && c->stop_after < 0;
+      TbFromC fc{};
+      if (!fuse_scale || (fuse_scale && !c->fuse_in_gram)) {
         sp = span_begin(c, TB_ST_SCALE);
-        TB_CUDA(c, tb_launch_scale32(d_scale, n_jobs, max_ntp, d_L32, c16 ? 1 : 0, st));
+        if (from_c) {
+          // only the first outer block column is written here; every later one is formed inside its own update
+          TB_CUDA(c, tb_launch_fuse_terms(d_scale, n_jobs, max_ntp, d_terms, d_coef, st));
+          TB_CUDA(c, tb_launch_scale32(d_scale, n_jobs, max_ntp, d_L32, c16 ? 1 : 0, st, 256));
+          count(c, TB_ST_SCALE, 2);
+          fc.C = d_C;
+          fc.terms = d_terms;
+          fc.coef = d_coef;
+          fc.rpad = rpad;
+          fc.c16 = c16 ? 1 : 0;
+          fc.n_t = sv[0].rs->n_t;
+        } else {
+          TB_CUDA(c, tb_launch_scale32(d_scale, n_jobs, max_ntp, d_L32, c16 ? 1 : 0, st));
+          count(c, TB_ST_SCALE, 1);
+        }
         span_end(c, sp);
-        count(c, TB_ST_SCALE, 1);
       }
       if (c->stop_after == TB_ST_SCALE) continue;
       {
@@ -480,7 +503,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
         std::string e;
         MarkCtx mc{c, 0};
         cudaError_t ce = tb_chol_tc_factor(d_L32, d_Linv32, d_L16, d_Linv256, d_status, n_jobs, max_ntp, c->n_sm, st, nl, &e,
-                                           c->profile ? &mark_cb : nullptr, &mc);
+                                           c->profile ? &mark_cb : nullptr, &mc, from_c ? &fc : nullptr);
         if (ce != cudaSuccess)
           return fail(c, "tensor-core Cholesky: " + (e.empty() ? std::string(cudaGetErrorString(ce)) : e), -2);
         count(c, TB_ST_CHOL_UPDATE, mc.n_update);
@@ -1228,6 +1251,7 @@ int tb_set_option(tb_ctx* c, const char* name, long long value) {
   else if (s == "max_wave") c->max_wave = (int)value;
   else if (s == "precision") c->precision = value != 0;
   else if (s == "fuse_scale") c->fuse_scale = value != 0;
+  else if (s == "fuse_in_gram") c->fuse_in_gram = value != 0;
   else if (s == "wide_panel") c->wide_panel = value != 0;
   else if (s == "narrow_c") c->narrow_c = value != 0;
   else if (s == "gram_fp4") c->gram_fp4 = value != 0;

@@ -61,6 +61,8 @@ struct GemmParams {
   int skip32;        // mode 1 only: do not write the fp32 copy (nothing reads these entries of L32 again)
   float* L32;
   __half* L16;       // optional half-precision copy of the final factor entries (read by the solve)
+  int from_c;        // mode 0 only: the matrix entries come from the integer cross-products (TbFromC), not from L32
+  TbFromC fc;
 };
 
 struct TBarriers {
@@ -108,7 +110,9 @@ __device__ __forceinline__ float round_tf32(float x) {
   return __uint_as_float(r);
 }
 
-template <bool F16>
+// SRC: where update mode reads the entries it modifies -- 0: the fp32 matrix L32, 1: int16 cross-products, 2: int32
+// cross-products (TbFromC: the scaled matrix is formed on the fly)
+template <bool F16, int SRC>
 __global__ void __launch_bounds__(T_THREADS, 1)
 tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ GemmParams p) {
@@ -216,14 +220,42 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int r_hi = p.row0 + mt * TBM + TBM - 1;
       float* crow = p.L32 + ((size_t)job * p.ntp + (r < p.row_end ? r : 0)) * p.ntp + p.c_col0 + half * nch * 32;
       const int col_base = p.c_col0 + half * nch * 32;
-      float4 cv[4][8];
-      if (p.mode == 0) {
+      float4 cv[4][SRC == 1 ? 4 : 8];
+      float f_scale = 0.f, f_lam = 0.f, f_rt = 0.f;
+      const float* f_ct = nullptr;
+      if (SRC != 0) {
+        // the entries of A this thread needs, as integer cross-products (8 or 16 bytes per 4 entries instead of a
+        // read of an fp32 matrix somebody had to write): cv holds the RAW bits until the accumulator is there
+        const float2 cf = p.fc.coef[job];
+        f_scale = cf.x;
+        f_lam = cf.y;
+        f_rt = p.fc.terms[(size_t)job * 2 * p.ntp + (r < p.row_end ? r : 0)];
+        f_ct = p.fc.terms + (size_t)job * 2 * p.ntp + p.ntp + col_base;
+        const size_t coff = ((size_t)job * p.fc.rpad + (r < p.row_end ? r : 0)) * p.fc.rpad + col_base;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          if (i < nch && col_base + i * 32 <= r_hi && r < p.row_end) {
+            if (SRC == 1) {
+              const uint4* src = reinterpret_cast<const uint4*>(static_cast<const int16_t*>(p.fc.C) + coff + i * 32);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const uint4 u = src[j];
+                cv[i][j] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
+              }
+            } else {
+              const float4* src = reinterpret_cast<const float4*>(static_cast<const int32_t*>(p.fc.C) + coff + i * 32);
+#pragma unroll
+              for (int j = 0; j < (SRC == 1 ? 4 : 8); ++j) cv[i][j] = src[j];
+            }
+          }
+        }
+      } else if (p.mode == 0) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (i < nch && col_base + i * 32 <= r_hi && r < p.row_end) {
             const float4* src = reinterpret_cast<const float4*>(crow + i * 32);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) cv[i][j] = src[j];
+            for (int j = 0; j < (SRC == 1 ? 4 : 8); ++j) cv[i][j] = src[j];
           }
         }
       }
@@ -240,9 +272,42 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * MAX_N + (half * nch + i) * 32, v);
         tmem_ld_wait();
         uint32_t o[32];
-        if (p.mode == 0) {
+        if (SRC != 0) {
+          // A_rb = scale C_rb + rowterm_r + colterm_b (+ lambda on the diagonal; identity on the padding rows), T = A - acc
+          const int b0 = col_base + i * 32;
+          const bool real_row = r < p.fc.n_t;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
+            const float4 ct = *reinterpret_cast<const float4*>(f_ct + i * 32 + 4 * j);
+            float cx[4];
+            if (SRC == 1) {
+              const float4 raw = cv[i][j >> 1];
+              const uint32_t w0 = (j & 1) ? __float_as_uint(raw.z) : __float_as_uint(raw.x);
+              const uint32_t w1 = (j & 1) ? __float_as_uint(raw.w) : __float_as_uint(raw.y);
+              // integers below 2^23: 0x4b000000 | c is the float 2^23 + c (no converter pipe)
+              cx[0] = __uint_as_float(0x4b000000u | (w0 & 0xffffu)) - 8388608.f;
+              cx[1] = __uint_as_float(0x4b000000u | (w0 >> 16)) - 8388608.f;
+              cx[2] = __uint_as_float(0x4b000000u | (w1 & 0xffffu)) - 8388608.f;
+              cx[3] = __uint_as_float(0x4b000000u | (w1 >> 16)) - 8388608.f;
+            } else {
+              const float4 raw = cv[i][SRC == 1 ? 0 : j];
+              cx[0] = __uint_as_float(0x4b000000u | __float_as_uint(raw.x)) - 8388608.f;
+              cx[1] = __uint_as_float(0x4b000000u | __float_as_uint(raw.y)) - 8388608.f;
+              cx[2] = __uint_as_float(0x4b000000u | __float_as_uint(raw.z)) - 8388608.f;
+              cx[3] = __uint_as_float(0x4b000000u | __float_as_uint(raw.w)) - 8388608.f;
+            }
+            const float ctv[4] = {ct.x, ct.y, ct.z, ct.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int b = b0 + 4 * j + e;
+              float a = real_row ? fmaf(cx[e], f_scale, f_rt + ctv[e]) : 0.f;
+              if (b == r) a = real_row ? a + f_lam : 1.f;
+              o[4 * j + e] = __float_as_uint(a - __uint_as_float(v[4 * j + e]));
+            }
+          }
+        } else if (p.mode == 0) {
+#pragma unroll
+          for (int j = 0; j < (SRC == 1 ? 4 : 8); ++j) {
             o[4 * j] = __float_as_uint(cv[i][j].x - __uint_as_float(v[4 * j]));
             o[4 * j + 1] = __float_as_uint(cv[i][j].y - __uint_as_float(v[4 * j + 1]));
             o[4 * j + 2] = __float_as_uint(cv[i][j].z - __uint_as_float(v[4 * j + 2]));
@@ -766,11 +831,15 @@ cudaError_t tb_chol_tc_init() {
     if (!fn || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
     g_encode32 = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  cudaError_t e = cudaFuncSetAttribute(tf32_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(tf32_gemm_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(trinv256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRINV_SMEM);
   if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(tf32_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
+  e = cudaFuncSetAttribute(tf32_gemm_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(tf32_gemm_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(tf32_gemm_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
 }
 
 // Factor every job's fp32 matrix in place.  L32: [n_jobs * ntp + 128 slack rows][ntp]; Linv32: [n_jobs * ntp][64].
@@ -778,7 +847,7 @@ cudaError_t tb_chol_tc_init() {
 // launches[0] / launches[1] receive the number of GEMM / diagonal-block kernel launches.
 cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, float* Linv256, int* status, int n_jobs, int ntp,
                               int n_sm, cudaStream_t st, int* launches, std::string* err,
-                              void (*mark)(void*, int, int), void* mark_ctx) {
+                              void (*mark)(void*, int, int), void* mark_ctx, const TbFromC* from_c) {
   CUtensorMap tm_l, tm_inv, tm_inv256;
   cudaError_t e = encode_f32(&tm_l, L32, (size_t)ntp, (size_t)n_jobs * ntp + 128, err);
   if (e != cudaSuccess) return e;
@@ -805,10 +874,14 @@ cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, float* Linv2
     if (p.n_mtiles <= 0 || p.K <= 0) return cudaSuccess;
     const int items = n_jobs * p.n_mtiles;
     const int grid = items < n_sm ? items : n_sm;
-    if (p.mode == 0 && upd16)
-      tf32_gemm_kernel<true><<<grid, T_THREADS, T_SMEM, st>>>(tm_l16, tm_l16, p);
+    if (p.mode == 0 && upd16 && p.from_c && p.fc.c16)
+      tf32_gemm_kernel<true, 1><<<grid, T_THREADS, T_SMEM, st>>>(tm_l16, tm_l16, p);
+    else if (p.mode == 0 && upd16 && p.from_c)
+      tf32_gemm_kernel<true, 2><<<grid, T_THREADS, T_SMEM, st>>>(tm_l16, tm_l16, p);
+    else if (p.mode == 0 && upd16)
+      tf32_gemm_kernel<true, 0><<<grid, T_THREADS, T_SMEM, st>>>(tm_l16, tm_l16, p);
     else
-      tf32_gemm_kernel<false><<<grid, T_THREADS, T_SMEM, st>>>(tm_l, tb, p);
+      tf32_gemm_kernel<false, 0><<<grid, T_THREADS, T_SMEM, st>>>(tm_l, tb, p);
     launches[0]++;
     return cudaGetLastError();
   };
@@ -820,6 +893,10 @@ cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, float* Linv2
       GemmParams p{};
       p.row0 = c0; p.a_col0 = 0; p.K = c0; p.b_row0 = c0; p.b_col0 = 0; p.b_rows_per_job = ntp; p.c_col0 = c0;
       p.N = w; p.mode = 0;
+      if (from_c && upd16) {                       // this launch is the first touch of block column c0: form it from C
+        p.from_c = 1;
+        p.fc = *from_c;
+      }
       if ((e = gemm(tm_l, p)) != cudaSuccess) return e;
       if (mark) mark(mark_ctx, 0, 1);
     }

@@ -122,7 +122,9 @@ struct TbCtx {
   int last_fallbacks = 0;         // jobs the last evaluation re-ran in fp64
   int last_fused = 0;
   int wide_panel = 1;             // 1: 256-wide panel solve through the inverse of the diagonal block (chol_tc.cu)
-  int fuse_scale = 1;             // 1: Gram epilogue writes the fp32 matrix when the row set allows it
+  int fuse_scale = 1;             // 1: with one contiguous row set the scaled fp32 matrix is never written by a pass of
+                                  //    its own (formed inside the Cholesky updates, or -- fuse_in_gram -- by the Gram epilogue)
+  int fuse_in_gram = 0;           // 1: round-1 behaviour, the Gram epilogue writes the whole fp32 matrix
   int n_sm = 148;
   // layout of the last wave (for tb_debug_fetch)
   struct DbgLayout {
@@ -273,12 +275,26 @@ cudaError_t tb_solve_mixed_init();
 bool tb_solve_mixed_fits(int ntp);
 cudaError_t tb_launch_solve_mixed(const TbSolveMixedJob* d_jobs, int n_jobs, int ntp, int contiguous, int c16, int hole,
                                   cudaStream_t st);
-cudaError_t tb_launch_scale32(const TbScaleJob* d_jobs, int n_jobs, int ntp, float* L32, int c16, cudaStream_t st);
+// col_end > 0: only columns [0, col_end) (the first outer block column of the factorisation)
+cudaError_t tb_launch_scale32(const TbScaleJob* d_jobs, int n_jobs, int ntp, float* L32, int c16, cudaStream_t st,
+                              int col_end = 0);
+// The fp32 matrix A = G_tt + lambda I is never materialised as a whole: block column J of the factorisation is formed
+// inside the epilogue of ITS outer update, T = A[:, J] - L[:, 0:J] L[J, 0:J]^T, with A evaluated on the fly from the
+// integer cross-products (2 or 4 bytes per entry instead of a 4-byte read of a matrix the Gram would have had to write).
+// terms: per job [2][ntp] floats -- row terms -(2N/den) s_a, then column terms (2/den)(Q - N s_b) (zero beyond n_t);
+// coef: per job {2 N^2 / den, lambda}.  One contiguous row set only (training animal a = panel row a).
+struct TbFromC {
+  const void* C;        // [n_jobs][rpad][rpad] cross-products (int16 when c16)
+  const float* terms;   // [n_jobs][2][ntp]
+  const float2* coef;   // [n_jobs]
+  int rpad, c16, n_t;
+};
+cudaError_t tb_launch_fuse_terms(const TbScaleJob* d_jobs, int n_jobs, int ntp, float* terms, float2* coef, cudaStream_t st);
 cudaError_t tb_chol_tc_init();
 // Linv256 (nullable): [n_jobs][256][256] scratch for the inverses of the 256-wide diagonal blocks (wide panel path)
 cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, float* Linv256, int* status, int n_jobs, int ntp,
                               int n_sm, cudaStream_t st, int* launches, std::string* err,
-                              void (*mark)(void*, int, int), void* mark_ctx);
+                              void (*mark)(void*, int, int), void* mark_ctx, const TbFromC* from_c = nullptr);
 
 // microbench.cu
 cudaError_t tb_microbench_dmma(int n_sm, cudaStream_t st, double* tflops);
