@@ -235,7 +235,12 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
   }
   // one contiguous row set: the Gram epilogue writes the fp32 matrix itself (no separate scaling pass over C)
   const bool fuse_scale = mixed && n_slots == 1 && (sv[0].rs->contiguous || use_perm) && c->n <= 46340 && c->fuse_scale;
-  c->last_fused = fuse_scale ? 1 : 0;
+  // the scaled fp32 matrix is not written by a pass of its own when every row set is a prefix of the panel rows or a
+  // prefix with one aligned hole (k-fold training sets): the Cholesky updates form it from C block column by block column
+  bool from_c_ok = mixed && c->n <= 46340 && c->fuse_scale;
+  for (int s = 0; s < n_slots; ++s)
+    from_c_ok = from_c_ok && (sv[s].rs->contiguous || (n_slots == 1 && use_perm) || sv[s].rs->seg_ok) && sv[s].rs->n_t % 4 == 0;
+  c->last_fused = (fuse_scale || from_c_ok) ? 1 : 0;
   const int kq = fp4 ? TB_GRAM_BK_FP4 : TB_GRAM_BK;      // markers per k-block
   const int kstride_max = tb_round_up(kmax, kq);
   // every cross-product is at most 4 k: int16 storage is exact for the whole batch when 4 kmax <= 32 767
@@ -316,11 +321,11 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     unsigned short* d_L16 = nullptr;
     float* d_Linv256 = nullptr;
     float* d_terms = nullptr;
-    float2* d_coef = nullptr;
+    TbFuseCoef* d_coef = nullptr;
     if (mixed) {
-      if (fuse_scale) {
+      if (from_c_ok) {
         d_terms = ar.take<float>((size_t)n_jobs * 2 * max_ntp);
-        d_coef = ar.take<float2>(n_jobs);
+        d_coef = ar.take<TbFuseCoef>(n_jobs);
       }
       if (c->wide_panel) d_Linv256 = ar.take<float>((size_t)n_jobs * 256 * 256);
       d_L32 = ar.take<float>(((size_t)n_jobs * max_ntp + 128) * max_ntp);
@@ -384,6 +389,9 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
         sj.ntp = rs->ntp;
         sj.rpad = rpad;
         sj.lambda = lambda;
+        sj.hole0 = use_perm ? rs->n_t : rs->hole0;
+        sj.gap = use_perm ? 0 : rs->gap;
+        sj.cw = w;
         TbCholJob& cj = h_chol[job];
         cj.M = Mj;
         cj.Linv = Lj;
@@ -476,9 +484,9 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
     if (c->stop_after == TB_ST_GRAM) continue;
 
     if (mixed) {
-      const bool from_c = fuse_scale && !c->fuse_in_gram && c->stop_after < 0;
+      const bool from_c = from_c_ok && !(fuse_scale && c->fuse_in_gram) && c->stop_after < 0;
       TbFromC fc{};
-      if (!fuse_scale || (fuse_scale && !c->fuse_in_gram)) {
+      if (!(fuse_scale && c->fuse_in_gram)) {
         sp = span_begin(c, TB_ST_SCALE);
         if (from_c) {
           // only the first outer block column is written here; every later one is formed inside its own update
@@ -490,7 +498,6 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
           fc.coef = d_coef;
           fc.rpad = rpad;
           fc.c16 = c16 ? 1 : 0;
-          fc.n_t = sv[0].rs->n_t;
         } else {
           TB_CUDA(c, tb_launch_scale32(d_scale, n_jobs, max_ntp, d_L32, c16 ? 1 : 0, st));
           count(c, TB_ST_SCALE, 1);

@@ -222,30 +222,41 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const int col_base = p.c_col0 + half * nch * 32;
       float4 cv[4][SRC == 1 ? 4 : 8];
       float f_scale = 0.f, f_lam = 0.f, f_rt = 0.f;
+      int f_nt = 0, f_h0 = 0, f_gap = 0;
       const float* f_ct = nullptr;
       if (SRC != 0) {
         // the entries of A this thread needs, as integer cross-products (8 or 16 bytes per 4 entries instead of a
         // read of an fp32 matrix somebody had to write): cv holds the RAW bits until the accumulator is there
-        const float2 cf = p.fc.coef[job];
-        f_scale = cf.x;
-        f_lam = cf.y;
+        const TbFuseCoef cf = p.fc.coef[job];
+        f_scale = cf.scale;
+        f_lam = cf.lam;
+        f_nt = cf.n_t;
         f_rt = p.fc.terms[(size_t)job * 2 * p.ntp + (r < p.row_end ? r : 0)];
         f_ct = p.fc.terms + (size_t)job * 2 * p.ntp + p.ntp + col_base;
-        const size_t coff = ((size_t)job * p.fc.rpad + (r < p.row_end ? r : 0)) * p.fc.rpad + col_base;
+        // compact index -> panel row / column: a + (a >= hole0 ? gap : 0); hole0 and gap are multiples of 8, so an
+        // 8-column group never straddles the hole (plain prefix: hole0 = n_t, gap = 0)
+        const int rr = r < cf.n_t ? r + (r >= cf.hole0 ? cf.gap : 0) : 0;
+        const size_t rowoff = ((size_t)cf.cw * p.fc.rpad + rr) * p.fc.rpad;
+        f_h0 = cf.hole0;
+        f_gap = cf.gap;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           if (i < nch && col_base + i * 32 <= r_hi && r < p.row_end) {
             if (SRC == 1) {
-              const uint4* src = reinterpret_cast<const uint4*>(static_cast<const int16_t*>(p.fc.C) + coff + i * 32);
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const uint4 u = src[j];
+              for (int j = 0; j < 4; ++j) {                      // 8 columns per 16-byte load
+                const int b = col_base + i * 32 + 8 * j;
+                const int ub = b + ((b >= f_h0 && b < f_nt) ? f_gap : 0);
+                const uint4 u = *reinterpret_cast<const uint4*>(static_cast<const int16_t*>(p.fc.C) + rowoff + ub);
                 cv[i][j] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
               }
             } else {
-              const float4* src = reinterpret_cast<const float4*>(static_cast<const int32_t*>(p.fc.C) + coff + i * 32);
 #pragma unroll
-              for (int j = 0; j < (SRC == 1 ? 4 : 8); ++j) cv[i][j] = src[j];
+              for (int j = 0; j < (SRC == 1 ? 4 : 8); ++j) {     // 4 columns per 16-byte load
+                const int b = col_base + i * 32 + 4 * j;
+                const int ub = b + ((b >= f_h0 && b < f_nt) ? f_gap : 0);
+                cv[i][j] = *reinterpret_cast<const float4*>(static_cast<const int32_t*>(p.fc.C) + rowoff + ub);
+              }
             }
           }
         }
@@ -275,7 +286,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (SRC != 0) {
           // A_rb = scale C_rb + rowterm_r + colterm_b (+ lambda on the diagonal; identity on the padding rows), T = A - acc
           const int b0 = col_base + i * 32;
-          const bool real_row = r < p.fc.n_t;
+          const bool real_row = r < f_nt;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
             const float4 ct = *reinterpret_cast<const float4*>(f_ct + i * 32 + 4 * j);

@@ -864,12 +864,13 @@ __global__ void __launch_bounds__(256) scale32_kernel(const TbScaleJob* __restri
 // Row / column terms and coefficients of the scaled matrix for the Cholesky update's epilogue (see TbFromC): the same
 // fp64-from-exact-integers coefficients, rounded once, that scale32_kernel and the old fused Gram epilogue used.
 __global__ void fuse_terms_kernel(const TbScaleJob* __restrict__ jobs, int ntp, float* __restrict__ terms,
-                                  float2* __restrict__ coef) {
+                                  TbFuseCoef* __restrict__ coef) {
   const TbScaleJob jb = jobs[blockIdx.y];
   const long long N = jb.N, S = jb.SQ[0], Q = jb.SQ[1];
   const double inv_d = 2.0 / (double)(2 * N * S - Q);
   const int a = blockIdx.x * blockDim.x + threadIdx.x;
-  if (a == 0) coef[blockIdx.y] = make_float2((float)(inv_d * (double)(N * N)), (float)jb.lambda);
+  if (a == 0)
+    coef[blockIdx.y] = TbFuseCoef{(float)(inv_d * (double)(N * N)), (float)jb.lambda, jb.n_t, jb.hole0, jb.gap, jb.cw};
   if (a >= ntp) return;
   float rt = 0.f, ct = 0.f;
   if (a < jb.n_t) {
@@ -938,7 +939,8 @@ cudaError_t tb_launch_solve_mixed(const TbSolveMixedJob* d_jobs, int n_jobs, int
   return cudaGetLastError();
 }
 
-cudaError_t tb_launch_fuse_terms(const TbScaleJob* d_jobs, int n_jobs, int ntp, float* terms, float2* coef, cudaStream_t st) {
+cudaError_t tb_launch_fuse_terms(const TbScaleJob* d_jobs, int n_jobs, int ntp, float* terms, TbFuseCoef* coef,
+                                 cudaStream_t st) {
   dim3 grid((ntp + 255) / 256, n_jobs);
   fuse_terms_kernel<<<grid, 256, 0, st>>>(d_jobs, ntp, terms, coef);
   return cudaGetLastError();

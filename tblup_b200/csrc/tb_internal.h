@@ -218,6 +218,7 @@ struct TbScaleJob {       // one (individual, rowset) matrix
   long long N;            // animals behind the allele frequencies
   int n_t, n_v, ntp, rpad;
   double lambda;
+  int hole0, gap, cw;     // "prefix with one aligned hole" (TbRowSet) and the genome's index in the wave (TbFromC)
 };
 cudaError_t tb_launch_scale(const TbScaleJob* d_jobs, int n_jobs, int max_rows, int max_ntp, cudaStream_t st);
 
@@ -282,14 +283,20 @@ cudaError_t tb_launch_scale32(const TbScaleJob* d_jobs, int n_jobs, int ntp, flo
 // inside the epilogue of ITS outer update, T = A[:, J] - L[:, 0:J] L[J, 0:J]^T, with A evaluated on the fly from the
 // integer cross-products (2 or 4 bytes per entry instead of a 4-byte read of a matrix the Gram would have had to write).
 // terms: per job [2][ntp] floats -- row terms -(2N/den) s_a, then column terms (2/den)(Q - N s_b) (zero beyond n_t);
-// coef: per job {2 N^2 / den, lambda}.  One contiguous row set only (training animal a = panel row a).
-struct TbFromC {
-  const void* C;        // [n_jobs][rpad][rpad] cross-products (int16 when c16)
-  const float* terms;   // [n_jobs][2][ntp]
-  const float2* coef;   // [n_jobs]
-  int rpad, c16, n_t;
+// coef: per job {2 N^2 / den, lambda, n_t, hole0, gap, genome index}.  Row sets that are a prefix of the panel rows, or a
+// prefix with one 8-aligned hole (k-fold training sets): training animal a sits at panel row a + (a >= hole0 ? gap : 0).
+struct TbFuseCoef {
+  float scale, lam;
+  int n_t, hole0, gap, cw;
 };
-cudaError_t tb_launch_fuse_terms(const TbScaleJob* d_jobs, int n_jobs, int ntp, float* terms, float2* coef, cudaStream_t st);
+struct TbFromC {
+  const void* C;        // [genomes][rpad][rpad] cross-products (int16 when c16)
+  const float* terms;   // [n_jobs][2][ntp]
+  const TbFuseCoef* coef;   // [n_jobs]
+  int rpad, c16;
+};
+cudaError_t tb_launch_fuse_terms(const TbScaleJob* d_jobs, int n_jobs, int ntp, float* terms, TbFuseCoef* coef,
+                                 cudaStream_t st);
 cudaError_t tb_chol_tc_init();
 // Linv256 (nullable): [n_jobs][256][256] scratch for the inverses of the 256-wide diagonal blocks (wide panel path)
 cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, float* Linv256, int* status, int n_jobs, int ntp,
