@@ -102,7 +102,8 @@ int tb_eval(tb_ctx* ctx, const int32_t* slots, int n_slots, const int32_t* idx_f
 
 /* Raw uncentred cross-products of one genome over universe rows [0, rows): out[a*rows + b], b <= a
  * (upper triangle zero).  impl 0 = tcgen05 int8 kernel, 1 = plain dp4a verification kernel, 2 = tcgen05 fp4 (E2M1)
- * kernel (packed resident genotypes only).
+ * kernel (packed resident genotypes only); 3 / 4 = the int8 / fp4 kernel run as clusters of two CTAs that share the
+ * B tile by TMA multicast (what evaluations use by default).
  * The integer part of make_grm (tblup/utils.py:17). */
 int tb_gram_debug(tb_ctx* ctx, const int32_t* idx, int k, int rows, int impl, int32_t* out);
 
@@ -117,6 +118,9 @@ int tb_debug_fetch(tb_ctx* ctx, int what, int job, void* out, size_t nbytes);
  * block), "narrow_c" (0/1, default 1: int16 storage of the cross-products when 4 k <= 32 767 for the whole batch),
  * "gram_fp4" (0/1, default 1: with packed resident genotypes the Gram runs on E2M1 operands, tcgen05 kind::mxf4 --
  * dosages 0/1/2 are exact in E2M1 and the fp32 accumulators hold the same integers; 0 = int8 operands),
+ * "gram_pair" (0/1, default 1: the Gram runs as clusters of two CTAs taking row blocks (I, I+1) of one column block together, the
+ * shared B tile fetched half by each and TMA-multicast to both), "fuse_in_gram" (0/1, default 0: the Gram epilogue writes
+ * the whole scaled fp32 matrix as in round 1; by default the Cholesky updates form it from the cross-products),
  * "perm_rows" (0/1, default 1: a single scattered row set -- Monte-Carlo split, unaligned fold, custom splitter -- is
  * turned into a prefix by permuting the panel rows at gather time, so it runs the contiguous kernels) */
 int tb_set_option(tb_ctx* ctx, const char* name, long long value);

@@ -78,8 +78,27 @@ inline void count(TbCtx* c, int stage, int n) {
 // Order matters for L2 reuse when one genome's panel is larger than L2 (config 4: 800 MB): the persistent CTAs
 // take consecutive list entries, so the list walks super-blocks of 12 x 6 tiles (1 536 x 1 536 entries): the ~148
 // tiles in flight then share 12 A row-blocks and 6 B row-blocks instead of streaming one long tile row.
-void build_tiles(int rpad, const std::vector<unsigned char>& has_train, std::vector<int>& tiles, int bn = TB_GRAM_BN) {
+void build_tiles(int rpad, const std::vector<unsigned char>& has_train, std::vector<int>& tiles, int bn = TB_GRAM_BN,
+                 bool pairs = false) {
   tiles.clear();
+  if (pairs) {
+    // items for the paired Gram kernel: row blocks (I, I + 1) x column block J, listed when either tile is needed
+    const int nI = rpad / TB_GRAM_BM, nJ = (rpad + bn - 1) / bn;
+    auto need = [&](int I, int J) {
+      if (I >= nI || J * bn > I * TB_GRAM_BM + TB_GRAM_BM - 1) return false;
+      if (has_train.empty() || has_train[I]) return true;
+      for (int blk = J * bn / TB_GRAM_BM; blk <= (J * bn + bn - 1) / TB_GRAM_BM; ++blk)
+        if (blk < nI && has_train[blk]) return true;
+      return false;
+    };
+    const int SBI = 12, SBJ = 6;
+    for (int I0 = 0; I0 < nI; I0 += SBI)
+      for (int J0 = 0; J0 < nJ; J0 += SBJ)
+        for (int I = I0; I < std::min(nI, I0 + SBI); I += 2)
+          for (int J = J0; J < std::min(nJ, J0 + SBJ); ++J)
+            if (need(I, J) || need(I + 1, J)) tiles.push_back((I << 16) | J);
+    return;
+  }
   const int nI = rpad / TB_GRAM_BM, nJ = (rpad + bn - 1) / bn;
   const int SBI = 12, SBJ = 6;
   for (int I0 = 0; I0 < nI; I0 += SBI) {
@@ -270,7 +289,8 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
   cudaStream_t st = c->stream;
   // tile list + genome offsets (device copies live at the start of the arena)
   std::vector<int> tiles;
-  build_tiles(rpad, has_train, tiles, fp4 ? TB_GRAM_BN_FP4 : TB_GRAM_BN);
+  const bool gram_pair = c->gram_pair && !(fuse_scale && c->fuse_in_gram);
+  build_tiles(rpad, has_train, tiles, fp4 ? TB_GRAM_BN_FP4 : TB_GRAM_BN, gram_pair);
   const int n_tiles = (int)tiles.size();
 
   Arena ar;
@@ -476,7 +496,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
       // (the Gram no longer writes the scaled matrix: with fuse_scale the Cholesky updates form it from C on the fly)
       cudaError_t ce = tb_launch_gram_tc(d_panel, Wc, rpad, kstride_b, d_kb, d_tiles, n_tiles, d_C, c->n_sm, st, &e,
                                          (fuse_scale && c->fuse_in_gram) ? d_scale : nullptr, d_L32, max_ntp, c16 ? 1 : 0,
-                                         fp4 ? 1 : 0);
+                                         fp4 ? 1 : 0, gram_pair ? 1 : 0);
       if (ce != cudaSuccess) return fail(c, "gram launch: " + (e.empty() ? std::string(cudaGetErrorString(ce)) : e), -2);
     }
     span_end(c, sp);
@@ -1127,13 +1147,14 @@ int tb_gram_debug(tb_ctx* c, const int32_t* idx, int k, int rows, int impl, int3
   for (int q = 0; q < k; ++q)
     if (idx[q] < 0 || idx[q] >= c->m) return fail(c, "tb_gram_debug: marker index out of range");
   TB_CUDA(c, cudaSetDevice(c->device));
-  const bool fp4 = impl == 2;
+  const bool fp4 = impl == 2 || impl == 4;
+  const bool pair = impl == 3 || impl == 4;          // the paired (cluster of two CTAs, TMA multicast) kernel
   if (fp4 && !c->d_x2) return fail(c, "tb_gram_debug: the fp4 Gram needs packed resident genotypes");
   const int kq = fp4 ? TB_GRAM_BK_FP4 : TB_GRAM_BK;
   const int rpad = tb_round_up(rows, TB_GRAM_BM), kmark = tb_round_up(k, kq);
   const int kstride = fp4 ? kmark / 2 : kmark;          // bytes per panel row
   std::vector<int> tiles;
-  build_tiles(rpad, std::vector<unsigned char>(), tiles, fp4 ? TB_GRAM_BN_FP4 : TB_GRAM_BN);
+  build_tiles(rpad, std::vector<unsigned char>(), tiles, fp4 ? TB_GRAM_BN_FP4 : TB_GRAM_BN, pair);
   const long long off[2] = {0, k};
   const int kb = kmark / kq;
   int8_t* d_panel = nullptr;
@@ -1159,10 +1180,10 @@ int tb_gram_debug(tb_ctx* c, const int32_t* idx, int k, int rows, int impl, int3
     ck(cudaMemcpyAsync(d_off, off, sizeof(off), cudaMemcpyHostToDevice, st), "H2D");
     if (fp4) ck(tb_launch_gather_fp4(c->geno(), d_i, d_off, 0, 1, rpad, kstride, d_panel, st), "gather");
     else ck(tb_launch_gather(c->geno(), d_i, d_off, 0, 1, rpad, kstride, d_panel, st), "gather");
-    if (impl == 0 || fp4) {
+    if (impl == 0 || fp4 || pair) {
       std::string e;
       cudaError_t ce = tb_launch_gram_tc(d_panel, 1, rpad, kstride, d_kb, d_t, (int)tiles.size(), d_C, c->n_sm, st, &e,
-                                         nullptr, nullptr, 0, 0, fp4 ? 1 : 0);
+                                         nullptr, nullptr, 0, 0, fp4 ? 1 : 0, pair ? 1 : 0);
       if (ce != cudaSuccess && rc == 0) rc = fail(c, "tb_gram_debug gram_tc: " + (e.empty() ? std::string(cudaGetErrorString(ce)) : e), -2);
     } else {
       ck(tb_launch_gram_simt(d_panel, 1, rpad, kstride, d_kb, d_C, st), "gram_simt");
@@ -1259,6 +1280,7 @@ int tb_set_option(tb_ctx* c, const char* name, long long value) {
   else if (s == "precision") c->precision = value != 0;
   else if (s == "fuse_scale") c->fuse_scale = value != 0;
   else if (s == "fuse_in_gram") c->fuse_in_gram = value != 0;
+  else if (s == "gram_pair") c->gram_pair = value != 0;
   else if (s == "wide_panel") c->wide_panel = value != 0;
   else if (s == "narrow_c") c->narrow_c = value != 0;
   else if (s == "gram_fp4") c->gram_fp4 = value != 0;

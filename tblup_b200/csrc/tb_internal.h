@@ -125,6 +125,7 @@ struct TbCtx {
   int fuse_scale = 1;             // 1: with one contiguous row set the scaled fp32 matrix is never written by a pass of
                                   //    its own (formed inside the Cholesky updates, or -- fuse_in_gram -- by the Gram epilogue)
   int fuse_in_gram = 0;           // 1: round-1 behaviour, the Gram epilogue writes the whole fp32 matrix
+  int gram_pair = 1;              // 1: Gram as clusters of two CTAs sharing the B tile by TMA multicast
   int n_sm = 148;
   // layout of the last wave (for tb_debug_fetch)
   struct DbgLayout {
@@ -203,7 +204,7 @@ struct TbScaleJob;
 cudaError_t tb_launch_gram_tc(const int8_t* d_panel, int W, int rpad, int kstride, const int* d_kblocks,
                               const int* d_tiles, int n_tiles, int32_t* d_C, int n_sm, cudaStream_t st,
                               std::string* err, const TbScaleJob* d_fuse_jobs = nullptr, float* d_L32 = nullptr,
-                              int ntp_all = 0, int c16 = 0, int fp4 = 0);
+                              int ntp_all = 0, int c16 = 0, int fp4 = 0, int pair = 0);
 cudaError_t tb_launch_gram_simt(const int8_t* d_panel, int W, int rpad, int kstride, const int* d_kblocks,
                                 int32_t* d_C, cudaStream_t st);
 

@@ -98,6 +98,19 @@ def test_fp4_gram_bit_exact_full_size(big, k):
     assert got.max() > (32767 if k == 50000 else 0)
 
 
+@pytest.mark.parametrize("impl", ["tc_pair", "fp4_pair"])
+def test_paired_gram_equals_single_cta_gram_full_size(big, impl):
+    """The default Gram schedule (clusters of two CTAs, B tile shared by TMA multicast) against the single-CTA kernel,
+    bit for bit, at the headline shape and on row counts that leave an odd number of row blocks / a ragged last tile."""
+    eng = big[0]
+    rng = np.random.default_rng(17)
+    idx = rng.choice(M, size=K, replace=False)
+    for rows in (4000, 3200, 129, 385, 1):
+        a = eng.gram_debug(idx[:K if rows > 400 else 700], rows, impl=impl)
+        b = eng.gram_debug(idx[:K if rows > 400 else 700], rows, impl=impl.split("_")[0])
+        assert np.array_equal(a, b), rows
+
+
 def test_k50000_fitness_uses_int32_cross_products(big):
     """k = 50 000: 4 k > 32 767, so the wave keeps int32 cross-products (fused scaling, mixed precision still on);
     fitness against the exact oracle."""
