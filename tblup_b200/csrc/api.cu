@@ -289,8 +289,8 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
   cudaStream_t st = c->stream;
   // tile list + genome offsets (device copies live at the start of the arena)
   std::vector<int> tiles;
-  const bool gram_pair = c->gram_pair && !(fuse_scale && c->fuse_in_gram);
-  build_tiles(rpad, has_train, tiles, fp4 ? TB_GRAM_BN_FP4 : TB_GRAM_BN, gram_pair);
+  const int gram_pair = (fuse_scale && c->fuse_in_gram) ? 0 : c->gram_pair;     // 0 single CTA, 1 multicast pair, 2 tcgen05 CTA pair
+  build_tiles(rpad, has_train, tiles, fp4 ? TB_GRAM_BN_FP4 : TB_GRAM_BN, gram_pair != 0);
   const int n_tiles = (int)tiles.size();
 
   Arena ar;
@@ -496,7 +496,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
       // (the Gram no longer writes the scaled matrix: with fuse_scale the Cholesky updates form it from C on the fly)
       cudaError_t ce = tb_launch_gram_tc(d_panel, Wc, rpad, kstride_b, d_kb, d_tiles, n_tiles, d_C, c->n_sm, st, &e,
                                          (fuse_scale && c->fuse_in_gram) ? d_scale : nullptr, d_L32, max_ntp, c16 ? 1 : 0,
-                                         fp4 ? 1 : 0, gram_pair ? 1 : 0);
+                                         fp4 ? 1 : 0, gram_pair);
       if (ce != cudaSuccess) return fail(c, "gram launch: " + (e.empty() ? std::string(cudaGetErrorString(ce)) : e), -2);
     }
     span_end(c, sp);
@@ -1147,14 +1147,15 @@ int tb_gram_debug(tb_ctx* c, const int32_t* idx, int k, int rows, int impl, int3
   for (int q = 0; q < k; ++q)
     if (idx[q] < 0 || idx[q] >= c->m) return fail(c, "tb_gram_debug: marker index out of range");
   TB_CUDA(c, cudaSetDevice(c->device));
-  const bool fp4 = impl == 2 || impl == 4;
-  const bool pair = impl == 3 || impl == 4;          // the paired (cluster of two CTAs, TMA multicast) kernel
+  const bool fp4 = impl == 2 || impl == 4 || impl == 6;
+  const int pair = (impl == 3 || impl == 4) ? 1 : (impl == 5 || impl == 6) ? 2 : 0;   // clusters of two CTAs: multicast / tcgen05 pair
+  if (impl == 6) impl = 4;
   if (fp4 && !c->d_x2) return fail(c, "tb_gram_debug: the fp4 Gram needs packed resident genotypes");
   const int kq = fp4 ? TB_GRAM_BK_FP4 : TB_GRAM_BK;
   const int rpad = tb_round_up(rows, TB_GRAM_BM), kmark = tb_round_up(k, kq);
   const int kstride = fp4 ? kmark / 2 : kmark;          // bytes per panel row
   std::vector<int> tiles;
-  build_tiles(rpad, std::vector<unsigned char>(), tiles, fp4 ? TB_GRAM_BN_FP4 : TB_GRAM_BN, pair);
+  build_tiles(rpad, std::vector<unsigned char>(), tiles, fp4 ? TB_GRAM_BN_FP4 : TB_GRAM_BN, pair != 0);
   const long long off[2] = {0, k};
   const int kb = kmark / kq;
   int8_t* d_panel = nullptr;
@@ -1183,7 +1184,7 @@ int tb_gram_debug(tb_ctx* c, const int32_t* idx, int k, int rows, int impl, int3
     if (impl == 0 || fp4 || pair) {
       std::string e;
       cudaError_t ce = tb_launch_gram_tc(d_panel, 1, rpad, kstride, d_kb, d_t, (int)tiles.size(), d_C, c->n_sm, st, &e,
-                                         nullptr, nullptr, 0, 0, fp4 ? 1 : 0, pair ? 1 : 0);
+                                         nullptr, nullptr, 0, 0, fp4 ? 1 : 0, pair);
       if (ce != cudaSuccess && rc == 0) rc = fail(c, "tb_gram_debug gram_tc: " + (e.empty() ? std::string(cudaGetErrorString(ce)) : e), -2);
     } else {
       ck(tb_launch_gram_simt(d_panel, 1, rpad, kstride, d_kb, d_C, st), "gram_simt");
@@ -1280,7 +1281,7 @@ int tb_set_option(tb_ctx* c, const char* name, long long value) {
   else if (s == "precision") c->precision = value != 0;
   else if (s == "fuse_scale") c->fuse_scale = value != 0;
   else if (s == "fuse_in_gram") c->fuse_in_gram = value != 0;
-  else if (s == "gram_pair") c->gram_pair = value != 0;
+  else if (s == "gram_pair") c->gram_pair = value < 0 ? 0 : value > 2 ? 2 : (int)value;
   else if (s == "wide_panel") c->wide_panel = value != 0;
   else if (s == "narrow_c") c->narrow_c = value != 0;
   else if (s == "gram_fp4") c->gram_fp4 = value != 0;

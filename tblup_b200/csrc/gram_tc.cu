@@ -69,7 +69,11 @@ struct Barriers {
 // need the same B rows, so each CTA fetches HALF of the B tile and TMA multicasts it into both shared memories -- the
 // L2 -> SM operand traffic per MMA drops by a third (r01 ncu: 15.5 TB/s of L2 reads held the tensor pipe at 57 %).
 // The MMAs stay cta_group::1; a ring slot is released to both producers by a multicast commit.
-template <bool FUSE, bool C16, bool FP4, bool PAIR>
+// PAIR == 2: the pair runs as ONE tcgen05 CTA pair (cta_group::2): M = 256 (128 rows from each CTA), each CTA fetches
+// and keeps only its HALF of the B tile (no multicast), one thread of the leader CTA issues the MMAs for both tensor
+// cores.  Per k-block a CTA's shared memory then takes 30 KB of TMA writes and 30 KB of operand reads instead of
+// 44 + 44 KB -- at the mxf4 rate the single-CTA form needs ~164 B/clk of a 128 B/clk shared-memory port.
+template <bool FUSE, bool C16, bool FP4, int PAIR>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_b,
                const int* __restrict__ tiles, int n_tiles,
@@ -84,21 +88,26 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = W * n_tiles;
   const int crank = PAIR ? (int)cluster_ctarank() : 0;          // which tile of the pair / which half of B this CTA loads
+  constexpr bool CG2 = PAIR == 2;
+  constexpr uint32_t STAGE_TX2 = A_BYTES + (BN / 2) * BK;       // what ONE CTA of a tcgen05 pair loads per k-block
   const int worker = PAIR ? blockIdx.x >> 1 : blockIdx.x, n_workers = PAIR ? gridDim.x >> 1 : gridDim.x;
 
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&tmap);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&bars->full[s], 1);
-      mbar_init(&bars->empty[s], PAIR ? 2 : 1);
+      mbar_init(&bars->empty[s], PAIR == 1 ? 2 : 1);
     }
     for (int s = 0; s < ACC_STAGES; ++s) {
       mbar_init(&bars->acc_full[s], 1);
-      mbar_init(&bars->acc_empty[s], EPI_WARPS);   // one arrival per epilogue warp
+      mbar_init(&bars->acc_empty[s], CG2 ? 2 * EPI_WARPS : EPI_WARPS);   // one arrival per epilogue warp (of both CTAs)
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  if (warp == 1) {
+    if (CG2) tmem_alloc_pair<TMEM_COLS>(&bars->tmem_base);
+    else tmem_alloc<TMEM_COLS>(&bars->tmem_base);
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -125,6 +134,18 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&bars->empty[stage], phase ^ 1);
           uint8_t* sa = smem + stage * STAGE_BYTES;
+          if (CG2) {
+            // both CTAs' loads are counted on the LEADER's ring barrier (its MMA thread is the only consumer)
+            if (crank == 0) mbar_arrive_expect_tx(&bars->full[stage], 2 * STAGE_TX2);
+            const uint32_t lead_full = mapa_u32(smem_u32(&bars->full[stage]), 0);
+            tma_load_2d_pair(sa, &tmap, lead_full, kb * BK, row_a);
+            tma_load_2d_pair(sa + A_BYTES, &tmap_b, lead_full, kb * BK, row_b + crank * (BN / 2));
+            if (++stage == STAGES) {
+              stage = 0;
+              phase ^= 1;
+            }
+            continue;
+          }
           mbar_arrive_expect_tx(&bars->full[stage], STAGE_TX);
           tma_load_2d(sa, &tmap, &bars->full[stage], kb * BK, row_a);
           if (PAIR) {
@@ -142,8 +163,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (with PAIR == 2: the leader CTA's thread drives both tensor cores) ============
+    if (lane == 0 && !(CG2 && crank != 0)) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -163,20 +184,28 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 #pragma unroll
           for (int k = 0; k < BK / 32; ++k) {
             // advance 32 bytes along K inside the 128-byte swizzle span: +2 in 16-byte units
-            if (FP4)
+            if (CG2) {
+              if (FP4)
+                umma_mxf4_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, umma_idesc_mxf4(2 * BM, BN), (kb | k) != 0,
+                               tmem_base + SF_COL, tmem_base + SF_COL + 8);
+              else
+                umma_s8_pair(tmem_d, adesc + 2 * k, bdesc + 2 * k, umma_idesc_s8(2 * BM, BN), (kb | k) != 0);
+            } else if (FP4)
               umma_mxf4(tmem_d, adesc + 2 * k, bdesc + 2 * k, umma_idesc_mxf4(BM, BN), (kb | k) != 0,
                         tmem_base + SF_COL, tmem_base + SF_COL + 8);
             else
               umma_s8(tmem_d, adesc + 2 * k, bdesc + 2 * k, IDESC, (kb | k) != 0);
           }
-          if (PAIR) umma_commit_multicast(&bars->empty[stage], (uint16_t)3);
+          if (CG2) umma_commit_pair(&bars->empty[stage], (uint16_t)3);
+          else if (PAIR) umma_commit_multicast(&bars->empty[stage], (uint16_t)3);
           else umma_commit(&bars->empty[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit(&bars->acc_full[acc]);
+        if (CG2) umma_commit_pair(&bars->acc_full[acc], (uint16_t)3);
+        else umma_commit(&bars->acc_full[acc]);
         if (++acc == ACC_STAGES) {
           acc = 0;
           acc_phase ^= 1;
@@ -325,7 +354,10 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+      if (lane == 0) {
+        if (CG2) mbar_arrive_cluster(mapa_u32(smem_u32(&bars->acc_empty[acc]), 0));   // the leader's MMA thread waits for both CTAs
+        else mbar_arrive(&bars->acc_empty[acc]);
+      }
       if (++acc == ACC_STAGES) {
         acc = 0;
         acc_phase ^= 1;
@@ -338,7 +370,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   if (PAIR) cluster_sync_all();       // nobody leaves while its partner may still multicast into its ring or barriers
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    if (CG2) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+    else tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
@@ -362,18 +395,22 @@ cudaError_t tb_gram_tc_init() {
   auto set = [&](const void* fn) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES);
   };
-  set((const void*)gram_tc_kernel<false, false, false, false>);
-  set((const void*)gram_tc_kernel<true, false, false, false>);
-  set((const void*)gram_tc_kernel<false, true, false, false>);
-  set((const void*)gram_tc_kernel<true, true, false, false>);
-  set((const void*)gram_tc_kernel<false, false, true, false>);
-  set((const void*)gram_tc_kernel<true, false, true, false>);
-  set((const void*)gram_tc_kernel<false, true, true, false>);
-  set((const void*)gram_tc_kernel<true, true, true, false>);
-  set((const void*)gram_tc_kernel<false, false, false, true>);
-  set((const void*)gram_tc_kernel<false, true, false, true>);
-  set((const void*)gram_tc_kernel<false, false, true, true>);
-  set((const void*)gram_tc_kernel<false, true, true, true>);
+  set((const void*)gram_tc_kernel<false, false, false, 0>);
+  set((const void*)gram_tc_kernel<true, false, false, 0>);
+  set((const void*)gram_tc_kernel<false, true, false, 0>);
+  set((const void*)gram_tc_kernel<true, true, false, 0>);
+  set((const void*)gram_tc_kernel<false, false, true, 0>);
+  set((const void*)gram_tc_kernel<true, false, true, 0>);
+  set((const void*)gram_tc_kernel<false, true, true, 0>);
+  set((const void*)gram_tc_kernel<true, true, true, 0>);
+  set((const void*)gram_tc_kernel<false, false, false, 1>);
+  set((const void*)gram_tc_kernel<false, true, false, 1>);
+  set((const void*)gram_tc_kernel<false, false, true, 1>);
+  set((const void*)gram_tc_kernel<false, true, true, 1>);
+  set((const void*)gram_tc_kernel<false, false, false, 2>);
+  set((const void*)gram_tc_kernel<false, true, false, 2>);
+  set((const void*)gram_tc_kernel<false, false, true, 2>);
+  set((const void*)gram_tc_kernel<false, true, true, 2>);
   return e;
 }
 
@@ -419,18 +456,25 @@ cudaError_t tb_launch_gram_tc(const int8_t* d_panel, int W, int rpad, int kstrid
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    const int which = (c16 ? 2 : 0) | (fp4 ? 1 : 0);
+    const int which = (pair == 2 ? 4 : 0) | (c16 ? 2 : 0) | (fp4 ? 1 : 0);
+#define TB_GRAM_PAIR(S, P4, PR) \
+  return cudaLaunchKernelEx(&cfg, gram_tc_kernel<false, S, P4, PR>, tmap, tmap_b, d_tiles, n_tiles, d_kblocks, W, rpad, d_C, fz)
     switch (which) {
-      case 0: return cudaLaunchKernelEx(&cfg, gram_tc_kernel<false, false, false, true>, tmap, tmap_b, d_tiles, n_tiles, d_kblocks, W, rpad, d_C, fz);
-      case 1: return cudaLaunchKernelEx(&cfg, gram_tc_kernel<false, false, true, true>, tmap, tmap_b, d_tiles, n_tiles, d_kblocks, W, rpad, d_C, fz);
-      case 2: return cudaLaunchKernelEx(&cfg, gram_tc_kernel<false, true, false, true>, tmap, tmap_b, d_tiles, n_tiles, d_kblocks, W, rpad, d_C, fz);
-      default: return cudaLaunchKernelEx(&cfg, gram_tc_kernel<false, true, true, true>, tmap, tmap_b, d_tiles, n_tiles, d_kblocks, W, rpad, d_C, fz);
+      case 0: TB_GRAM_PAIR(false, false, 1);
+      case 1: TB_GRAM_PAIR(false, true, 1);
+      case 2: TB_GRAM_PAIR(true, false, 1);
+      case 3: TB_GRAM_PAIR(true, true, 1);
+      case 4: TB_GRAM_PAIR(false, false, 2);
+      case 5: TB_GRAM_PAIR(false, true, 2);
+      case 6: TB_GRAM_PAIR(true, false, 2);
+      default: TB_GRAM_PAIR(true, true, 2);
     }
+#undef TB_GRAM_PAIR
   }
   const int grid = n_items < n_sm ? n_items : n_sm;
   const int which = (d_fuse_jobs ? 4 : 0) | (c16 ? 2 : 0) | (fp4 ? 1 : 0);
 #define TB_GRAM_LAUNCH(F, S, P4) \
-  gram_tc_kernel<F, S, P4, false><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmap, tmap_b, d_tiles, n_tiles, d_kblocks, W, rpad, d_C, fz)
+  gram_tc_kernel<F, S, P4, 0><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(tmap, tmap_b, d_tiles, n_tiles, d_kblocks, W, rpad, d_C, fz)
   switch (which) {
     case 0: TB_GRAM_LAUNCH(false, false, false); break;
     case 1: TB_GRAM_LAUNCH(false, false, true); break;

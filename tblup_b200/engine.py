@@ -208,7 +208,7 @@ class GblupEngine:
         flat, _ = pack_genomes([indices], self.m)
         out = np.empty((rows, rows), dtype=np.int32)
         self._check(self._lib.tb_gram_debug(self._ctx, flat.ctypes.data, flat.size, int(rows),
-                                            {"tc": 0, "simt": 1, "fp4": 2, "tc_pair": 3, "fp4_pair": 4}[impl], out.ctypes.data), "tb_gram_debug")
+                                            {"tc": 0, "simt": 1, "fp4": 2, "tc_pair": 3, "fp4_pair": 4, "tc_cg2": 5, "fp4_cg2": 6}[impl], out.ctypes.data), "tb_gram_debug")
         return out
 
     def debug_dims(self, job=0):

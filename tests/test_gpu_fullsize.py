@@ -98,10 +98,10 @@ def test_fp4_gram_bit_exact_full_size(big, k):
     assert got.max() > (32767 if k == 50000 else 0)
 
 
-@pytest.mark.parametrize("impl", ["tc_pair", "fp4_pair"])
+@pytest.mark.parametrize("impl", ["tc_pair", "fp4_pair", "tc_cg2", "fp4_cg2"])
 def test_paired_gram_equals_single_cta_gram_full_size(big, impl):
-    """The default Gram schedule (clusters of two CTAs, B tile shared by TMA multicast) against the single-CTA kernel,
-    bit for bit, at the headline shape and on row counts that leave an odd number of row blocks / a ragged last tile."""
+    """The paired Gram schedules (clusters of two CTAs: B tile shared by TMA multicast, or one tcgen05 CTA pair with
+    cta_group::2 MMAs) against the single-CTA kernel, bit for bit, at the headline shape and on row counts that leave an odd number of row blocks / a ragged last tile."""
     eng = big[0]
     rng = np.random.default_rng(17)
     idx = rng.choice(M, size=K, replace=False)
