@@ -450,6 +450,12 @@ def main():
     peak_dmma = eng.microbench(0)
     peak_i8 = eng.microbench(1)
     peak_mxf4 = eng.microbench(2)
+    # the Gram runs inside a long step under the board's power cap: its roofline is the SUSTAINED rate, measured with
+    # random operand bits and with genotype-like operands (the larger of the two is used as the denominator)
+    sus = {"i8_random": eng.microbench(3), "mxf4_random": eng.microbench(4),
+           "i8_dosage": eng.microbench(5), "mxf4_dosage": eng.microbench(6)} if rank == 0 or True else {}
+    peak_i8_sus = max(sus["i8_random"], sus["i8_dosage"])
+    peak_mxf4_sus = max(sus["mxf4_random"], sus["mxf4_dosage"])
 
     def barrier():
         if world > 1:
@@ -685,7 +691,7 @@ def main():
             gram_ops = 2.0 * k * (rows_t * (rows_t + 1) / 2 + (len(valid) * rows_t if folds == 1 else 0)) * p_loc * args.steps
             gram_tops = gram_ops / (gram_ms * 1e-3) / 1e12 if gram_ms > 0 else None
             gram_traffic = ncu.get("gram_fp4_fused_c16" if fp4 else "gram_fused_c16") if (fused and c16) else None
-            gram_peak = peak_mxf4 if fp4 else peak_i8
+            gram_peak = peak_mxf4_sus if fp4 else peak_i8_sus
             rl_gram = {"bound": "tensor",
                        "kernel": ("gram_tc_kernel (tcgen05 kind::mxf4 on E2M1 dosages, block scales 2^0, M128 x N224 x K64, "
                                   "fp32 in TMEM holding exact integers%s)" if fp4 else
@@ -696,8 +702,13 @@ def main():
                        "traffic": gram_traffic["bytes_per_unit"] * p_loc if gram_traffic else None,
                        "traffic_source": gram_traffic["source"] if gram_traffic else None,
                        "algorithmic_ops_per_launch": gram_ops / max(1, gram_launches),
-                       "peak_source": "tcgen05 %s issue rate measured in this process on shared-memory-resident operands, "
-                                      "one CTA per SM (tb_microbench %d)" % (("kind::mxf4", 2) if fp4 else ("kind::i8", 1)),
+                       "peak_source": "SUSTAINED tcgen05 %s issue rate measured in this process (tb_microbench %s: MMAs back "
+                                      "to back on shared-memory-resident operands, one CTA per SM, ~2.5 s, rate over the last "
+                                      "~1.5 s; the larger of random and genotype-like operand bits)"
+                                      % (("kind::mxf4", "4/6") if fp4 else ("kind::i8", "3/5")),
+                       "frac_of_burst_peak": gram_tops / (peak_mxf4 if fp4 else peak_i8) if gram_tops else None,
+                       "tile_padding_factor": "executed / algorithmic multiply-accumulates = 1.154 at the headline shape "
+                                              "(128 x 224 tiles on the triangle, k padded to 256, rows to 128)",
                        "frac_of_4x_bf16_sustained" if fp4 else "frac_of_2x_bf16_sustained":
                            gram_tops / ((4 if fp4 else 2) * bf16) if gram_tops else None,
                        "launches": int(gram_launches), "avg_launch_ms": gram_ms / max(1, gram_launches),
@@ -743,7 +754,7 @@ def main():
                                        "balanced by genome length); NCCL all-gather of the fitness vector",
                         "other_scaling": summary(other, "strong" if args.scaling == "weak" else "weak") if other else None,
                         "measured_peaks": {"tcgen05_i8_tops": peak_i8, "tcgen05_mxf4_tops": peak_mxf4,
-                                           "fp64_dmma_tflops": peak_dmma,
+                                           "tcgen05_sustained_tops": sus, "fp64_dmma_tflops": peak_dmma,
                                            "how": "tb_microbench: MMAs issued back to back on shared-memory-resident "
                                                   "operands, one CTA per SM, best of 3 launches of ~20 ms"}},
             "e2e": {"value": evals / (prim["ms_e2e"] * 1e-3), "unit": UNIT, "h2d_bytes_per_step": prim["h2d"],

@@ -148,7 +148,10 @@ int tb_set_stream(tb_ctx* ctx, void* cuda_stream);
 
 /* Peak probes for roofline denominators (the Gram of tblup/utils.py:17 is reported against them): which = 0 -> fp64 DMMA
  * (mma.sync m8n8k4) TFLOP/s; 1 -> tcgen05 kind::i8 TOP/s and 2 -> tcgen05 kind::mxf4 (E2M1) TOP/s, M128 x N256 MMAs
- * issued back to back on shared-memory-resident operands, one CTA per SM (2 ops per multiply-accumulate). */
+ * issued back to back on shared-memory-resident operands, one CTA per SM (2 ops per multiply-accumulate): best of
+ * three ~20 ms launches on random operand bits (burst); 3 / 4 -> the same two SUSTAINED (back to back for ~2.5 s, rate over
+ * the last ~1.5 s, when the clock has settled under the board's power cap); 5 / 6 -> sustained with genotype-like operands
+ * (dosages 0/1/2 at realistic frequencies: fewer toggling bits, a higher sustained clock). */
 int tb_microbench(tb_ctx* ctx, int which, double* out);
 
 /* ---- on-device differential evolution on random-key individuals (tblup/evolver.py:63-157 DE/rand/1 with binary

@@ -1365,9 +1365,9 @@ int tb_microbench(tb_ctx* c, int which, double* out) {
     c->launches += 4;
     return 0;
   }
-  if (which == 1 || which == 2) {
+  if (which >= 1 && which <= 6) {
     TB_CUDA(c, tb_microbench_umma(which, c->n_sm, c->stream, out));
-    c->launches += 4;
+    c->launches += which >= 3 ? 126 : 4;
     return 0;
   }
   return fail(c, "tb_microbench: unknown probe");

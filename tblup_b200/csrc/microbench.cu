@@ -14,8 +14,11 @@ using namespace tbptx;
 // (pseudo-random bytes: every E2M1 nibble / int8 byte is a finite value) and ONE thread issues
 // M128 x N256 MMAs back to back into one TMEM accumulator: K = 32 per instruction for kind::i8, K = 64 for
 // kind::mxf4 (block scales 2^0).  A commit every 16 k-blocks, at most two batches in flight.
+// dosage != 0: the operands hold genotype-like values (dosage 0 / 1 / 2 with probabilities ~ .55 / .37 / .08, the E2M1
+// nibble 2 d or the int8 byte d) instead of random bits -- the tensor cores' power draw, and with it the clock the
+// board sustains under its power cap, depends on how many operand bits toggle.
 template <bool FP4>
-__global__ void __launch_bounds__(128, 1) umma_peak_kernel(int iters, uint32_t seed) {
+__global__ void __launch_bounds__(128, 1) umma_peak_kernel(int iters, uint32_t seed, int dosage) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int A_BYTES = 128 * 128, B_BYTES = 256 * 128;
@@ -25,6 +28,17 @@ __global__ void __launch_bounds__(128, 1) umma_peak_kernel(int iters, uint32_t s
   for (int i = threadIdx.x; i < (A_BYTES + B_BYTES) / 4; i += blockDim.x) {
     uint32_t h = (uint32_t)i * 2654435761u + seed + blockIdx.x * 40503u;
     h ^= h >> 15; h *= 2246822519u; h ^= h >> 13; h *= 3266489917u; h ^= h >> 16;
+    if (dosage) {
+      uint32_t out = 0, g = h;
+      const int per = FP4 ? 8 : 4, bits = FP4 ? 4 : 8;
+      for (int e = 0; e < per; ++e) {
+        g = g * 1664525u + 1013904223u;
+        const uint32_t u = g >> 24;                     // 0..255
+        const uint32_t d = u < 141 ? 0u : (u < 236 ? 1u : 2u);
+        out |= (FP4 ? 2u * d : d) << (bits * e);
+      }
+      h = out;
+    }
     reinterpret_cast<uint32_t*>(smem)[i] = h;
   }
   if (threadIdx.x == 0) {
@@ -129,10 +143,15 @@ cudaError_t tb_microbench_dmma(int n_sm, cudaStream_t st, double* tflops) {
 }
 
 
-// which: 1 = tcgen05 kind::i8 (TOP/s, 2 ops per multiply-accumulate), 2 = kind::mxf4 on E2M1 operands.
+// which: 1 = tcgen05 kind::i8 (TOP/s, 2 ops per multiply-accumulate), 2 = kind::mxf4 on E2M1 operands: best of three
+// ~20 ms launches on random operand bits (burst).  3 / 4 = the same two instructions SUSTAINED: launches back to back
+// for ~2.5 s, rate over the last ~1.5 s (the clock has settled under the power cap by then), random operand bits;
+// 5 / 6 = sustained with genotype-like operands.
 cudaError_t tb_microbench_umma(int which, int n_sm, cudaStream_t st, double* tops) {
   const int smem = 128 * 128 + 256 * 128 + 1024 + 64;
-  const bool fp4 = which == 2;
+  const bool fp4 = which == 2 || which == 4 || which == 6;
+  const bool sustained = which >= 3;
+  const int dosage = which >= 5 ? 1 : 0;
   cudaError_t e = fp4 ? cudaFuncSetAttribute((const void*)umma_peak_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)
                       : cudaFuncSetAttribute((const void*)umma_peak_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) return e;
@@ -140,12 +159,28 @@ cudaError_t tb_microbench_umma(int which, int n_sm, cudaStream_t st, double* top
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
   auto launch = [&](int iters) {
-    if (fp4) umma_peak_kernel<true><<<n_sm, 128, smem, st>>>(iters, 12345u);
-    else umma_peak_kernel<false><<<n_sm, 128, smem, st>>>(iters, 12345u);
+    if (fp4) umma_peak_kernel<true><<<n_sm, 128, smem, st>>>(iters, 12345u, dosage);
+    else umma_peak_kernel<false><<<n_sm, 128, smem, st>>>(iters, 12345u, dosage);
   };
   launch(2048);                                    // warm-up
   const int iters = fp4 ? 80000 : 40000;           // ~20 ms per launch
   double best = 0.0;
+  if (sustained) {
+    const double ops1 = (double)n_sm * iters * 4.0 * 2.0 * 128.0 * 256.0 * (fp4 ? 64.0 : 32.0);
+    const int n_pre = 50, n_meas = 75;             // ~1 s to settle, ~1.5 s measured
+    for (int i = 0; i < n_pre; ++i) launch(iters);
+    cudaEventRecord(e0, st);
+    for (int i = 0; i < n_meas; ++i) launch(iters);
+    cudaEventRecord(e1, st);
+    e = cudaEventSynchronize(e1);
+    float ms = 0.f;
+    if (e == cudaSuccess) cudaEventElapsedTime(&ms, e0, e1);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tops = ms > 0.f ? ops1 * n_meas / (ms * 1e-3) / 1e12 : 0.0;
+    return e;
+  }
   for (int rep = 0; rep < 3; ++rep) {
     cudaEventRecord(e0, st);
     launch(iters);
