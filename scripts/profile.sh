@@ -6,7 +6,7 @@ set -u
 TAG=${1:-r01}
 PREC=${2:-mixed}
 POP=${3:-64}
-CMD="python bench.py --steps 1 --warmup 1 --pop $POP --no-cpu-baseline --precision $PREC"
+CMD="python bench.py --steps 1 --warmup 1 --pop $POP --no-cpu-baseline --no-parity --no-sustained-peaks --precision $PREC"
 mkdir -p gpurun_out
 $CMD > gpurun_out/plain_$TAG.log 2>&1 || { echo "plain run failed"; tail -5 gpurun_out/plain_$TAG.log; exit 1; }
 tail -1 gpurun_out/plain_$TAG.log | cut -c1-300
@@ -16,13 +16,13 @@ FULL="ncu --set full --clock-control none --import-source on"
 if [ "$PREC" = "mixed" ]; then
   $FULL -k regex:solve_mixed_kernel -s 0 -c 1 -o gpurun_out/prof_solve_$TAG -f $CMD > gpurun_out/ncu_solve_$TAG.log 2>&1
   echo "solve capture rc=$?"
-  # tf32_gemm_kernel launches of one evaluation, in order: block column 0 has 7 (narrow solves / updates of the
-  # diagonal block + the wide solve), every later block column J has 8, starting with its outer update.
-  # J = 6: launch 7 + 5 * 8 = 47 is the outer update (fp16 operands, K = 1536, N = 256), launch 54 the wide
-  # triangular solve (tf32, K = 256, N = 256)
-  $FULL -k regex:tf32_gemm_kernel -s 47 -c 1 -o gpurun_out/prof_update_$TAG -f $CMD > gpurun_out/ncu_update_$TAG.log 2>&1
+  # tf32_gemm_kernel launches of one evaluation, in order (round 2: the narrow rounds of the diagonal block are their
+  # own mma.sync kernels): block column 0 has 1 (the wide solve), every later full block column J has 2 (its outer
+  # update, then its wide solve).  J = 6: launch 1 + 5 * 2 = 11 is the outer update (fp16 operands, K = 1536, N = 256,
+  # block column formed from the int16 cross-products), launch 12 the wide triangular solve (tf32, K = N = 256)
+  $FULL -k regex:tf32_gemm_kernel -s 11 -c 1 -o gpurun_out/prof_update_$TAG -f $CMD > gpurun_out/ncu_update_$TAG.log 2>&1
   echo "update capture rc=$?"
-  $FULL -k regex:tf32_gemm_kernel -s 54 -c 1 -o gpurun_out/prof_trsm_$TAG -f $CMD > gpurun_out/ncu_trsm_$TAG.log 2>&1
+  $FULL -k regex:tf32_gemm_kernel -s 12 -c 1 -o gpurun_out/prof_trsm_$TAG -f $CMD > gpurun_out/ncu_trsm_$TAG.log 2>&1
   echo "wide trsm capture rc=$?"
 else
   $FULL -k regex:chol_gemm_kernel -s 76 -c 4 -o gpurun_out/prof_chol_$TAG -f $CMD > gpurun_out/ncu_chol_$TAG.log 2>&1
@@ -30,4 +30,10 @@ else
 fi
 $FULL -k regex:gram_tc_kernel -s 1 -c 1 -o gpurun_out/prof_gram_$TAG -f $CMD > gpurun_out/ncu_gram_$TAG.log 2>&1
 echo "gram capture rc=$?"
+# raw metric pages as CSV (what profiles/ keeps; the .ncu-rep files stay in gpurun_out/)
+for k in solve update trsm gram chol; do
+  if [ -f gpurun_out/prof_${k}_$TAG.ncu-rep ]; then
+    ncu -i gpurun_out/prof_${k}_$TAG.ncu-rep --page raw --csv > gpurun_out/${TAG}_${k}_raw.csv 2>/dev/null
+  fi
+done
 ls -la gpurun_out/ | grep $TAG
