@@ -55,9 +55,17 @@ struct GramFuse {
 };
 constexpr uint32_t IDESC = umma_idesc_s8(BM, BN);
 
+constexpr int MAX_STAGES = 8;
+// ring depth: a CTA of a tcgen05 pair keeps only its half of the B tile, so its k-block is 30 KB (fp4) / 32 KB (int8)
+// instead of 44 / 48 KB and six stages fit where four did -- the ring is what hides the L2 / HBM latency of the operand
+// stream (r02: single-CTA, multicast-pair and CTA-pair kernels all ran at the same ~60 % of the MMA rate with four)
+template <int PAIR, bool FP4> struct RingCfg {
+  static constexpr int STAGE = PAIR == 2 ? A_BYTES + ((FP4 ? TB_GRAM_BN_FP4 : BN) / 2) * BK : STAGE_BYTES;
+  static constexpr int N = PAIR == 2 ? 6 : STAGES;
+};
 struct Barriers {
-  uint64_t full[STAGES];
-  uint64_t empty[STAGES];
+  uint64_t full[MAX_STAGES];
+  uint64_t empty[MAX_STAGES];
   uint64_t acc_full[ACC_STAGES];
   uint64_t acc_empty[ACC_STAGES];
   uint32_t tmem_base;
@@ -81,9 +89,13 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
   constexpr int BN = FP4 ? BN4 : BN_I8;                     // tile columns of this variant
   constexpr int ACC_STRIDE = FP4 ? ACC_STRIDE4 : BN_I8;     // TMEM columns between the two accumulators
   constexpr uint32_t STAGE_TX = A_BYTES + BN * BK;
+  constexpr int STAGES = RingCfg<PAIR, FP4>::N;              // (shadows the file-scope constants: this variant's ring)
+  constexpr int STAGE_BYTES = RingCfg<PAIR, FP4>::STAGE;
+  constexpr int RING_BYTES = 4 * 49152;                      // the ring region is the same size for every variant
+  static_assert(STAGES * STAGE_BYTES <= RING_BYTES && STAGE_BYTES % 1024 == 0, "ring layout");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  Barriers* bars = reinterpret_cast<Barriers*>(smem + STAGES * STAGE_BYTES);
+  Barriers* bars = reinterpret_cast<Barriers*>(smem + RING_BYTES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_items = W * n_tiles;
@@ -218,8 +230,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
     const int chalf = (warp - 2) >> 2;   // which half of the tile's 32-column chunks
     int acc = 0;
     uint32_t acc_phase = 0;
-    const uint32_t colterm = smem_u32(smem + STAGES * STAGE_BYTES + 256);     // [2][BN] doubles
-    const uint32_t stg = smem_u32(smem + STAGES * STAGE_BYTES + 256 + COLTERM_BYTES) + (warp - 2) * 2048;
+    const uint32_t colterm = smem_u32(smem + RING_BYTES + 256);     // [2][BN] doubles
+    const uint32_t stg = smem_u32(smem + RING_BYTES + 256 + COLTERM_BYTES) + (warp - 2) * 2048;
     int fbuf = 0;
     for (int item = worker; item < n_items; item += n_workers) {
       const int w = item / n_tiles, t = tiles[item - w * n_tiles];

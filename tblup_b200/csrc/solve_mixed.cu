@@ -312,9 +312,10 @@ __device__ void apply_minv_f32(const __half* __restrict__ L, const float* __rest
 // the unit; the row partials of four rows are reduced across the warp by a transposing butterfly (6 shuffles per four
 // rows) and added to out[] with shared-memory atomics, as are the column sums at the end of the unit (about 40
 // warp-level atomics per 16 K entries of C).  The same "prefix with one aligned hole" index mapping as before.
-template <bool HOLE>
-__device__ void sym_matvec16_1p(const int16_t* __restrict__ C, int rpad, int n_t, int h0, int gap, const double* alpha,
+template <bool HOLE, typename CT>
+__device__ void sym_matvec16_1p(const CT* __restrict__ C, int rpad, int n_t, int h0, int gap, const double* alpha,
                                 double amax, double* out, int* counter) {
+  constexpr bool W16 = sizeof(CT) == 2;              // int16 cross-products (8-byte loads of 4) or int32 (16-byte loads of 4)
   const int tid = threadIdx.x, lane = tid & 31;
   auto U = [&](int i) { return HOLE ? i + (i >= h0 ? gap : 0) : i; };   // compact index -> universe position
   // The partial sums of many warps meet in out[]: they are accumulated as 64-bit FIXED-POINT integers, so the result
@@ -322,7 +323,7 @@ __device__ void sym_matvec16_1p(const int16_t* __restrict__ C, int rpad, int n_t
   // |sum_b C_ab alpha_b| <= 32768 n_t amax =: bound < 2^ex; one quantum = 2^(ex - 62) <= bound 2^-61 -- finer than the
   // rounding of the fp64 dot product it replaces (~ n_t 2^-53 of the same bound).
   unsigned long long* outq = reinterpret_cast<unsigned long long*>(out);
-  const double bound = 32768.0 * (double)n_t * fmax(amax, 1e-290);
+  const double bound = (W16 ? 32768.0 : 8388608.0) * (double)n_t * fmax(amax, 1e-290);   // C_ab <= 4 k < 2^15 resp. 2^23
   const int ex = ((__double2hiint(bound) >> 20) & 0x7ff) - 1022;
   const double scale = __hiloint2double((62 - ex + 1023) << 20, 0), inv_scale = __hiloint2double((ex - 62 + 1023) << 20, 0);
   for (int a = tid; a < n_t; a += ST) outq[a] = 0ull;
@@ -352,26 +353,35 @@ __device__ void sym_matvec16_1p(const int16_t* __restrict__ C, int rpad, int n_t
       ac[e] = 0.0;
       al[e] = col_ok ? alpha[c0 + e] : 0.0;
     }
-    const int16_t* colp = C + U(c0);
+    const CT* colp = C + U(c0);
     const bool diag_unit = u == 0;                    // SW == RU: only a strip's first unit reaches its diagonal
-    for (int r = r0; r < r1; r += 8) {                // eight rows (8-byte loads) in flight; n_t % 4 == 0
-      uint2 v[8];
+    constexpr int RB = W16 ? 8 : 4;                   // rows in flight per lane (64 bytes of loads either way)
+    for (int r = r0; r < r1; r += RB) {               // n_t % 4 == 0
+      uint4 v[RB];                                    // int16: .x, .y hold the four entries; int32: all four words
 #pragma unroll
-      for (int q = 0; q < 8; ++q) {
-        v[q] = make_uint2(0u, 0u);
-        if (col_ok && r + q < r1 && (!diag_unit || c0 <= r + q))
-          v[q] = *reinterpret_cast<const uint2*>(colp + (size_t)U(r + q) * rpad);
+      for (int q = 0; q < RB; ++q) {
+        v[q] = make_uint4(0u, 0u, 0u, 0u);
+        if (col_ok && r + q < r1 && (!diag_unit || c0 <= r + q)) {
+          if (W16) {
+            const uint2 t2 = *reinterpret_cast<const uint2*>(colp + (size_t)U(r + q) * rpad);
+            v[q].x = t2.x;
+            v[q].y = t2.y;
+          } else {
+            v[q] = *reinterpret_cast<const uint4*>(colp + (size_t)U(r + q) * rpad);
+          }
+        }
       }
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
+      for (int h = 0; h < RB / 4; ++h) {
         if (r + 4 * h >= r1) break;
         double p[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int rr = r + 4 * h + q;
           const double ar = alpha[rr];
-          const uint32_t w0 = v[4 * h + q].x, w1 = v[4 * h + q].y;
-          const double cc[4] = {u2d(w0 & 0xffffu), u2d(w0 >> 16), u2d(w1 & 0xffffu), u2d(w1 >> 16)};
+          const uint4 vv = v[4 * h + q];
+          const double cc[4] = {W16 ? u2d(vv.x & 0xffffu) : u2d(vv.x), W16 ? u2d(vv.x >> 16) : u2d(vv.y),
+                                W16 ? u2d(vv.y & 0xffffu) : u2d(vv.z), W16 ? u2d(vv.y >> 16) : u2d(vv.w)};
           double pr = 0.0;
           if (!diag_unit || c0 + 3 < rr) {
 #pragma unroll
@@ -420,82 +430,9 @@ template <bool CONTIG, bool HOLE, typename CT>
 __device__ void sym_matvec(const CT* __restrict__ C, int rpad, int n_t, int h0, int gap, const int* tp,
                            const double* alpha, double amax, double* work, double* part2) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if constexpr (CONTIG && sizeof(CT) == 2) {
-    sym_matvec16_1p<HOLE>(reinterpret_cast<const int16_t*>(C), rpad, n_t, h0, gap, alpha, amax, work,
-                          reinterpret_cast<int*>(part2));
-  } else if constexpr (CONTIG) {
-    // rows: (C alpha)_a += sum_{b <= a} C[a][b] alpha_b, 16-byte loads, four in flight
-    for (int a = warp; a < n_t; a += ST / 32) {
-      const int4* row = reinterpret_cast<const int4*>(C + (size_t)a * rpad);
-      const int n4 = a / 4 + 1;                     // int4 groups that contain a column <= a
-      double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
-      int c = lane;
-      for (; c + 96 < n4 - 1; c += 128) {           // groups strictly before the one holding the diagonal
-        const int4 v0 = row[c], v1 = row[c + 32], v2 = row[c + 64], v3 = row[c + 96];
-        d0 += dot4i(v0, alpha + 4 * c);
-        d1 += dot4i(v1, alpha + 4 * (c + 32));
-        d2 += dot4i(v2, alpha + 4 * (c + 64));
-        d3 += dot4i(v3, alpha + 4 * (c + 96));
-      }
-      for (; c < n4; c += 32) {
-        const int4 v = row[c];
-        const int b = 4 * c;
-        d0 += (double)v.x * alpha[b];
-        if (b + 1 <= a) d1 += (double)v.y * alpha[b + 1];
-        if (b + 2 <= a) d2 += (double)v.z * alpha[b + 2];
-        if (b + 3 <= a) d3 += (double)v.w * alpha[b + 3];
-      }
-      const double d = warp_sum((d0 + d1) + (d2 + d3));
-      if (lane == 0) work[a] = d;
-    }
-    __syncthreads();
-    // columns: (C alpha)_a += sum_{b > a} C[b][a] alpha_b; thread = 4 consecutive columns x one of 4 row groups
-    const int cg = tid & 127, rg = tid >> 7;
-    for (int a0 = 0; a0 < n_t; a0 += 512) {
-      const int ca = a0 + 4 * cg;
-      double e0 = 0.0, e1 = 0.0, e2 = 0.0, e3 = 0.0;
-      if (ca < n_t) {
-        const int32_t* colp = C + ca;
-        int b = a0 + 1 + rg;
-        const int b_tri = min(n_t, a0 + 516);        // rows that may still cross the diagonal of this column block
-        for (; b < b_tri; b += 4) {
-          const int4 v = *reinterpret_cast<const int4*>(colp + (size_t)b * rpad);
-          const double w = alpha[b];
-          if (b > ca) e0 += (double)v.x * w;
-          if (b > ca + 1) e1 += (double)v.y * w;
-          if (b > ca + 2) e2 += (double)v.z * w;
-          if (b > ca + 3) e3 += (double)v.w * w;
-        }
-        for (; b + 12 < n_t; b += 16) {
-          const int4 v0 = *reinterpret_cast<const int4*>(colp + (size_t)b * rpad);
-          const int4 v1 = *reinterpret_cast<const int4*>(colp + (size_t)(b + 4) * rpad);
-          const int4 v2 = *reinterpret_cast<const int4*>(colp + (size_t)(b + 8) * rpad);
-          const int4 v3 = *reinterpret_cast<const int4*>(colp + (size_t)(b + 12) * rpad);
-          const double w0 = alpha[b], w1 = alpha[b + 4], w2 = alpha[b + 8], w3 = alpha[b + 12];
-          e0 += (double)v0.x * w0 + (double)v1.x * w1 + (double)v2.x * w2 + (double)v3.x * w3;
-          e1 += (double)v0.y * w0 + (double)v1.y * w1 + (double)v2.y * w2 + (double)v3.y * w3;
-          e2 += (double)v0.z * w0 + (double)v1.z * w1 + (double)v2.z * w2 + (double)v3.z * w3;
-          e3 += (double)v0.w * w0 + (double)v1.w * w1 + (double)v2.w * w2 + (double)v3.w * w3;
-        }
-        for (; b < n_t; b += 4) {
-          const int4 v = *reinterpret_cast<const int4*>(colp + (size_t)b * rpad);
-          const double w = alpha[b];
-          e0 += (double)v.x * w;
-          e1 += (double)v.y * w;
-          e2 += (double)v.z * w;
-          e3 += (double)v.w * w;
-        }
-      }
-      double* pr = part2 + rg * 512 + 4 * cg;
-      pr[0] = e0;
-      pr[1] = e1;
-      pr[2] = e2;
-      pr[3] = e3;
-      __syncthreads();
-      const int a = a0 + tid;
-      if (a < n_t) work[a] += (part2[tid] + part2[512 + tid]) + (part2[1024 + tid] + part2[1536 + tid]);
-      __syncthreads();
-    }
+  if constexpr (CONTIG) {
+    // one pass over the triangle for both storage widths (HOLE only occurs with the int16 layout)
+    sym_matvec16_1p<HOLE, CT>(C, rpad, n_t, h0, gap, alpha, amax, work, reinterpret_cast<int*>(part2));
   } else {
     for (int a = warp; a < n_t; a += ST / 32) {
       const int pa = tp[a];
