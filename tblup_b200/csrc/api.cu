@@ -455,6 +455,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
         mj.gap = use_perm ? 0 : rs->gap;
         mj.valid_in_hole = (!use_perm && rs->valid_in_hole) ? 1 : 0;
         mj.lambda = lambda;
+        mj.cmax = 4 * k;
         c->dbg.M[job] = Mj;
         c->dbg.alpha[job] = aj;
         c->dbg.pred[job] = pj;
@@ -544,7 +545,8 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
         contig = contig && (((sv[s].rs->contiguous || use_perm) && sv[s].rs->n_t % 4 == 0) || (c16 && sv[s].rs->seg_ok));
         hole = hole || (!use_perm && sv[s].rs->gap > 0);
       }
-      TB_CUDA(c, tb_launch_solve_mixed(d_msolve, n_jobs, max_ntp, contig ? 1 : 0, c16 ? 1 : 0, hole ? 1 : 0, st));
+      TB_CUDA(c, tb_launch_solve_mixed(d_msolve, n_jobs, max_ntp, contig ? 1 : 0, c16 ? 1 : 0, hole ? 1 : 0, st, c->n_sm,
+                                       c->solve_pair));
       span_end(c, sp);
       count(c, TB_ST_SOLVE, 1);
       continue;
@@ -1281,6 +1283,7 @@ int tb_set_option(tb_ctx* c, const char* name, long long value) {
   else if (s == "precision") c->precision = value != 0;
   else if (s == "fuse_scale") c->fuse_scale = value != 0;
   else if (s == "fuse_in_gram") c->fuse_in_gram = value != 0;
+  else if (s == "solve_pair") c->solve_pair = value < 0 ? 0 : value > 2 ? 2 : (int)value;
   else if (s == "gram_pair") c->gram_pair = value < 0 ? 0 : value > 2 ? 2 : (int)value;
   else if (s == "wide_panel") c->wide_panel = value != 0;
   else if (s == "narrow_c") c->narrow_c = value != 0;

@@ -170,6 +170,39 @@ __device__ void hole_predict16(const int16_t* __restrict__ C, int rpad, int n_t,
 }
 
 
+// ---- two CTAs per matrix (small batches) --------------------------------------------------------------------------
+// With fewer matrices than CTA slots (strong scaling: 125 genomes per GPU; config 4: 53 matrices per wave) one CTA per
+// matrix leaves most of the machine idle and the kernel runs at the latency of ONE CTA's byte stream.  CL = 2 runs a
+// cluster of two CTAs per matrix: each streams half of every block step of the triangular solves, half of the work units
+// of the symmetric mat-vec and half of the validation rows; the 64 partial sums of a step (or the fixed-point partial
+// vector of a mat-vec) are read from the partner's shared memory after a cluster barrier.  Everything else is computed
+// redundantly -- and identically, since every cross-CTA sum is one commutative addition -- by both CTAs, so they take
+// the same branches and meet at the same barriers.
+template <int CL>
+__device__ __forceinline__ void team_sync() {
+  if (CL > 1) {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  } else {
+    __syncthreads();
+  }
+}
+__device__ __forceinline__ uint32_t peer_addr(const void* p, uint32_t peer) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"((uint32_t)__cvta_generic_to_shared(p)), "r"(peer));
+  return r;
+}
+__device__ __forceinline__ float ld_peer_f32(const float* p, uint32_t peer) {
+  float v;
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(peer_addr(p, peer)) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long ld_peer_u64(const unsigned long long* p, uint32_t peer) {
+  unsigned long long v;
+  asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(peer_addr(p, peer)) : "memory");
+  return v;
+}
+
 // ---- fp32 application of the preconditioner -----------------------------------------------------------------------
 // wf <- (L L^T)^-1 wf in place, entirely in fp32 (fp16 factor widened pairwise, FFMA accumulation).  The factor is a
 // 10-bit preconditioner (it contracts the error ~300x per sweep); applying it with fp32 rounding (~1e-6 relative)
@@ -188,17 +221,20 @@ __device__ __forceinline__ float warp_sumf(float v) {
   return v;
 }
 
+// xp: [2][NB] exchange buffer (CL = 2), crank: this CTA's rank in its cluster
+template <int CL>
 __device__ void apply_minv_f32(const __half* __restrict__ L, const float* __restrict__ Linv, int ntp, float* wf,
-                               float* rvec, float* part) {
+                               float* rvec, float* part, float* xp, int crank) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nb = ntp / NB;
+  int par = 0;
   for (int b = 0; b < nb; ++b) {                      // forward: L z = wf
     const int kc = b * NB;
     {
       const uint4* r0 = reinterpret_cast<const uint4*>(L + (size_t)(kc + 4 * warp) * ntp);
       const size_t rs = ntp / 8;
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      for (int c = lane; c < kc / 8; c += 32) {
+      for (int c = lane + 32 * crank; c < kc / 8; c += 32 * CL) {
         const uint4 l0 = r0[c], l1 = r0[rs + c], l2 = r0[2 * rs + c], l3 = r0[3 * rs + c];
         const float4 z0 = *reinterpret_cast<const float4*>(wf + 8 * c), z1 = *reinterpret_cast<const float4*>(wf + 8 * c + 4);
         s0 += dot8hf(l0, z0, z1);
@@ -210,7 +246,18 @@ __device__ void apply_minv_f32(const __half* __restrict__ L, const float* __rest
       s1 = warp_sumf(s1);
       s2 = warp_sumf(s2);
       s3 = warp_sumf(s3);
-      if (lane == 0) {
+      if (CL > 1) {
+        if (lane == 0) {
+          float* x = xp + par * NB + 4 * warp;
+          x[0] = s0;
+          x[1] = s1;
+          x[2] = s2;
+          x[3] = s3;
+        }
+        team_sync<CL>();
+        if (tid < NB) rvec[tid] = wf[kc + tid] - (xp[par * NB + tid] + ld_peer_f32(xp + par * NB + tid, crank ^ 1));
+        par ^= 1;
+      } else if (lane == 0) {
         rvec[4 * warp + 0] = wf[kc + 4 * warp + 0] - s0;
         rvec[4 * warp + 1] = wf[kc + 4 * warp + 1] - s1;
         rvec[4 * warp + 2] = wf[kc + 4 * warp + 2] - s2;
@@ -253,15 +300,17 @@ __device__ void apply_minv_f32(const __half* __restrict__ L, const float* __rest
         a[6] = fmaf(f3.x, w, a[6]);
         a[7] = fmaf(f3.y, w, a[7]);
       };
-      int i = kc + NB + rg;
-      for (; i + 448 < ntp; i += 512) {                // eight independent 16-byte loads in flight
+      // rows kc + 64 + rg + 64 j below the block; with CL = 2 CTA r takes the 64-row groups j = r (mod 2)
+      int i = kc + NB + rg + 64 * crank;
+      constexpr int RS = 64 * CL;
+      for (; i + 7 * RS < ntp; i += 8 * RS) {          // eight independent 16-byte loads in flight
         uint4 l[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) l[u] = *reinterpret_cast<const uint4*>(base + (size_t)(i + 64 * u) * ntp);
+        for (int u = 0; u < 8; ++u) l[u] = *reinterpret_cast<const uint4*>(base + (size_t)(i + RS * u) * ntp);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc8(l[u], wf[i + 64 * u]);
+        for (int u = 0; u < 8; ++u) acc8(l[u], wf[i + RS * u]);
       }
-      for (; i < ntp; i += 64) acc8(*reinterpret_cast<const uint4*>(base + (size_t)i * ntp), wf[i]);
+      for (; i < ntp; i += RS) acc8(*reinterpret_cast<const uint4*>(base + (size_t)i * ntp), wf[i]);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         a[e] += __shfl_xor_sync(0xffffffffu, a[e], 8);
@@ -274,7 +323,17 @@ __device__ void apply_minv_f32(const __half* __restrict__ L, const float* __rest
       }
     }
     __syncthreads();
-    if (tid < NB) {
+    if (CL > 1) {
+      if (tid < NB) {
+        float sv = 0.f;
+#pragma unroll
+        for (int gI = 0; gI < ST / 32; ++gI) sv += part[gI * NB + tid];
+        xp[par * NB + tid] = sv;
+      }
+      team_sync<CL>();
+      if (tid < NB) rvec[tid] = wf[kc + tid] - (xp[par * NB + tid] + ld_peer_f32(xp + par * NB + tid, crank ^ 1));
+      par ^= 1;
+    } else if (tid < NB) {
       float sv = 0.f;
 #pragma unroll
       for (int gI = 0; gI < ST / 32; ++gI) sv += part[gI * NB + tid];
@@ -312,18 +371,18 @@ __device__ void apply_minv_f32(const __half* __restrict__ L, const float* __rest
 // the unit; the row partials of four rows are reduced across the warp by a transposing butterfly (6 shuffles per four
 // rows) and added to out[] with shared-memory atomics, as are the column sums at the end of the unit (about 40
 // warp-level atomics per 16 K entries of C).  The same "prefix with one aligned hole" index mapping as before.
-template <bool HOLE, typename CT>
+template <bool HOLE, typename CT, int CL>
 __device__ void sym_matvec16_1p(const CT* __restrict__ C, int rpad, int n_t, int h0, int gap, const double* alpha,
-                                double amax, double* out, int* counter) {
+                                double amax, int cmax, double* out, int* counter, int crank) {
   constexpr bool W16 = sizeof(CT) == 2;              // int16 cross-products (8-byte loads of 4) or int32 (16-byte loads of 4)
   const int tid = threadIdx.x, lane = tid & 31;
   auto U = [&](int i) { return HOLE ? i + (i >= h0 ? gap : 0) : i; };   // compact index -> universe position
   // The partial sums of many warps meet in out[]: they are accumulated as 64-bit FIXED-POINT integers, so the result
   // does not depend on the order in which the warps arrive (bit-identical from run to run and for any wave size).
-  // |sum_b C_ab alpha_b| <= 32768 n_t amax =: bound < 2^ex; one quantum = 2^(ex - 62) <= bound 2^-61 -- finer than the
+  // |sum_b C_ab alpha_b| <= 4 k n_t amax =: bound < 2^ex; one quantum = 2^(ex - 62) <= bound 2^-61 -- finer than the
   // rounding of the fp64 dot product it replaces (~ n_t 2^-53 of the same bound).
   unsigned long long* outq = reinterpret_cast<unsigned long long*>(out);
-  const double bound = (W16 ? 32768.0 : 8388608.0) * (double)n_t * fmax(amax, 1e-290);   // C_ab <= 4 k < 2^15 resp. 2^23
+  const double bound = (double)cmax * (double)n_t * fmax(amax, 1e-290);   // C_ab <= 4 k
   const int ex = ((__double2hiint(bound) >> 20) & 0x7ff) - 1022;
   const double scale = __hiloint2double((62 - ex + 1023) << 20, 0), inv_scale = __hiloint2double((ex - 62 + 1023) << 20, 0);
   for (int a = tid; a < n_t; a += ST) outq[a] = 0ull;
@@ -336,7 +395,7 @@ __device__ void sym_matvec16_1p(const CT* __restrict__ C, int rpad, int n_t, int
   for (;;) {
     int u = 0;
     if (lane == 0) u = atomicAdd(counter, 1);
-    u = __shfl_sync(0xffffffffu, u, 0);
+    u = __shfl_sync(0xffffffffu, u, 0) * CL + crank;  // CL = 2: the partner CTA takes the other units
     if (u >= total) break;
     int s = 0;
     for (;; ++s) {
@@ -419,6 +478,27 @@ __device__ void sym_matvec16_1p(const CT* __restrict__ C, int rpad, int n_t, int
       for (int e = 0; e < 4; ++e) atomicAdd(outq + c0 + e, (unsigned long long)__double2ll_rn(ac[e] * scale));
     }
   }
+  if (CL > 1) {
+    // own + partner's partial vector (integers: the order does not matter); the partner reads ours at the same time,
+    // so nothing is overwritten before both have read a chunk
+    for (int base = 0; base < n_t; base += 8 * ST) {
+      team_sync<CL>();
+      double v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int a = base + j * ST + tid;
+        v[j] = a < n_t ? (double)(long long)(outq[a] + ld_peer_u64(outq + a, crank ^ 1)) * inv_scale : 0.0;
+      }
+      team_sync<CL>();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int a = base + j * ST + tid;
+        if (a < n_t) out[a] = v[j];
+      }
+    }
+    __syncthreads();
+    return;
+  }
   __syncthreads();
   for (int a = tid; a < n_t; a += ST) out[a] = (double)(long long)outq[a] * inv_scale;
   __syncthreads();
@@ -426,13 +506,13 @@ __device__ void sym_matvec16_1p(const CT* __restrict__ C, int rpad, int n_t, int
 
 // (C alpha)_a over the training animals into work[a]; CONTIG: training animal b sits at universe position b.
 // CT: element type of the stored cross-products (int32_t, or int16_t in C16 mode).
-template <bool CONTIG, bool HOLE, typename CT>
+template <bool CONTIG, bool HOLE, typename CT, int CL>
 __device__ void sym_matvec(const CT* __restrict__ C, int rpad, int n_t, int h0, int gap, const int* tp,
-                           const double* alpha, double amax, double* work, double* part2) {
+                           const double* alpha, double amax, int cmax, double* work, double* part2, int crank) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if constexpr (CONTIG) {
     // one pass over the triangle for both storage widths (HOLE only occurs with the int16 layout)
-    sym_matvec16_1p<HOLE, CT>(C, rpad, n_t, h0, gap, alpha, amax, work, reinterpret_cast<int*>(part2));
+    sym_matvec16_1p<HOLE, CT, CL>(C, rpad, n_t, h0, gap, alpha, amax, cmax, work, reinterpret_cast<int*>(part2), crank);
   } else {
     for (int a = warp; a < n_t; a += ST / 32) {
       const int pa = tp[a];
@@ -481,11 +561,18 @@ __device__ void sym_matvec(const CT* __restrict__ C, int rpad, int n_t, int h0, 
   }
 }
 
-template <bool CONTIG, bool BIG, bool C16, bool HOLE>
+template <bool CONTIG, bool BIG, bool C16, bool HOLE, int CL>
 __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJob* __restrict__ jobs) {
+  static_assert(CL == 1 || CONTIG, "two CTAs per matrix only with the contiguous kernels");
   using CT = typename std::conditional<C16, int16_t, int32_t>::type;
   extern __shared__ double msm[];
-  const TbSolveMixedJob jb = jobs[blockIdx.x];
+  const TbSolveMixedJob jb = jobs[blockIdx.x / CL];
+  int crank = 0;
+  if (CL > 1) {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    crank = (int)r;
+  }
   const int ntp = jb.ntp, n_t = jb.n_t, n_v = jb.n_v, rpad = jb.rpad;
   // small matrices keep alpha and the position table in shared memory; beyond MIXED_SMEM_NTP rows alpha lives in
   // the job's global output vector and the positions are read from the row set (both stay L1/L2 resident)
@@ -510,6 +597,7 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
   }
   float* rvec = wf + ntp;            // [NB]
   float* part = rvec + NB;           // [ST/32][NB]
+  float* xp = part + (ST / 32) * NB; // [2][NB] partial sums offered to the partner CTA (CL = 2)
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const double Nd = (double)jb.N, Sd = (double)jb.SQ[0], Qd = (double)jb.SQ[1];
   const double coef = 2.0 / (2.0 * Nd * Sd - Qd);
@@ -520,9 +608,11 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
     wf[a] = (float)jb.y_t[a];
   }
   __syncthreads();
-  apply_minv_f32(static_cast<const __half*>(jb.L16), jb.Linv32, ntp, wf, rvec, part);
+  apply_minv_f32<CL>(static_cast<const __half*>(jb.L16), jb.Linv32, ntp, wf, rvec, part, xp, crank);
+  // (BIG: alpha is the job's global vector -- with CL = 2 both CTAs store the same values, then meet at a barrier)
   for (int a = tid; a < ntp; a += ST) alpha[a] = (double)wf[a];
-  __syncthreads();
+  if (BIG) team_sync<CL>();
+  else __syncthreads();
 
   int sweeps = 0;
   bool solved = false;               // refinement reached the tolerance (else the host re-runs the job in fp64)
@@ -539,7 +629,7 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
     const double amax_now = block_max(l2, red);
     if (sweeps == MAX_SWEEPS) break;
     if (!(amax_now < 1e300)) break;                     // non-finite first solve (overflowing factor): leave it to fp64
-    sym_matvec<CONTIG, HOLE, CT>(C, rpad, n_t, jb.hole0, jb.gap, tp, alpha, amax_now, work, part2);      // work[a] = (C alpha)_a, a < n_t
+    sym_matvec<CONTIG, HOLE, CT, CL>(C, rpad, n_t, jb.hole0, jb.gap, tp, alpha, amax_now, jb.cmax, work, part2, crank);   // work[a] = (C alpha)_a
     for (int a = tid; a < ntp; a += ST) {
       double rr = 0.0;
       if (a < n_t) {
@@ -550,15 +640,30 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
       wf[a] = (float)rr;
     }
     __syncthreads();
-    apply_minv_f32(static_cast<const __half*>(jb.L16), jb.Linv32, ntp, wf, rvec, part);
+    apply_minv_f32<CL>(static_cast<const __half*>(jb.L16), jb.Linv32, ntp, wf, rvec, part, xp, crank);
     double dmax = 0.0, amax = 0.0;
-    for (int a = tid; a < ntp; a += ST) {
-      const double d = (double)wf[a];
-      const double v = alpha[a] + d;
-      alpha[a] = v;
-      // fmax drops NaN operands: map anything non-finite to +inf so that it cannot pass for "converged"
-      dmax = fmax(dmax, fabs(d) < 1e300 ? fabs(d) : __longlong_as_double(0x7ff0000000000000LL));
-      amax = fmax(amax, fabs(v) < 1e300 ? fabs(v) : __longlong_as_double(0x7ff0000000000000LL));
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    if (BIG && CL > 1) {
+      // alpha is ONE global vector shared by the pair: both CTAs read it to form the same maxima, then one of them updates
+      for (int a = tid; a < ntp; a += ST) {
+        const double d = (double)wf[a];
+        const double v = alpha[a] + d;
+        dmax = fmax(dmax, fabs(d) < 1e300 ? fabs(d) : INF);
+        amax = fmax(amax, fabs(v) < 1e300 ? fabs(v) : INF);
+      }
+      team_sync<CL>();
+      if (crank == 0)
+        for (int a = tid; a < ntp; a += ST) alpha[a] = alpha[a] + (double)wf[a];
+      team_sync<CL>();
+    } else {
+      for (int a = tid; a < ntp; a += ST) {
+        const double d = (double)wf[a];
+        const double v = alpha[a] + d;
+        alpha[a] = v;
+        // fmax drops NaN operands: map anything non-finite to +inf so that it cannot pass for "converged"
+        dmax = fmax(dmax, fabs(d) < 1e300 ? fabs(d) : INF);
+        amax = fmax(amax, fabs(v) < 1e300 ? fabs(v) : INF);
+      }
     }
     dmax = block_max(dmax, red);
     amax = block_max(amax, red);
@@ -586,10 +691,10 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
       break;
     }
   }
-  if (!big)
+  if (!big && crank == 0)
     for (int a = tid; a < ntp; a += ST) jb.alpha[a] = alpha[a];
-  if (tid == 0 && jb.sweeps) *jb.sweeps = sweeps;
-  if (tid == 0 && jb.fail && (!solved || *jb.status != 0)) *jb.fail = 1;
+  if (tid == 0 && crank == 0 && jb.sweeps) *jb.sweeps = sweeps;
+  if (tid == 0 && crank == 0 && jb.fail && (!solved || *jb.status != 0)) *jb.fail = 1;
 
   // ---- predictions on the validation animals
   if constexpr (CONTIG && C16) {
@@ -597,11 +702,13 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
       if (HOLE && jb.gap > 0 && jb.valid_in_hole) {
       // k-fold cross-validation: the validation animals are exactly the hole of the training set
       __syncthreads();
-      hole_predict16(reinterpret_cast<const int16_t*>(C), rpad, n_t, jb.hole0, jb.gap, alpha, work, part2);
-      for (int v = tid; v < n_v; v += ST)
-        jb.pred[v] = coef * (Nd * Nd * work[v] - Nd * (double)jb.s[jb.hole0 + v] * sa - Nd * ssa + Qd * sa);
+      if (crank == 0) {                                 // (not split over the pair: a tenth of a sweep's bytes)
+        hole_predict16(reinterpret_cast<const int16_t*>(C), rpad, n_t, jb.hole0, jb.gap, alpha, work, part2);
+        for (int v = tid; v < n_v; v += ST)
+          jb.pred[v] = coef * (Nd * Nd * work[v] - Nd * (double)jb.s[jb.hole0 + v] * sa - Nd * ssa + Qd * sa);
+      }
     } else
-    for (int v0i = 4 * warp; v0i < n_v; v0i += 4 * (ST / 32)) {
+    for (int v0i = 4 * (warp + (ST / 32) * crank); v0i < n_v; v0i += 4 * (ST / 32) * CL) {
       int pv[4];
       bool fast = true;
 #pragma unroll
@@ -639,7 +746,7 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
       }
     }
   } else {
-  for (int v = warp; v < n_v; v += ST / 32) {
+  for (int v = warp + (ST / 32) * crank; v < n_v; v += (ST / 32) * CL) {
     const int pv = jb.vpos[v];
     double d0 = 0.0, d1 = 0.0, d2 = 0.0, d3 = 0.0;
     if (CONTIG && !C16 && pv >= n_t) {
@@ -673,7 +780,8 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
     if (lane == 0) jb.pred[v] = coef * (Nd * Nd * d - Nd * (double)jb.s[pv] * sa - Nd * ssa + Qd * sa);
   }
   }
-  __syncthreads();
+  team_sync<CL>();                    // (CL = 2: the partner's half of the predictions is visible in global memory)
+  if (crank != 0) return;             // the accuracy is one CTA's work; nothing of this CTA is read remotely any more
 
   double sy = 0.0, sp = 0.0;
   for (int v = tid; v < n_v; v += ST) {
@@ -824,7 +932,7 @@ int g_solve_mixed_smem_max = 0;
 }  // namespace
 
 static inline int solve_mixed_smem_bytes(int ntp) {
-  const int fixed = (ntp + 4 * 512 + ST / 32) * (int)sizeof(double) + (ntp + NB + (ST / 32) * NB) * (int)sizeof(float);
+  const int fixed = (ntp + 4 * 512 + ST / 32) * (int)sizeof(double) + (ntp + NB + (ST / 32) * NB + 2 * NB) * (int)sizeof(float);
   return ntp > MIXED_SMEM_NTP ? fixed : fixed + ntp * (int)(sizeof(double) + sizeof(int));
 }
 
@@ -834,16 +942,22 @@ cudaError_t tb_solve_mixed_init() {
   auto set = [&](const void* fn) {
     if (e == cudaSuccess) e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, g_solve_mixed_smem_max);
   };
-  set((const void*)solve_mixed_kernel<true, false, false, false>);
-  set((const void*)solve_mixed_kernel<false, false, false, false>);
-  set((const void*)solve_mixed_kernel<true, true, false, false>);
-  set((const void*)solve_mixed_kernel<false, true, false, false>);
-  set((const void*)solve_mixed_kernel<true, false, true, false>);
-  set((const void*)solve_mixed_kernel<false, false, true, false>);
-  set((const void*)solve_mixed_kernel<true, true, true, false>);
-  set((const void*)solve_mixed_kernel<false, true, true, false>);
-  set((const void*)solve_mixed_kernel<true, false, true, true>);
-  set((const void*)solve_mixed_kernel<true, true, true, true>);
+  set((const void*)solve_mixed_kernel<true, false, false, false, 1>);
+  set((const void*)solve_mixed_kernel<false, false, false, false, 1>);
+  set((const void*)solve_mixed_kernel<true, true, false, false, 1>);
+  set((const void*)solve_mixed_kernel<false, true, false, false, 1>);
+  set((const void*)solve_mixed_kernel<true, false, true, false, 1>);
+  set((const void*)solve_mixed_kernel<false, false, true, false, 1>);
+  set((const void*)solve_mixed_kernel<true, true, true, false, 1>);
+  set((const void*)solve_mixed_kernel<false, true, true, false, 1>);
+  set((const void*)solve_mixed_kernel<true, false, true, true, 1>);
+  set((const void*)solve_mixed_kernel<true, true, true, true, 1>);
+  set((const void*)solve_mixed_kernel<true, false, false, false, 2>);
+  set((const void*)solve_mixed_kernel<true, true, false, false, 2>);
+  set((const void*)solve_mixed_kernel<true, false, true, false, 2>);
+  set((const void*)solve_mixed_kernel<true, true, true, false, 2>);
+  set((const void*)solve_mixed_kernel<true, false, true, true, 2>);
+  set((const void*)solve_mixed_kernel<true, true, true, true, 2>);
   return e;
 }
 
@@ -853,25 +967,53 @@ bool tb_solve_mixed_fits(int ntp) { return solve_mixed_smem_bytes(ntp) <= 220 * 
 // (vectorised symmetric mat-vec); otherwise positions are looked up per element.
 // hole != 0 (with contiguous and c16): some row set is contiguous with one aligned hole (see TbRowSet).
 cudaError_t tb_launch_solve_mixed(const TbSolveMixedJob* d_jobs, int n_jobs, int ntp, int contiguous, int c16, int hole,
-                                  cudaStream_t st) {
+                                  cudaStream_t st, int n_sm, int pair_mode) {
   const int smem = solve_mixed_smem_bytes(ntp);
   if (smem > g_solve_mixed_smem_max) return cudaErrorInvalidConfiguration;
   const bool big = ntp > MIXED_SMEM_NTP;
+  // two CTAs per matrix when the batch would leave more than half of the CTA slots empty (pair_mode: 0 never, 1 auto,
+  // 2 always); contiguous kernels only
+  const int slots = n_sm * ((smem + 1024) * 2 <= 228 * 1024 ? 2 : 1);
+  const bool pair = contiguous && pair_mode != 0 && (pair_mode == 2 || 2 * n_jobs <= slots);
+  if (pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * n_jobs);
+    cfg.blockDim = dim3(ST);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    if (hole && c16) {
+      if (big) return cudaLaunchKernelEx(&cfg, solve_mixed_kernel<true, true, true, true, 2>, d_jobs);
+      return cudaLaunchKernelEx(&cfg, solve_mixed_kernel<true, false, true, true, 2>, d_jobs);
+    }
+    if (c16) {
+      if (big) return cudaLaunchKernelEx(&cfg, solve_mixed_kernel<true, true, true, false, 2>, d_jobs);
+      return cudaLaunchKernelEx(&cfg, solve_mixed_kernel<true, false, true, false, 2>, d_jobs);
+    }
+    if (big) return cudaLaunchKernelEx(&cfg, solve_mixed_kernel<true, true, false, false, 2>, d_jobs);
+    return cudaLaunchKernelEx(&cfg, solve_mixed_kernel<true, false, false, false, 2>, d_jobs);
+  }
   if (hole && contiguous && c16) {
-    if (big) solve_mixed_kernel<true, true, true, true><<<n_jobs, ST, smem, st>>>(d_jobs);
-    else solve_mixed_kernel<true, false, true, true><<<n_jobs, ST, smem, st>>>(d_jobs);
+    if (big) solve_mixed_kernel<true, true, true, true, 1><<<n_jobs, ST, smem, st>>>(d_jobs);
+    else solve_mixed_kernel<true, false, true, true, 1><<<n_jobs, ST, smem, st>>>(d_jobs);
     return cudaGetLastError();
   }
   const int which = (contiguous ? 4 : 0) | (big ? 2 : 0) | (c16 ? 1 : 0);
   switch (which) {
-    case 0: solve_mixed_kernel<false, false, false, false><<<n_jobs, ST, smem, st>>>(d_jobs); break;
-    case 1: solve_mixed_kernel<false, false, true, false><<<n_jobs, ST, smem, st>>>(d_jobs); break;
-    case 2: solve_mixed_kernel<false, true, false, false><<<n_jobs, ST, smem, st>>>(d_jobs); break;
-    case 3: solve_mixed_kernel<false, true, true, false><<<n_jobs, ST, smem, st>>>(d_jobs); break;
-    case 4: solve_mixed_kernel<true, false, false, false><<<n_jobs, ST, smem, st>>>(d_jobs); break;
-    case 5: solve_mixed_kernel<true, false, true, false><<<n_jobs, ST, smem, st>>>(d_jobs); break;
-    case 6: solve_mixed_kernel<true, true, false, false><<<n_jobs, ST, smem, st>>>(d_jobs); break;
-    default: solve_mixed_kernel<true, true, true, false><<<n_jobs, ST, smem, st>>>(d_jobs); break;
+    case 0: solve_mixed_kernel<false, false, false, false, 1><<<n_jobs, ST, smem, st>>>(d_jobs); break;
+    case 1: solve_mixed_kernel<false, false, true, false, 1><<<n_jobs, ST, smem, st>>>(d_jobs); break;
+    case 2: solve_mixed_kernel<false, true, false, false, 1><<<n_jobs, ST, smem, st>>>(d_jobs); break;
+    case 3: solve_mixed_kernel<false, true, true, false, 1><<<n_jobs, ST, smem, st>>>(d_jobs); break;
+    case 4: solve_mixed_kernel<true, false, false, false, 1><<<n_jobs, ST, smem, st>>>(d_jobs); break;
+    case 5: solve_mixed_kernel<true, false, true, false, 1><<<n_jobs, ST, smem, st>>>(d_jobs); break;
+    case 6: solve_mixed_kernel<true, true, false, false, 1><<<n_jobs, ST, smem, st>>>(d_jobs); break;
+    default: solve_mixed_kernel<true, true, true, false, 1><<<n_jobs, ST, smem, st>>>(d_jobs); break;
   }
   return cudaGetLastError();
 }

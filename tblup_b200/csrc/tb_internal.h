@@ -125,6 +125,7 @@ struct TbCtx {
   int fuse_scale = 1;             // 1: with one contiguous row set the scaled fp32 matrix is never written by a pass of
                                   //    its own (formed inside the Cholesky updates, or -- fuse_in_gram -- by the Gram epilogue)
   int fuse_in_gram = 0;           // 1: round-1 behaviour, the Gram epilogue writes the whole fp32 matrix
+  int solve_pair = 1;             // solve with two CTAs per matrix: 0 never, 1 when the batch leaves half the CTA slots empty, 2 always
   int gram_pair = 2;              // Gram schedule: 0 one CTA per tile, 1 clusters of two CTAs sharing the B tile by TMA multicast,
                                   // 2 (default) tcgen05 CTA pairs: cta_group::2 MMAs, M = 256, each CTA holds half of the B tile
   int n_sm = 148;
@@ -273,11 +274,12 @@ struct TbSolveMixedJob {
   int n_t, n_v, ntp, rpad;
   int hole0, gap, valid_in_hole;   // see TbRowSet (contiguous kernels only)
   double lambda;
+  int cmax;                // bound on the cross-products of this genome: 4 k (every dosage <= 2)
 };
 cudaError_t tb_solve_mixed_init();
 bool tb_solve_mixed_fits(int ntp);
 cudaError_t tb_launch_solve_mixed(const TbSolveMixedJob* d_jobs, int n_jobs, int ntp, int contiguous, int c16, int hole,
-                                  cudaStream_t st);
+                                  cudaStream_t st, int n_sm = 148, int pair_mode = 1);
 // col_end > 0: only columns [0, col_end) (the first outer block column of the factorisation)
 cudaError_t tb_launch_scale32(const TbScaleJob* d_jobs, int n_jobs, int ntp, float* L32, int c16, cudaStream_t st,
                               int col_end = 0);

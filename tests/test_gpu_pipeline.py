@@ -444,3 +444,33 @@ def test_scattered_row_set_runs_as_a_prefix_after_row_permutation():
         assert np.abs(c - want).max() < 1e-9
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("name", ["fit_small", "fit_mid"])
+def test_two_ctas_per_matrix_solve_matches_one(name):
+    """Small batches run the solve with a cluster of two CTAs per matrix (half of every block step, of the mat-vec work
+    units and of the validation rows each; partial sums exchanged through distributed shared memory).  Forced on and
+    off: same fitness (to the refinement tolerance) for the base split, the testing split and k-fold row sets, and
+    against the reference fixtures."""
+    from tblup_b200 import engine as E
+    g = load_golden(name)
+    x, y, h2 = g["x"], g["y"], float(g["h2"])
+    tr, va, te = g["train"], g["valid"], g["test"]
+    f_tr = unpack(g["fold_train_flat"], g["fold_train_off"])
+    f_va = unpack(g["fold_valid_flat"], g["fold_valid_off"])
+    extra = [(np.concatenate([tr, va]), te)] + [(t, v) for t, v in zip(f_tr, f_va)]
+    eng, perm = _engine(x, y, tr, va, te, extra_sets=extra)
+    genomes = [gen for gen in unpack(g["genomes_flat"], g["genomes_off"])]
+    try:
+        out = {}
+        for mode in (0, 2):
+            eng.set_option("solve_pair", mode)
+            out[mode] = [eng.evaluate(genomes, slots=[0], h2=h2, mode=E.MODE_AUTO),
+                         eng.evaluate(genomes, slots=[1], h2=h2, mode=E.MODE_AUTO),
+                         eng.evaluate(genomes, slots=list(range(2, 2 + len(f_tr))), h2=h2, mode=E.MODE_AUTO)]
+            assert eng.last_precision() == "mixed"
+        for a, b in zip(out[0], out[2]):
+            assert np.array_equal(np.isnan(a), np.isnan(b)) and np.nanmax(np.abs(a - b)) < 1e-9
+        assert np.abs(out[2][0][:, 0] - g["ref_blup"]).max() < FIT_TOL
+    finally:
+        eng.close()
