@@ -181,8 +181,11 @@ __device__ void hole_predict16(const int16_t* __restrict__ C, int rpad, int n_t,
 template <int CL>
 __device__ __forceinline__ void team_sync() {
   if (CL > 1) {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    // CTA barrier first: the cluster barrier is issued from inline PTX, so the compiler does not know that the warps
+    // must have reconverged (callers sit right behind `if (lane == 0)` blocks); the non-.aligned forms tolerate the rest
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
   } else {
     __syncthreads();
   }

@@ -79,8 +79,8 @@ __device__ __forceinline__ uint32_t cluster_ctarank() {
   return r;
 }
 __device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
 }
 
 // shared::cluster address of the same shared-memory offset in CTA `rank` of the cluster
