@@ -531,7 +531,7 @@ def main():
             eng.set_option("profile", 0)
             if precision == "mixed" and hi > lo:
                 last = (hi - lo - 1) % wave + 1          # jobs in the last wave (the one the debug view points at)
-                res["mean_sweeps"] = float(np.mean([eng.debug_fetch(E.DBG_SWEEPS, j)[0] for j in range(min(last * S, 64))]))
+                res["mean_sweeps"] = float(np.mean([eng.debug_fetch(E.DBG_SWEEPS, j)[0] & 255 for j in range(min(last * S, 64))]))
         for i in range(max(1, min(args.warmup, 2))):
             fit_host = step_e2e(i)
         barrier()

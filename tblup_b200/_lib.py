@@ -7,7 +7,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtblup_b200.so")
+LIB_PATH = os.environ.get("TBLUP_B200_LIB") or os.path.join(_HERE, "libtblup_b200.so")   # (override: A/B of library builds)
 
 # every symbol include/tblup_b200.h declares: name -> (restype, argtypes)
 _i32p = C.POINTER(C.c_int32)

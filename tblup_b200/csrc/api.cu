@@ -585,7 +585,7 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
   // host time spent issuing the evaluation (everything above is asynchronous): diagnostics, "last_issue_us"
   c->last_issue_us = (long long)std::chrono::duration_cast<std::chrono::microseconds>(
                          std::chrono::steady_clock::now() - t_host0).count();
-  if (mixed && allow_fallback && c->stop_after < 0) return fp64_fallback(c, slots, n_slots, h2, mode_rule, d_fit);
+  if (mixed && allow_fallback && c->stop_after < 0 && !c->no_fallback) return fp64_fallback(c, slots, n_slots, h2, mode_rule, d_fit);
   return 0;
 }
 
@@ -1283,6 +1283,7 @@ int tb_set_option(tb_ctx* c, const char* name, long long value) {
   else if (s == "precision") c->precision = value != 0;
   else if (s == "fuse_scale") c->fuse_scale = value != 0;
   else if (s == "fuse_in_gram") c->fuse_in_gram = value != 0;
+  else if (s == "no_fallback") c->no_fallback = value != 0;     // diagnostics: keep the mixed-precision result of failed jobs
   else if (s == "solve_pair") c->solve_pair = value < 0 ? 0 : value > 2 ? 2 : (int)value;
   else if (s == "gram_pair") c->gram_pair = value < 0 ? 0 : value > 2 ? 2 : (int)value;
   else if (s == "wide_panel") c->wide_panel = value != 0;

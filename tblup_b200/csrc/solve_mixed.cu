@@ -696,7 +696,8 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
   }
   if (!big && crank == 0)
     for (int a = tid; a < ntp; a += ST) jb.alpha[a] = alpha[a];
-  if (tid == 0 && crank == 0 && jb.sweeps) *jb.sweeps = sweeps;
+  // diagnostics: sweeps in the low byte, + 256 when the refinement did not reach the tolerance, + 512 on a pivot failure
+  if (tid == 0 && crank == 0 && jb.sweeps) *jb.sweeps = sweeps | (solved ? 0 : 256) | (*jb.status != 0 ? 512 : 0);
   if (tid == 0 && crank == 0 && jb.fail && (!solved || *jb.status != 0)) *jb.fail = 1;
 
   // ---- predictions on the validation animals
