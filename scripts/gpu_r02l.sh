@@ -1,7 +1,7 @@
 #!/bin/bash
 # guarded run: a short smoke of the two-CTA solve first (strict timeout), everything else only if it passes
 mkdir -p gpurun_out
-timeout 150 python -m pytest tests/test_gpu_pipeline.py -m gpu -x -q -k "two_ctas or fitness_matches_reference" > gpurun_out/r02l_smoke.log 2>&1; rc=$?; echo "smoke rc=$rc"
+timeout 150 python -m pytest tests/test_gpu_pipeline.py -m gpu -x -q -k "two_ctas or fitness_matches_reference or small_matrices" > gpurun_out/r02l_smoke.log 2>&1; rc=$?; echo "smoke rc=$rc"
 tail -5 gpurun_out/r02l_smoke.log | cut -c1-300
 if [ $rc -ne 0 ]; then echo "smoke failed: stopping"; exit 1; fi
 timeout 900 python -m pytest tests/test_gpu_pipeline.py tests/test_gpu_fullsize.py tests/test_gpu_packed.py tests/test_gpu_knockout.py tests/test_gpu_large.py -m gpu -x -q > gpurun_out/r02l_tests.log 2>&1; echo "tests rc=$?"

@@ -1283,6 +1283,7 @@ int tb_set_option(tb_ctx* c, const char* name, long long value) {
   else if (s == "precision") c->precision = value != 0;
   else if (s == "fuse_scale") c->fuse_scale = value != 0;
   else if (s == "fuse_in_gram") c->fuse_in_gram = value != 0;
+  else if (s == "solve_debug") tb_solve_mixed_set_debug((int)value);
   else if (s == "no_fallback") c->no_fallback = value != 0;     // diagnostics: keep the mixed-precision result of failed jobs
   else if (s == "solve_pair") c->solve_pair = value < 0 ? 0 : value > 2 ? 2 : (int)value;
   else if (s == "gram_pair") c->gram_pair = value < 0 ? 0 : value > 2 ? 2 : (int)value;

@@ -21,7 +21,8 @@ constexpr int NB = TB_NB;
 constexpr int ST = 512;
 constexpr int MAX_SWEEPS = 5;
 constexpr int MIXED_SMEM_NTP = 4096;  // up to this many (padded) training animals alpha stays in shared memory
-constexpr double REL_TOL = 1e-8;     // stop when the PREDICTED remaining error is below 1e-8 of the solution
+constexpr double REL_TOL = 1e-8;
+     // stop when the PREDICTED remaining error is below 1e-8 of the solution
                                      // (fitness bar of BASELINE.json: 1e-6 absolute)
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -183,6 +184,7 @@ __device__ __forceinline__ void team_sync() {
   if (CL > 1) {
     // CTA barrier first: the cluster barrier is issued from inline PTX, so the compiler does not know that the warps
     // must have reconverged (callers sit right behind `if (lane == 0)` blocks); the non-.aligned forms tolerate the rest
+    __syncwarp();
     __syncthreads();
     asm volatile("barrier.cluster.arrive.release;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
@@ -474,13 +476,20 @@ __device__ void sym_matvec16_1p(const CT* __restrict__ C, int rpad, int n_t, int
         yv += __shfl_xor_sync(0xffffffffu, yv, 1);
         if ((lane & 7) == 0)
           atomicAdd(outq + r + 4 * h + 2 * (lane >> 4) + ((lane >> 3) & 1), (unsigned long long)__double2ll_rn(yv * scale));
+        __syncwarp();      // the 64-bit shared atomic is a CAS spin loop: bring the lanes back together (see below)
       }
     }
     if (col_ok) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) atomicAdd(outq + c0 + e, (unsigned long long)__double2ll_rn(ac[e] * scale));
     }
+    __syncwarp();
   }
+  // MEASURED (r02): without this reconvergence a warp that ran the CAS-loop atomics above stayed split, reached the
+  // block barriers below in pieces and ended up one barrier behind the others -- with a single work unit (n_t <= 128)
+  // the triangular solves then read a stale partial sum of that warp (fp64 fallback on every small matrix), and the
+  // cluster barrier of the two-CTA variant dead-locked.
+  __syncwarp();
   if (CL > 1) {
     // own + partner's partial vector (integers: the order does not matter); the partner reads ours at the same time,
     // so nothing is overwritten before both have read a chunk
@@ -934,6 +943,8 @@ __global__ void fuse_terms_kernel(const TbScaleJob* __restrict__ jobs, int ntp, 
 int g_solve_mixed_smem_max = 0;
 
 }  // namespace
+
+void tb_solve_mixed_set_debug(int) {}
 
 static inline int solve_mixed_smem_bytes(int ntp) {
   const int fixed = (ntp + 4 * 512 + ST / 32) * (int)sizeof(double) + (ntp + NB + (ST / 32) * NB + 2 * NB) * (int)sizeof(float);

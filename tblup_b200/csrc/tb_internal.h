@@ -278,6 +278,7 @@ struct TbSolveMixedJob {
   int cmax;                // bound on the cross-products of this genome: 4 k (every dosage <= 2)
 };
 cudaError_t tb_solve_mixed_init();
+void tb_solve_mixed_set_debug(int v);
 bool tb_solve_mixed_fits(int ntp);
 cudaError_t tb_launch_solve_mixed(const TbSolveMixedJob* d_jobs, int n_jobs, int ntp, int contiguous, int c16, int hole,
                                   cudaStream_t st, int n_sm = 148, int pair_mode = 1);
