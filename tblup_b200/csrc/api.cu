@@ -496,8 +496,8 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
       std::string e;
       // (the Gram no longer writes the scaled matrix: with fuse_scale the Cholesky updates form it from C on the fly)
       cudaError_t ce = tb_launch_gram_tc(d_panel, Wc, rpad, kstride_b, d_kb, d_tiles, n_tiles, d_C, c->n_sm, st, &e,
-                                         (fuse_scale && c->fuse_in_gram) ? d_scale : nullptr, d_L32, max_ntp, c16 ? 1 : 0,
-                                         fp4 ? 1 : 0, gram_pair);
+                                         (fuse_scale && c->fuse_in_gram) ? d_scale : nullptr, d_L32,
+                                         c->gram_experiment ? -c->gram_experiment : max_ntp, c16 ? 1 : 0, fp4 ? 1 : 0, gram_pair);
       if (ce != cudaSuccess) return fail(c, "gram launch: " + (e.empty() ? std::string(cudaGetErrorString(ce)) : e), -2);
     }
     span_end(c, sp);
@@ -1286,6 +1286,7 @@ int tb_set_option(tb_ctx* c, const char* name, long long value) {
   else if (s == "solve_debug") tb_solve_mixed_set_debug((int)value);
   else if (s == "no_fallback") c->no_fallback = value != 0;     // diagnostics: keep the mixed-precision result of failed jobs
   else if (s == "solve_pair") c->solve_pair = value < 0 ? 0 : value > 2 ? 2 : (int)value;
+  else if (s == "gram_experiment") c->gram_experiment = (int)value;   // timing experiments only (results are wrong): 1 = no stores, 2 = no epilogue
   else if (s == "gram_pair") c->gram_pair = value < 0 ? 0 : value > 2 ? 2 : (int)value;
   else if (s == "wide_panel") c->wide_panel = value != 0;
   else if (s == "narrow_c") c->narrow_c = value != 0;

@@ -287,6 +287,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
       for (int c = chalf * 4; c < (chalf + 1) * 4 && c < BN / 32; ++c) {
         const int col0 = tj * BN + c * 32;
         if (col0 >= rpad || col0 > row_hi || ti * BM >= rpad) continue;   // outside the matrix / strictly above the diagonal
+        if (!FUSE && fz.ntp_all == -2) continue;                         // experiment: no epilogue work at all
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * ACC_STRIDE + c * 32, v);
         tmem_ld_wait();
@@ -309,7 +310,8 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__
 #pragma unroll
           for (int it = 0; it < 4; ++it) {
             const uint4 u = stage_read16(stg, lane, it);
-            *reinterpret_cast<uint4*>(cwarp16 + (size_t)(8 * it + rl) * rpad + col0 + 2 * gl) = u;
+            if (FUSE || fz.ntp_all != -1)                                  // (experiment -1: everything but the global stores)
+              *reinterpret_cast<uint4*>(cwarp16 + (size_t)(8 * it + rl) * rpad + col0 + 2 * gl) = u;
           }
           __syncwarp();
         } else {

@@ -126,6 +126,7 @@ struct TbCtx {
                                   //    its own (formed inside the Cholesky updates, or -- fuse_in_gram -- by the Gram epilogue)
   int fuse_in_gram = 0;           // 1: round-1 behaviour, the Gram epilogue writes the whole fp32 matrix
   int no_fallback = 0;
+  int gram_experiment = 0;
   int solve_pair = 1;             // solve with two CTAs per matrix: 0 never, 1 when the batch leaves half the CTA slots empty, 2 always
   int gram_pair = 2;              // Gram schedule: 0 one CTA per tile, 1 clusters of two CTAs sharing the B tile by TMA multicast,
                                   // 2 (default) tcgen05 CTA pairs: cta_group::2 MMAs, M = 256, each CTA holds half of the B tile
