@@ -59,9 +59,9 @@ DEFAULT_WORKLOAD = "c2_5000x50000_k5001_pop1000"
 # captures (profiles/README.md says how each was taken); filled in after every re-profile
 NCU_TRAFFIC = {
     "solve_c32": {"bytes_per_unit": 164.06e6, "source": "profiles/r01p_solve_raw.csv"},
-    "solve_c16": {"bytes_per_unit": 112.05e6, "source": "profiles/r01q_solve_raw.csv (1 000 matrices per launch)"},
+    "solve_c16": {"bytes_per_unit": 91.13e6, "source": "profiles/r02_solve_raw.csv (1 000 matrices per launch)"},
     "gram_fused_c16": {"bytes_per_unit": 58.93e6, "source": "profiles/r01q_gram_raw.csv (1 000 genomes per launch)"},
-    "gram_fp4_fused_c16": {"bytes_per_unit": 48.43e6, "source": "profiles/r01r_gram_raw.csv (1 000 genomes per launch)"},
+    "gram_fp4_fused_c16": {"bytes_per_unit": 35.55e6, "source": "profiles/r02_gram_raw.csv (1 000 genomes per launch)"},
 }
 H2 = 0.4
 METRIC = "gblup_fitness_evals_per_sec"
@@ -336,15 +336,17 @@ def chol_update_flops(ntp, nb=64):
     return tot
 
 
-def chol_update_bytes(ntp, ob=256):
+def chol_update_bytes(ntp, ob=256, entry_read_bytes=4):
     """Algorithmic DRAM bytes of the outer Cholesky updates of one matrix in mixed precision: the fp32 block column
     is read and written once (8 B per entry of the rows at and below the diagonal block) and the fp16 row operand
-    L[rows, 0:c0] is streamed once per block column (2 B per entry); the 256-row column operand stays in L2."""
+    L[rows, 0:c0] is streamed once per block column (2 B per entry); the 256-row column operand stays in L2.
+    entry_read_bytes: 4 when the update reads the fp32 matrix, 2 / 4 when it forms the entries from int16 / int32
+    cross-products (round 2: nothing is read-modify-written, the block column is written once as fp32)."""
     tot = 0
     for c0 in range(ob, ntp, ob):
         w = min(ob, ntp - c0)
         rows = ntp - c0
-        tot += rows * w * 8 + rows * c0 * 2
+        tot += rows * w * (4 + entry_read_bytes) + rows * c0 * 2
     return tot
 
 
@@ -649,7 +651,9 @@ def main():
             if precision == "mixed":
                 upd_flops = chol_update_flops(ntp, 256) * n_mats
                 upd_kernel = ("tf32_gemm_kernel<F16> (outer left-looking Cholesky update on the fp16 copy of the factor, "
-                              "tcgen05 kind::f16, M128 x N256, fp32 accumulate)")
+                              "tcgen05 kind::f16, M128 x N256, fp32 accumulate%s)"
+                              % ("; the block column of the scaled matrix is formed from the integer cross-products in the "
+                                 "epilogue" if fused else ""))
                 upd_peak, upd_peak_src = bf16, bf16_src + " (fp16 operands run at the bf16 rate)"
             else:
                 upd_flops = chol_update_flops(ntp, 64) * n_mats
@@ -662,7 +666,7 @@ def main():
                          "peak_source": upd_peak_src, "launches": int(upd_launches),
                          "avg_launch_ms": upd_ms / max(1, upd_launches), "share_of_step": upd_ms / ms_i}
             if precision == "mixed" and upd_ms > 0:
-                upd_bytes = chol_update_bytes(ntp, 256)
+                upd_bytes = chol_update_bytes(ntp, 256, (2 if c16 else 4) if fused else 4)
                 upd_gbs = upd_bytes * n_mats / (upd_ms * 1e-3) / 1e9
                 rl_update = {"bound": "hbm", "kernel": upd_kernel, "achieved": upd_gbs, "peak": hbm, "unit": "GB/s",
                              "frac": upd_gbs / hbm, "traffic": None, "algorithmic_bytes_per_matrix": upd_bytes,
@@ -699,10 +703,10 @@ def main():
             gram_traffic = ncu.get("gram_fp4_fused_c16" if fp4 else "gram_fused_c16") if (fused and c16) else None
             gram_peak = peak_mxf4_sus if fp4 else peak_i8_sus
             rl_gram = {"bound": "tensor",
-                       "kernel": ("gram_tc_kernel (tcgen05 kind::mxf4 on E2M1 dosages, block scales 2^0, M128 x N224 x K64, "
-                                  "fp32 in TMEM holding exact integers%s)" if fp4 else
-                                  "gram_tc_kernel (tcgen05 kind::i8, M128 x N256 x K32, s32 in TMEM%s)")
-                                 % ("; epilogue also writes the scaled fp32 matrix" if fused else ""),
+                       "kernel": ("gram_tc_kernel (tcgen05 cta_group::2 kind::mxf4 on E2M1 dosages, block scales 2^0, CTA pairs "
+                                  "M256 x N224 x K64, 6-stage TMA ring, fp32 in TMEM holding exact integers%s)" if fp4 else
+                                  "gram_tc_kernel (tcgen05 cta_group::2 kind::i8, CTA pairs M256 x N256 x K32, s32 in TMEM%s)")
+                                 % ("; writes only the integer cross-products" if fused else ""),
                        "achieved": gram_tops, "peak": gram_peak, "unit": "TOP/s",
                        "frac": gram_tops / gram_peak if gram_tops and gram_peak else None,
                        "traffic": gram_traffic["bytes_per_unit"] * p_loc if gram_traffic else None,
@@ -752,7 +756,8 @@ def main():
             "config": base_config(args, wl),
             "details": {"pop_total": p_primary, "pop_per_gpu": prim["p_local"], "n_train": int(n_t), "n_valid": int(n_v),
                         "individuals_per_wave": prim["wave"], "precision": precision, "genotype_storage": args.storage,
-                        "cross_product_storage": "int16" if c16 else "int32", "scaling_fused_into_gram": fused,
+                        "cross_product_storage": "int16" if c16 else "int32",
+                        "scaled_matrix_formed_inside_cholesky_updates": fused,
                         "gram_operands": "e2m1 (fp4)" if fp4 else "int8",
                         "genotype_bytes_resident": eng.resident_genotype_bytes(),
                         "l2": "inputs larger than L2 (each step streams >20 GB of per-genome panels and matrices)",

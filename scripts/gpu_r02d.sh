@@ -10,7 +10,7 @@ python - <<'PY'
 import json
 try:
     d = json.loads([l for l in open("gpurun_out/r02d_bench_n2.log") if l.startswith("{")][-1])
-    print("N=2 value", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"]["value"], "parity", d["parity_ok"], d["details"]["cross_product_storage"], d["details"]["scaling_fused_into_gram"])
+    print("N=2 value", d["value"], "ms", d["ms_per_step"], "e2e", d["e2e"]["value"], "parity", d["parity_ok"], d["details"]["cross_product_storage"], d["details"]["scaled_matrix_formed_inside_cholesky_updates"])
     print("other", json.dumps(d["details"]["other_scaling"]))
 except Exception as e:
     print("no line", e)

@@ -227,7 +227,9 @@ __device__ __forceinline__ float warp_sumf(float v) {
 }
 
 // xp: [2][NB] exchange buffer (CL = 2), crank: this CTA's rank in its cluster
-template <int CL>
+// U: column groups per lane and loop trip in the forward sweep (2 for the large-matrix instantiations, which run one
+// CTA per SM with 128 registers: eight 16-byte loads in flight per lane instead of four)
+template <int CL, int U>
 __device__ void apply_minv_f32(const __half* __restrict__ L, const float* __restrict__ Linv, int ntp, float* wf,
                                float* rvec, float* part, float* xp, int crank) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -239,13 +241,29 @@ __device__ void apply_minv_f32(const __half* __restrict__ L, const float* __rest
       const uint4* r0 = reinterpret_cast<const uint4*>(L + (size_t)(kc + 4 * warp) * ntp);
       const size_t rs = ntp / 8;
       float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      for (int c = lane + 32 * crank; c < kc / 8; c += 32 * CL) {
-        const uint4 l0 = r0[c], l1 = r0[rs + c], l2 = r0[2 * rs + c], l3 = r0[3 * rs + c];
-        const float4 z0 = *reinterpret_cast<const float4*>(wf + 8 * c), z1 = *reinterpret_cast<const float4*>(wf + 8 * c + 4);
-        s0 += dot8hf(l0, z0, z1);
-        s1 += dot8hf(l1, z0, z1);
-        s2 += dot8hf(l2, z0, z1);
-        s3 += dot8hf(l3, z0, z1);
+      for (int c = lane + 32 * crank; c < kc / 8; c += 32 * CL * U) {
+        uint4 l[U][4];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int cu = c + 32 * CL * u;
+          if (cu < kc / 8) {
+            l[u][0] = r0[cu];
+            l[u][1] = r0[rs + cu];
+            l[u][2] = r0[2 * rs + cu];
+            l[u][3] = r0[3 * rs + cu];
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int cu = c + 32 * CL * u;
+          if (cu < kc / 8) {
+            const float4 z0 = *reinterpret_cast<const float4*>(wf + 8 * cu), z1 = *reinterpret_cast<const float4*>(wf + 8 * cu + 4);
+            s0 += dot8hf(l[u][0], z0, z1);
+            s1 += dot8hf(l[u][1], z0, z1);
+            s2 += dot8hf(l[u][2], z0, z1);
+            s3 += dot8hf(l[u][3], z0, z1);
+          }
+        }
       }
       s0 = warp_sumf(s0);
       s1 = warp_sumf(s1);
@@ -376,7 +394,7 @@ __device__ void apply_minv_f32(const __half* __restrict__ L, const float* __rest
 // the unit; the row partials of four rows are reduced across the warp by a transposing butterfly (6 shuffles per four
 // rows) and added to out[] with shared-memory atomics, as are the column sums at the end of the unit (about 40
 // warp-level atomics per 16 K entries of C).  The same "prefix with one aligned hole" index mapping as before.
-template <bool HOLE, typename CT, int CL>
+template <bool HOLE, typename CT, int CL, bool WIDE_REGS>
 __device__ void sym_matvec16_1p(const CT* __restrict__ C, int rpad, int n_t, int h0, int gap, const double* alpha,
                                 double amax, int cmax, double* out, int* counter, int crank) {
   constexpr bool W16 = sizeof(CT) == 2;              // int16 cross-products (8-byte loads of 4) or int32 (16-byte loads of 4)
@@ -419,7 +437,7 @@ __device__ void sym_matvec16_1p(const CT* __restrict__ C, int rpad, int n_t, int
     }
     const CT* colp = C + U(c0);
     const bool diag_unit = u == 0;                    // SW == RU: only a strip's first unit reaches its diagonal
-    constexpr int RB = W16 ? 8 : 4;                   // rows in flight per lane (64 bytes of loads either way)
+    constexpr int RB = (W16 || WIDE_REGS) ? 8 : 4;    // rows in flight per lane (64 bytes of loads; 128 with 128 registers)
     for (int r = r0; r < r1; r += RB) {               // n_t % 4 == 0
       uint4 v[RB];                                    // int16: .x, .y hold the four entries; int32: all four words
 #pragma unroll
@@ -518,13 +536,13 @@ __device__ void sym_matvec16_1p(const CT* __restrict__ C, int rpad, int n_t, int
 
 // (C alpha)_a over the training animals into work[a]; CONTIG: training animal b sits at universe position b.
 // CT: element type of the stored cross-products (int32_t, or int16_t in C16 mode).
-template <bool CONTIG, bool HOLE, typename CT, int CL>
+template <bool CONTIG, bool HOLE, typename CT, int CL, bool WIDE_REGS>
 __device__ void sym_matvec(const CT* __restrict__ C, int rpad, int n_t, int h0, int gap, const int* tp,
                            const double* alpha, double amax, int cmax, double* work, double* part2, int crank) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if constexpr (CONTIG) {
     // one pass over the triangle for both storage widths (HOLE only occurs with the int16 layout)
-    sym_matvec16_1p<HOLE, CT, CL>(C, rpad, n_t, h0, gap, alpha, amax, cmax, work, reinterpret_cast<int*>(part2), crank);
+    sym_matvec16_1p<HOLE, CT, CL, WIDE_REGS>(C, rpad, n_t, h0, gap, alpha, amax, cmax, work, reinterpret_cast<int*>(part2), crank);
   } else {
     for (int a = warp; a < n_t; a += ST / 32) {
       const int pa = tp[a];
@@ -574,7 +592,7 @@ __device__ void sym_matvec(const CT* __restrict__ C, int rpad, int n_t, int h0, 
 }
 
 template <bool CONTIG, bool BIG, bool C16, bool HOLE, int CL>
-__global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJob* __restrict__ jobs) {
+__global__ void __launch_bounds__(ST, BIG ? 1 : 2) solve_mixed_kernel(const TbSolveMixedJob* __restrict__ jobs) {
   static_assert(CL == 1 || CONTIG, "two CTAs per matrix only with the contiguous kernels");
   using CT = typename std::conditional<C16, int16_t, int32_t>::type;
   extern __shared__ double msm[];
@@ -620,7 +638,7 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
     wf[a] = (float)jb.y_t[a];
   }
   __syncthreads();
-  apply_minv_f32<CL>(static_cast<const __half*>(jb.L16), jb.Linv32, ntp, wf, rvec, part, xp, crank);
+  apply_minv_f32<CL, BIG ? 2 : 1>(static_cast<const __half*>(jb.L16), jb.Linv32, ntp, wf, rvec, part, xp, crank);
   // (BIG: alpha is the job's global vector -- with CL = 2 both CTAs store the same values, then meet at a barrier)
   for (int a = tid; a < ntp; a += ST) alpha[a] = (double)wf[a];
   if (BIG) team_sync<CL>();
@@ -641,7 +659,7 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
     const double amax_now = block_max(l2, red);
     if (sweeps == MAX_SWEEPS) break;
     if (!(amax_now < 1e300)) break;                     // non-finite first solve (overflowing factor): leave it to fp64
-    sym_matvec<CONTIG, HOLE, CT, CL>(C, rpad, n_t, jb.hole0, jb.gap, tp, alpha, amax_now, jb.cmax, work, part2, crank);   // work[a] = (C alpha)_a
+    sym_matvec<CONTIG, HOLE, CT, CL, BIG>(C, rpad, n_t, jb.hole0, jb.gap, tp, alpha, amax_now, jb.cmax, work, part2, crank);   // work[a] = (C alpha)_a
     for (int a = tid; a < ntp; a += ST) {
       double rr = 0.0;
       if (a < n_t) {
@@ -652,7 +670,7 @@ __global__ void __launch_bounds__(ST, 2) solve_mixed_kernel(const TbSolveMixedJo
       wf[a] = (float)rr;
     }
     __syncthreads();
-    apply_minv_f32<CL>(static_cast<const __half*>(jb.L16), jb.Linv32, ntp, wf, rvec, part, xp, crank);
+    apply_minv_f32<CL, BIG ? 2 : 1>(static_cast<const __half*>(jb.L16), jb.Linv32, ntp, wf, rvec, part, xp, crank);
     double dmax = 0.0, amax = 0.0;
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     if (BIG && CL > 1) {
