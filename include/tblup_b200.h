@@ -197,6 +197,14 @@ int tb_de_set_removed(tb_ctx* ctx, const int32_t* markers, int n);
 int tb_de_ban_genome(tb_ctx* ctx, int which, int32_t* n_removed_out);
 int tb_de_evaluate_testing(tb_ctx* ctx, int slot, double h2, int mode_rule, double* fitness_out);
 
+/* ---- start-up scan of the top-SNPs seeder (tblup/seeder.py:144-160 get_sorted_indices, :202-210 p_value ->
+ * sklearn.feature_selection.f_regression) ------------------------------------------------------------------------
+ * Per-marker sums over a list of animals (original indices, duplicates allowed) with one weight each:
+ * sum_x[j] = sum_i x_ij, sum_xx[j] = sum_i x_ij^2 (exact), sum_xw[j] = sum_i x_ij w_i -- everything f_regression needs
+ * (with w = y - mean(y)) without the dense float64 matrix the reference slices (X[train]); all outputs host, [m] doubles. */
+int tb_marker_stats(tb_ctx* ctx, const int32_t* animals, int n_animals, const double* weights, double* sum_x,
+                    double* sum_xx, double* sum_xw);
+
 /* ---- knockout local search (tblup/local.py:50-76, KnockoutLocalSearch.search) ------------------------------------
  * The reference walks the markers of the best genome in order and calls evaluator.blup(genome[mask], training_indices,
  * validation_indices, data, labels, h2) once per marker (local.py:65-66), keeping the marker out when the fitness

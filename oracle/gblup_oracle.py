@@ -318,3 +318,28 @@ def bed_bytes_loops(x_int):
                     b |= code[int(x_int[a, j])] << (2 * i)
             body.append(b)
     return bytes((0x6C, 0x1B, 0x01)) + bytes(body)
+
+
+# ---- start-up helpers: restatements used by the tests of tblup_b200.splitter / tblup_b200.seeder ----
+
+def ref_pca_split(grm, split=0.8, outliers=False):
+    """tblup/evaluator.py:641-663 from a given GRM: 2-component PCA, squared distance from the centroid, sort, cut."""
+    from sklearn.decomposition import PCA
+    x = PCA(n_components=2).fit_transform(grm)
+    mu = np.mean(x, axis=0)
+    d = ((x - mu) ** 2).sum(axis=1)
+    order = sorted(range(len(d)), key=lambda i: d[i], reverse=outliers)
+    k = int(len(order) * split)
+    return order[:k], order[k:]
+
+
+def ref_seed_scores(x, y, n_training, n_splits=5):
+    """Summed negated p-values of tblup/seeder.py:144-160 with the p_value metric (:202-210), same sklearn calls."""
+    from sklearn.feature_selection import f_regression
+    from sklearn.model_selection import KFold
+    xf = np.asarray(x, dtype=np.float64)
+    yy = np.asarray(y, dtype=np.float64).ravel()
+    scores = np.zeros(xf.shape[1])
+    for train, _ in KFold(n_splits=n_splits).split(np.arange(n_training)):
+        scores += -1 * f_regression(xf[train], yy[train])[1]
+    return scores

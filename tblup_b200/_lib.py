@@ -50,6 +50,7 @@ SYMBOLS = {
     "tb_de_set_removed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int]),
     "tb_de_ban_genome": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "tb_de_evaluate_testing": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p]),
+    "tb_marker_stats": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "tb_knockout": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_void_p,
                               C.c_void_p, C.c_void_p, C.c_void_p]),
     "tb_knockout_scan": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p]),

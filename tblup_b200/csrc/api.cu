@@ -1355,6 +1355,42 @@ int tb_storage_info(const tb_ctx* c, int* storage, uint64_t* bytes) {
   return 0;
 }
 
+int tb_marker_stats(tb_ctx* c, const int32_t* animals, int n_animals, const double* weights, double* sum_x,
+                    double* sum_xx, double* sum_xw) {
+  if (!c) return -1;
+  if (!animals || !weights || !sum_x || !sum_xx || !sum_xw || n_animals <= 0) return fail(c, "tb_marker_stats: null or empty argument");
+  TB_CUDA(c, cudaSetDevice(c->device));
+  std::vector<int> pos(n_animals);
+  for (int i = 0; i < n_animals; ++i) {
+    if (animals[i] < 0 || animals[i] >= c->n) return fail(c, "tb_marker_stats: animal index out of range");
+    pos[i] = c->pos_of[animals[i]];
+  }
+  int* d_pos = nullptr;
+  double *d_w = nullptr, *d_out = nullptr;
+  int rc = 0;
+  auto ck = [&](cudaError_t e, const char* what) {
+    if (e != cudaSuccess && rc == 0) rc = fail(c, std::string("tb_marker_stats ") + what + ": " + cudaGetErrorString(e), -2);
+  };
+  ck(cudaMalloc(&d_pos, (size_t)n_animals * sizeof(int)), "malloc");
+  ck(cudaMalloc(&d_w, (size_t)n_animals * sizeof(double)), "malloc");
+  ck(cudaMalloc(&d_out, (size_t)3 * c->m * sizeof(double)), "malloc");
+  if (rc == 0) {
+    cudaStream_t st = c->stream;
+    ck(cudaMemcpyAsync(d_pos, pos.data(), (size_t)n_animals * sizeof(int), cudaMemcpyHostToDevice, st), "H2D");
+    ck(cudaMemcpyAsync(d_w, weights, (size_t)n_animals * sizeof(double), cudaMemcpyHostToDevice, st), "H2D");
+    ck(tb_launch_marker_stats(c->geno(), c->m, d_pos, d_w, n_animals, d_out, d_out + c->m, d_out + 2 * (size_t)c->m, st), "launch");
+    c->launches += 1;
+    ck(cudaMemcpyAsync(sum_x, d_out, (size_t)c->m * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H");
+    ck(cudaMemcpyAsync(sum_xx, d_out + c->m, (size_t)c->m * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H");
+    ck(cudaMemcpyAsync(sum_xw, d_out + 2 * (size_t)c->m, (size_t)c->m * sizeof(double), cudaMemcpyDeviceToHost, st), "D2H");
+    ck(cudaStreamSynchronize(st), "execution");
+  }
+  cudaFree(d_pos);
+  cudaFree(d_w);
+  cudaFree(d_out);
+  return rc;
+}
+
 int tb_set_stream(tb_ctx* c, void* cuda_stream) {
   if (!c) return -1;
   TB_CUDA(c, cudaSetDevice(c->device));

@@ -79,6 +79,46 @@ __global__ void colsum2_kernel(const uint8_t* __restrict__ x2, int ld4, int m, c
   if (lane == 0) colsum[warp] = acc;
 }
 
+// Per-marker statistics over a list of animals with one weight each (the GWAS-style scan of the top-SNPs seeder,
+// tblup/seeder.py:144-160,202-210 -> sklearn f_regression): one warp per marker,
+//   sx[j] = sum_i x_ij,   sxx[j] = sum_i x_ij^2   (exact integers),   sxw[j] = sum_i x_ij w_i   (fp64, fixed order).
+// HBM-bound: every marker row of the resident matrix is read once.
+__global__ void marker_stats_kernel(TbGeno g, int m, const int* __restrict__ pos, const double* __restrict__ w, int n_pos,
+                                    double* __restrict__ sx, double* __restrict__ sxx, double* __restrict__ sxw) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= m) return;
+  int a1 = 0, a2 = 0;
+  double aw = 0.0;
+  if (g.x2) {
+    const uint8_t* row = g.x2 + (size_t)warp * g.ld4;
+    for (int i = lane; i < n_pos; i += 32) {
+      const int p = pos[i];
+      const int v = (row[p >> 2] >> (2 * (p & 3))) & 3;
+      a1 += v;
+      a2 += v * v;
+      aw += (double)v * w[i];
+    }
+  } else {
+    const int8_t* row = g.x + (size_t)warp * g.ldn;
+    for (int i = lane; i < n_pos; i += 32) {
+      const int v = row[pos[i]];
+      a1 += v;
+      a2 += v * v;
+      aw += (double)v * w[i];
+    }
+  }
+  for (int o = 16; o; o >>= 1) {
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    aw += __shfl_xor_sync(0xffffffffu, aw, o);
+  }
+  if (lane == 0) {
+    sx[warp] = (double)a1;
+    sxx[warp] = (double)a2;
+    sxw[warp] = aw;
+  }
+}
+
 }  // namespace
 
 cudaError_t tb_launch_pack2(const int8_t* d_x, int ldn, int m, uint8_t* d_x2, cudaStream_t st) {
@@ -113,5 +153,13 @@ cudaError_t tb_launch_colsum(const TbGeno& g, int m, const int* d_pos, int n_pos
   const int ldn = g.ldn;
   colsum_kernel<<<(m + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(d_x, ldn, m, d_pos,
                                                                                              n_pos, d_colsum);
+  return cudaGetLastError();
+}
+
+cudaError_t tb_launch_marker_stats(const TbGeno& g, int m, const int* d_pos, const double* d_w, int n_pos, double* d_sx,
+                                   double* d_sxx, double* d_sxw, cudaStream_t st) {
+  const int warps_per_block = 8;
+  marker_stats_kernel<<<(m + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(g, m, d_pos, d_w, n_pos,
+                                                                                                   d_sx, d_sxx, d_sxw);
   return cudaGetLastError();
 }

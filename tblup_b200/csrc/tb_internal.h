@@ -179,6 +179,8 @@ __host__ __device__ static inline int tb_round_up(int x, int q) { return (x + q 
 cudaError_t tb_launch_transpose_rows(const int8_t* d_rows, int n_rows, int m, int8_t* d_x, int ldn, int pos0,
                                      cudaStream_t st);
 cudaError_t tb_launch_colsum(const TbGeno& g, int m, const int* d_pos, int n_pos, int* d_colsum, cudaStream_t st);
+cudaError_t tb_launch_marker_stats(const TbGeno& g, int m, const int* d_pos, const double* d_w, int n_pos, double* d_sx,
+                                   double* d_sxx, double* d_sxw, cudaStream_t st);
 cudaError_t tb_launch_pack2(const int8_t* d_x, int ldn, int m, uint8_t* d_x2, cudaStream_t st);
 cudaError_t tb_launch_unpack2_perm(const uint8_t* d_rows2, int n_rows, int stride, const int* d_perm, int n,
                                    int8_t* d_x, int ldn, int j0, int* d_bad, cudaStream_t st);

@@ -183,6 +183,18 @@ class GblupEngine:
         self._n_staged = P
         return out
 
+    # -- per-marker statistics (top-SNPs seeder, tblup/seeder.py:144-160) ------------------------
+    def marker_stats(self, animals, weights):
+        """(sum_x, sum_xx, sum_xw) per marker over the listed animals (original indices), weights one per animal."""
+        a = np.ascontiguousarray(np.asarray(animals, dtype=np.int32))
+        w = np.ascontiguousarray(np.asarray(weights, dtype=np.float64))
+        if a.shape != w.shape:
+            raise ValueError("one weight per listed animal")
+        out = np.empty((3, self.m), dtype=np.float64)
+        self._check(self._lib.tb_marker_stats(self._ctx, a.ctypes.data, a.size, w.ctypes.data, out[0].ctypes.data,
+                                              out[1].ctypes.data, out[2].ctypes.data), "tb_marker_stats")
+        return out[0], out[1], out[2]
+
     # -- knockout local search (tblup/local.py:50-76) -------------------------------------------
     def knockout(self, genome, start_fitness, slot=0, h2=0.4, mode=MODE_AUTO):
         """Greedy knockout of the reference's ``KnockoutLocalSearch.search``: returns (keep mask, best fitness,

@@ -40,11 +40,10 @@ def get_evaluator(args):
     """Evaluator for ``args.regressor`` (argparse namespace of tblup/config.py); mirrors evaluator.py:14-55."""
     splitter = None
     if args.splitter == "pca":
-        try:
-            from tblup import pca_splitter      # start-up-only helper, out of the hot path (SURVEY.md §2 #6)
-        except ImportError as e:
-            raise NotImplementedError("--splitter pca needs the reference package's pca_splitter") from e
-        splitter = lambda data: pca_splitter(data, outliers=args.pca_outliers)  # noqa: E731
+        # start-up helper (SURVEY.md 8f row F4): the full-marker GRM behind the split comes from the GPU kernels
+        from .splitter import pca_splitter
+        device = _devices_from_env()[0]
+        splitter = lambda data: pca_splitter(data, outliers=args.pca_outliers, device=device)  # noqa: E731
     r = args.features if args.removal_r is None else args.removal_r
     positional = [args.geno, args.pheno, args.heritability]
     keyword = {"n_procs": args.processes, "splitter": splitter,

@@ -53,4 +53,13 @@ def install(tblup_module=None):
 
         ref_local.get_local_search = get_local_search
         tblup_module.get_local_search = get_local_search
+    # top-SNPs seeder (tblup/seeder.py:7-45 get_seeder builds TopSNPsSeedStrategy by its module-level name): the marker
+    # scan runs on the GPU; the class keeps the reference class as a base
+    from . import seeder as ours_seeder
+    ref_seeder = getattr(tblup_module, "seeder", None)
+    if (ref_seeder is not None and hasattr(ref_seeder, "TopSNPsSeedStrategy")
+            and ref_seeder.TopSNPsSeedStrategy.__module__ != __name__):        # (install() may run more than once)
+        ref_seeder.TopSNPsSeedStrategy = type("TopSNPsSeedStrategy",
+                                              (ours_seeder.TopSNPsSeedStrategy, ref_seeder.TopSNPsSeedStrategy),
+                                              {"__module__": __name__})
     return get_evaluator
