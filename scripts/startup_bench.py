@@ -30,6 +30,9 @@ def main():
     t0 = time.perf_counter()
     g_gpu = splitter.full_grm(x)
     out["full_grm_gpu_s"] = time.perf_counter() - t0          # includes the ingest of the matrix
+    # sklearn's PCA picks its randomized solver at this size and draws from the GLOBAL numpy RNG (random_state=None): the
+    # reference's split is reproducible only through main.py's numpy.random.seed(args.seed); same state for both calls
+    np.random.seed(0)
     t0 = time.perf_counter()
     split_gpu = splitter.pca_splitter(x)
     out["pca_splitter_gpu_s"] = time.perf_counter() - t0
@@ -38,6 +41,7 @@ def main():
     g_ref = O.ref_make_grm(xf)                               # tblup/utils.py:7-18, all BLAS threads
     out["make_grm_host_s"] = time.perf_counter() - t0
     out["grm_max_abs_diff"] = float(np.abs(g_gpu - g_ref).max())
+    np.random.seed(0)
     split_ref = O.ref_pca_split(g_ref)
     out["pca_split_identical"] = bool(split_gpu[0] == split_ref[0] and split_gpu[1] == split_ref[1])
     n_tr = int(0.64 * args.n)
