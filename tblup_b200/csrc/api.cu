@@ -510,10 +510,11 @@ int eval_core(TbCtx* c, const int32_t* slots, int n_slots, double h2, int mode_r
       if (!(fuse_scale && c->fuse_in_gram)) {
         sp = span_begin(c, TB_ST_SCALE);
         if (from_c) {
-          // only the first outer block column is written here; every later one is formed inside its own update
+          // every block column (the first one included: a launch with K = 0) is formed inside the update kernel's epilogue
           TB_CUDA(c, tb_launch_fuse_terms(d_scale, n_jobs, max_ntp, d_terms, d_coef, st));
-          TB_CUDA(c, tb_launch_scale32(d_scale, n_jobs, max_ntp, d_L32, c16 ? 1 : 0, st, 256));
-          count(c, TB_ST_SCALE, 2);
+          if (c->blk0_scale32) TB_CUDA(c, tb_launch_scale32(d_scale, n_jobs, max_ntp, d_L32, c16 ? 1 : 0, st, 256));
+          count(c, TB_ST_SCALE, c->blk0_scale32 ? 2 : 1);
+          fc.skip_blk0 = c->blk0_scale32;
           fc.C = d_C;
           fc.terms = d_terms;
           fc.coef = d_coef;
@@ -1285,6 +1286,7 @@ int tb_set_option(tb_ctx* c, const char* name, long long value) {
   else if (s == "fuse_in_gram") c->fuse_in_gram = value != 0;
   else if (s == "solve_debug") tb_solve_mixed_set_debug((int)value);
   else if (s == "no_fallback") c->no_fallback = value != 0;     // diagnostics: keep the mixed-precision result of failed jobs
+  else if (s == "blk0_scale32") c->blk0_scale32 = value != 0;   // A/B: block column 0 of the scaled matrix by its own scaling pass
   else if (s == "solve_pair") c->solve_pair = value < 0 ? 0 : value > 2 ? 2 : (int)value;
   else if (s == "gram_experiment") c->gram_experiment = (int)value;   // timing experiments only (results are wrong): 1 = no stores, 2 = no epilogue
   else if (s == "gram_pair") c->gram_pair = value < 0 ? 0 : value > 2 ? 2 : (int)value;

@@ -170,7 +170,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (lane == 0 && nkb > 0) {       // (K = 0: block column 0 formed from the cross-products alone, no product to subtract)
       const uint32_t idesc = F16 ? umma_idesc_f16(TBM, p.N) : umma_idesc_tf32(TBM, p.N);
       int stage = 0;
       uint32_t phase = 0;
@@ -270,8 +270,11 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           }
         }
       }
-      mbar_wait(&bars->acc_full[acc], acc_phase);
-      tc_fence_after();
+      const bool has_acc = nkb > 0;
+      if (has_acc) {
+        mbar_wait(&bars->acc_full[acc], acc_phase);
+        tc_fence_after();
+      }
       // stores go through the per-warp staging buffer (tb_ptx.cuh): 8 rows x 64 contiguous bytes per instruction
       const int rw0 = p.row0 + mt * TBM + q * 32;               // first row of this warp
       float* wbase = p.L32 + ((size_t)job * p.ntp + rw0) * p.ntp + col_base;
@@ -280,8 +283,13 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       for (int i = 0; i < 4; ++i) {
         if (i >= nch || col_base + i * 32 > r_hi) continue;      // beyond N, or strictly above the diagonal
         uint32_t v[32];
-        tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * MAX_N + (half * nch + i) * 32, v);
-        tmem_ld_wait();
+        if (has_acc) {
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * MAX_N + (half * nch + i) * 32, v);
+          tmem_ld_wait();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0u;
+        }
         uint32_t o[32];
         if (SRC != 0) {
           // A_rb = scale C_rb + rowterm_r + colterm_b (+ lambda on the diagonal; identity on the padding rows), T = A - acc
@@ -363,7 +371,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&bars->acc_empty[acc]);
+      if (lane == 0 && has_acc) mbar_arrive(&bars->acc_empty[acc]);
       if (++acc == TACC) {
         acc = 0;
         acc_phase ^= 1;
@@ -882,7 +890,7 @@ cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, float* Linv2
     p.L16 = static_cast<__half*>(L16);
     if (p.row_end <= 0 || p.row_end > ntp) p.row_end = ntp;
     p.n_mtiles = (p.row_end - p.row0 + TBM - 1) / TBM;
-    if (p.n_mtiles <= 0 || p.K <= 0) return cudaSuccess;
+    if (p.n_mtiles <= 0 || (p.K <= 0 && !p.from_c)) return cudaSuccess;
     const int items = n_jobs * p.n_mtiles;
     const int grid = items < n_sm ? items : n_sm;
     if (p.mode == 0 && upd16 && p.from_c && p.fc.c16)
@@ -899,7 +907,8 @@ cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, float* Linv2
   const int OB = 256;
   for (int c0 = 0; c0 < ntp; c0 += OB) {
     const int w = (ntp - c0) < OB ? (ntp - c0) : OB;
-    if (c0 > 0) {
+    if (c0 > 0 || (from_c && upd16 && !from_c->skip_blk0)) {
+      // (block column 0 with from_c: K = 0, the launch only forms the block column from the cross-products)
       if (mark) mark(mark_ctx, 0, 0);
       GemmParams p{};
       p.row0 = c0; p.a_col0 = 0; p.K = c0; p.b_row0 = c0; p.b_col0 = 0; p.b_rows_per_job = ntp; p.c_col0 = c0;

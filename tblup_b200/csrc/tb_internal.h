@@ -126,6 +126,7 @@ struct TbCtx {
                                   //    its own (formed inside the Cholesky updates, or -- fuse_in_gram -- by the Gram epilogue)
   int fuse_in_gram = 0;           // 1: round-1 behaviour, the Gram epilogue writes the whole fp32 matrix
   int no_fallback = 0;
+  int blk0_scale32 = 0;           // 1: block column 0 of the scaled matrix by scale32_kernel (round-2 first version)
   int gram_experiment = 0;
   int solve_pair = 1;             // solve with two CTAs per matrix: 0 never, 1 when the batch leaves half the CTA slots empty, 2 always
   int gram_pair = 2;              // Gram schedule: 0 one CTA per tile, 1 clusters of two CTAs sharing the B tile by TMA multicast,
@@ -303,6 +304,7 @@ struct TbFromC {
   const float* terms;   // [n_jobs][2][ntp]
   const TbFuseCoef* coef;   // [n_jobs]
   int rpad, c16;
+  int skip_blk0;        // block column 0 was already written by a scaling pass (A/B option)
 };
 cudaError_t tb_launch_fuse_terms(const TbScaleJob* d_jobs, int n_jobs, int ntp, float* terms, TbFuseCoef* coef,
                                  cudaStream_t st);
