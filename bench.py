@@ -563,6 +563,26 @@ def main():
         p_other = P if args.scaling == "weak" else P * world
         other = measure(p_other, 2000, profile=True)
 
+    # a device-driven DE generation (north_star (e): evolve -> radix-select decode -> evaluate -> select, keys never leave
+    # the GPU) on the same population size: the number a user of the device DE sees, next to the bare evaluation
+    device_de = None
+    if rank == 0 and world == 1 and folds == 1 and m <= 100000:
+        from tblup_b200.de import DeviceDE, mutation_intensity
+        de = DeviceDE(eng, P, k, seed=1)
+        de.evaluate(slots, h2=H2, mode=MODE_AUTO)
+        ts = []
+        for gen in range(1, 5):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            de.step(mutation_intensity(gen, 0.5), 0.8, slots, h2=H2, mode=MODE_AUTO, seed=gen)
+            torch.cuda.synchronize()
+            ts.append(time.perf_counter() - t0)
+        device_de = {"ms_per_generation": 1e3 * float(np.median(ts)), "individuals_per_s": P / float(np.median(ts)),
+                     "generations_timed": len(ts),
+                     "what": "DeviceDE.step: DE/rand/1 + binary crossover on the P x m key matrix, random-key decode by radix "
+                             "select, evaluation of the offspring, greedy selection -- wall time per generation incl. the "
+                             "host call"}
+
     # ------------------------------------------------------------------------------------------------------------
     # parity gate (rank 0; the other ranks wait at the barrier below)
     # ------------------------------------------------------------------------------------------------------------
@@ -763,6 +783,7 @@ def main():
                         "l2": "inputs larger than L2 (each step streams >20 GB of per-genome panels and matrices)",
                         "parallelism": "replicated genotypes; generation sharded by tblup_b200.dist (contiguous slices "
                                        "balanced by genome length); NCCL all-gather of the fitness vector",
+                        "device_de": device_de,
                         "other_scaling": summary(other, "strong" if args.scaling == "weak" else "weak") if other else None,
                         "measured_peaks": {"tcgen05_i8_tops": peak_i8, "tcgen05_mxf4_tops": peak_mxf4,
                                            "tcgen05_sustained_tops": sus, "fp64_dmma_tflops": peak_dmma,
