@@ -336,17 +336,19 @@ def chol_update_flops(ntp, nb=64):
     return tot
 
 
-def chol_update_bytes(ntp, ob=256, entry_read_bytes=4):
+def chol_update_bytes(ntp, ob=256, entry_read_bytes=4, t16=False):
     """Algorithmic DRAM bytes of the outer Cholesky updates of one matrix in mixed precision: the fp32 block column
     is read and written once (8 B per entry of the rows at and below the diagonal block) and the fp16 row operand
     L[rows, 0:c0] is streamed once per block column (2 B per entry); the 256-row column operand stays in L2.
     entry_read_bytes: 4 when the update reads the fp32 matrix, 2 / 4 when it forms the entries from int16 / int32
-    cross-products (round 2: nothing is read-modify-written, the block column is written once as fp32)."""
+    cross-products (round 2: nothing is read-modify-written, the block column is written once as fp32).
+    t16: the rows below the diagonal block of a full-width block column are written as halves (option t16)."""
     tot = 0
     for c0 in range(ob, ntp, ob):
         w = min(ob, ntp - c0)
         rows = ntp - c0
-        tot += rows * w * (4 + entry_read_bytes) + rows * c0 * 2
+        below = rows - w if (t16 and w == ob and c0 + w < ntp) else 0
+        tot += (rows - below) * w * (4 + entry_read_bytes) + below * w * (2 + entry_read_bytes) + rows * c0 * 2
     return tot
 
 
@@ -686,7 +688,8 @@ def main():
                          "peak_source": upd_peak_src, "launches": int(upd_launches),
                          "avg_launch_ms": upd_ms / max(1, upd_launches), "share_of_step": upd_ms / ms_i}
             if precision == "mixed" and upd_ms > 0:
-                upd_bytes = chol_update_bytes(ntp, 256, (2 if c16 else 4) if fused else 4)
+                t16 = bool(fused and eng.info("t16"))
+                upd_bytes = chol_update_bytes(ntp, 256, (2 if c16 else 4) if fused else 4, t16)
                 upd_gbs = upd_bytes * n_mats / (upd_ms * 1e-3) / 1e9
                 rl_update = {"bound": "hbm", "kernel": upd_kernel, "achieved": upd_gbs, "peak": hbm, "unit": "GB/s",
                              "frac": upd_gbs / hbm, "traffic": None, "algorithmic_bytes_per_matrix": upd_bytes,

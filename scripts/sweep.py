@@ -27,6 +27,7 @@ def main():
     ap.add_argument("--pops", default="100,1000,4000")
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--budget_s", type=float, default=12.0, help="skip repeating a point whose one step takes longer")
+    ap.add_argument("--opt", action="append", default=[], help="engine option name=value (A/B runs)")
     args = ap.parse_args()
     import torch
     from oracle import gblup_oracle as O
@@ -36,6 +37,9 @@ def main():
     tr, va, te = synth.split_indices(n, seed=0)
     eng = GblupEngine(x, y, perm=np.concatenate([tr, va, te]))
     eng.set_rowset(0, tr, va)
+    for kv in args.opt:
+        name, val = kv.split("=")
+        eng.set_option(name, int(val))
     stream = torch.cuda.current_stream()
     eng.set_stream(stream.cuda_stream)
     points = []
@@ -76,7 +80,8 @@ def main():
             pt = {"k": k, "pop": P, "evals_per_s": P / (ms * 1e-3), "ms_per_step": ms, "wave": eng.last_wave(),
                   "stage_ms": {s: round(v, 3) for s, v in st.items()}, "gram_over_cholesky": st["gram"] / chol if chol else None,
                   "gram_tops": 2.0 * k * (3200 * 3201 / 2 + 800 * 3200) * P / (st["gram"] * 1e-3) / 1e12 if st["gram"] else None,
-                  "cross_products": "int16" if facts["last_c16"] else "int32", "parity_at_this_k": parity}
+                  "cross_products": "int16" if facts["last_c16"] else "int32", "parity_at_this_k": parity,
+                  "fp64_fallbacks": eng.info("last_fallbacks")}
             points.append(pt)
             print(json.dumps(pt), flush=True)
     # crossover: interpolate gram/cholesky = 1 over k at the largest population

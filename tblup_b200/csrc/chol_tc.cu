@@ -38,11 +38,11 @@ constexpr int TA_BYTES = TBM * TBK * 4;          // 16 KiB
 constexpr int TB_BYTES_MAX = MAX_N * TBK * 4;    // 32 KiB
 constexpr int TSTAGE_BYTES = TA_BYTES + TB_BYTES_MAX;
 constexpr int TACC = 2;
-constexpr int EPI_WARPS = 8;                    // two warps per TMEM lane quarter, each owning half of the columns
-constexpr int T_THREADS = 64 + 32 * EPI_WARPS;
+// epilogue warps (template parameter EW): 8 or 16 -- EW / 4 warps per TMEM lane quarter share the columns of a tile
+constexpr int t_threads(int ew) { return 64 + 32 * ew; }
 constexpr int HBK = 64;              // halves per k-block when the operands are fp16 (same 128-byte span)
-constexpr int T_STAGING = EPI_WARPS * 2048;       // per-warp transposition buffers (coalescing epilogue stores)
-constexpr int T_SMEM = TSTAGES * TSTAGE_BYTES + 1024 + 256 + T_STAGING;
+// ring + alignment slack + barriers + per-warp transposition buffers (coalescing epilogue stores)
+constexpr int t_smem(int ew) { return TSTAGES * TSTAGE_BYTES + 1024 + 256 + ew * 2048; }
 
 struct GemmParams {
   int n_jobs;
@@ -62,6 +62,9 @@ struct GemmParams {
   float* L32;
   __half* L16;       // optional half-precision copy of the final factor entries (read by the solve)
   int from_c;        // mode 0 only: the matrix entries come from the integer cross-products (TbFromC), not from L32
+  int t16;           // mode 0 only: tiles BELOW the 256-row diagonal block (m-tile >= 2) are written as halves into L16 (where
+                     // the wide panel GEMM reads them and writes the final factor entries in place), not as fp32 into L32
+  int f16ops;        // mode 1 only: both operands are fp16 (A from L16 in place, B the fp16 inverse of the diagonal block)
   TbFromC fc;
 };
 
@@ -112,8 +115,8 @@ __device__ __forceinline__ float round_tf32(float x) {
 
 // SRC: where update mode reads the entries it modifies -- 0: the fp32 matrix L32, 1: int16 cross-products, 2: int32
 // cross-products (TbFromC: the scaled matrix is formed on the fly)
-template <bool F16, int SRC>
-__global__ void __launch_bounds__(T_THREADS, 1)
+template <bool F16, int SRC, int EW>
+__global__ void __launch_bounds__(t_threads(EW), 1)
 tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -135,7 +138,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     }
     for (int s = 0; s < TACC; ++s) {
       mbar_init(&bars->acc_full[s], 1);
-      mbar_init(&bars->acc_empty[s], EPI_WARPS);
+      mbar_init(&bars->acc_empty[s], EW);
     }
     fence_barrier_init();
   }
@@ -205,22 +208,28 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
     }
   } else {
-    // Epilogue: warp w reads TMEM lanes 32 (w & 3) .. +31 (one accumulator row per thread); the two warps of a lane
-    // quarter split the N columns.  In update mode the C values a thread will modify do not depend on the MMA, so
-    // all of its loads (up to 4 x 128 B) are issued BEFORE it waits for the accumulator: the read latency of the
-    // read-modify-write hides behind the tile's own MMA instead of serialising chunk by chunk.
-    const int q = warp & 3, half = (warp - 2) >> 2;
+    // Epilogue: warp w reads TMEM lanes 32 (w & 3) .. +31 (one accumulator row per thread); the EW / 4 warps of a lane
+    // quarter take the 32-column chunks of the tile round-robin (chunk g, g + CG, ...).  In update mode the C values a
+    // thread will modify do not depend on the MMA, so all of its loads are issued BEFORE it waits for the accumulator:
+    // the read latency hides behind the tile's own MMA instead of serialising chunk by chunk.
+    // The first block columns of a factorisation are bound by THIS code, not by the operand stream (the K = 0 launch
+    // runs at what the epilogue alone sustains); sixteen warps instead of eight double the latency cover, and the
+    // per-entry work is what the common case needs: the diagonal (+ lambda) and the padding rows are patched in
+    // warp-uniform side branches instead of being tested per entry.
+    constexpr int CG = EW / 4;                                  // column groups
+    constexpr int MAXI = 8 / CG;                                // chunks per warp at N = 256
+    constexpr int CVN = SRC == 1 ? 4 : 8;                       // 16-byte loads per chunk and thread
+    const int q = warp & 3, g = (warp - 2) >> 2;
     const uint32_t stg = smem_u32(smem + TSTAGES * TSTAGE_BYTES + 256) + (warp - 2) * 2048;
-    const int nch = p.N / 64;                                   // 32-column chunks per warp (1 .. 4)
+    const int nchunks = p.N / 32;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int job = item / p.n_mtiles, mt = item - job * p.n_mtiles;
       const int r = p.row0 + mt * TBM + q * 32 + lane;          // row inside the job's matrix
       const int r_hi = p.row0 + mt * TBM + TBM - 1;
-      float* crow = p.L32 + ((size_t)job * p.ntp + (r < p.row_end ? r : 0)) * p.ntp + p.c_col0 + half * nch * 32;
-      const int col_base = p.c_col0 + half * nch * 32;
-      float4 cv[4][SRC == 1 ? 4 : 8];
+      const float* crow = p.L32 + ((size_t)job * p.ntp + (r < p.row_end ? r : 0)) * p.ntp + p.c_col0;
+      float4 cv[MAXI][CVN];
       float f_scale = 0.f, f_lam = 0.f, f_rt = 0.f;
       int f_nt = 0, f_h0 = 0, f_gap = 0;
       const float* f_ct = nullptr;
@@ -232,7 +241,7 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         f_lam = cf.lam;
         f_nt = cf.n_t;
         f_rt = p.fc.terms[(size_t)job * 2 * p.ntp + (r < p.row_end ? r : 0)];
-        f_ct = p.fc.terms + (size_t)job * 2 * p.ntp + p.ntp + col_base;
+        f_ct = p.fc.terms + (size_t)job * 2 * p.ntp + p.ntp + p.c_col0;
         // compact index -> panel row / column: a + (a >= hole0 ? gap : 0); hole0 and gap are multiples of 8, so an
         // 8-column group never straddles the hole (plain prefix: hole0 = n_t, gap = 0)
         const int rr = r < cf.n_t ? r + (r >= cf.hole0 ? cf.gap : 0) : 0;
@@ -240,20 +249,21 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         f_h0 = cf.hole0;
         f_gap = cf.gap;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (i < nch && col_base + i * 32 <= r_hi && r < p.row_end) {
+        for (int i = 0; i < MAXI; ++i) {
+          const int ch = g + CG * i;
+          if (ch < nchunks && p.c_col0 + ch * 32 <= r_hi && r < p.row_end) {
             if (SRC == 1) {
 #pragma unroll
               for (int j = 0; j < 4; ++j) {                      // 8 columns per 16-byte load
-                const int b = col_base + i * 32 + 8 * j;
+                const int b = p.c_col0 + ch * 32 + 8 * j;
                 const int ub = b + ((b >= f_h0 && b < f_nt) ? f_gap : 0);
                 const uint4 u = *reinterpret_cast<const uint4*>(static_cast<const int16_t*>(p.fc.C) + rowoff + ub);
                 cv[i][j] = make_float4(__uint_as_float(u.x), __uint_as_float(u.y), __uint_as_float(u.z), __uint_as_float(u.w));
               }
             } else {
 #pragma unroll
-              for (int j = 0; j < (SRC == 1 ? 4 : 8); ++j) {     // 4 columns per 16-byte load
-                const int b = col_base + i * 32 + 4 * j;
+              for (int j = 0; j < CVN; ++j) {                    // 4 columns per 16-byte load
+                const int b = p.c_col0 + ch * 32 + 4 * j;
                 const int ub = b + ((b >= f_h0 && b < f_nt) ? f_gap : 0);
                 cv[i][j] = *reinterpret_cast<const float4*>(static_cast<const int32_t*>(p.fc.C) + rowoff + ub);
               }
@@ -262,11 +272,12 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       } else if (p.mode == 0) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          if (i < nch && col_base + i * 32 <= r_hi && r < p.row_end) {
-            const float4* src = reinterpret_cast<const float4*>(crow + i * 32);
+        for (int i = 0; i < MAXI; ++i) {
+          const int ch = g + CG * i;
+          if (ch < nchunks && p.c_col0 + ch * 32 <= r_hi && r < p.row_end) {
+            const float4* src = reinterpret_cast<const float4*>(crow + ch * 32);
 #pragma unroll
-            for (int j = 0; j < (SRC == 1 ? 4 : 8); ++j) cv[i][j] = src[j];
+            for (int j = 0; j < CVN; ++j) cv[i][j] = src[j];
           }
         }
       }
@@ -277,14 +288,16 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       }
       // stores go through the per-warp staging buffer (tb_ptx.cuh): 8 rows x 64 contiguous bytes per instruction
       const int rw0 = p.row0 + mt * TBM + q * 32;               // first row of this warp
-      float* wbase = p.L32 + ((size_t)job * p.ntp + rw0) * p.ntp + col_base;
+      const bool tile16 = p.mode == 0 && p.t16 && mt >= 2;      // (tile-uniform) block-column entries kept as halves
       const int rl = lane >> 2, gl = 4 * (lane & 3);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        if (i >= nch || col_base + i * 32 > r_hi) continue;      // beyond N, or strictly above the diagonal
+      for (int i = 0; i < MAXI; ++i) {
+        const int ch = g + CG * i;
+        const int b0 = p.c_col0 + ch * 32;
+        if (ch >= nchunks || b0 > r_hi) continue;                // beyond N, or strictly above the diagonal
         uint32_t v[32];
         if (has_acc) {
-          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * MAX_N + (half * nch + i) * 32, v);
+          tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * MAX_N + ch * 32, v);
           tmem_ld_wait();
         } else {
 #pragma unroll
@@ -293,21 +306,21 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         uint32_t o[32];
         if (SRC != 0) {
           // A_rb = scale C_rb + rowterm_r + colterm_b (+ lambda on the diagonal; identity on the padding rows), T = A - acc
-          const int b0 = col_base + i * 32;
+          const bool pad_warp = rw0 + 32 > f_nt;                 // (warp-uniform) some rows of this warp are padding
           const bool real_row = r < f_nt;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            const float4 ct = *reinterpret_cast<const float4*>(f_ct + i * 32 + 4 * j);
+            const float4 ct = *reinterpret_cast<const float4*>(f_ct + ch * 32 + 4 * j);
             float cx[4];
             if (SRC == 1) {
               const float4 raw = cv[i][j >> 1];
               const uint32_t w0 = (j & 1) ? __float_as_uint(raw.z) : __float_as_uint(raw.x);
               const uint32_t w1 = (j & 1) ? __float_as_uint(raw.w) : __float_as_uint(raw.y);
-              // integers below 2^23: 0x4b000000 | c is the float 2^23 + c (no converter pipe)
-              cx[0] = __uint_as_float(0x4b000000u | (w0 & 0xffffu)) - 8388608.f;
-              cx[1] = __uint_as_float(0x4b000000u | (w0 >> 16)) - 8388608.f;
-              cx[2] = __uint_as_float(0x4b000000u | (w1 & 0xffffu)) - 8388608.f;
-              cx[3] = __uint_as_float(0x4b000000u | (w1 >> 16)) - 8388608.f;
+              // integers below 2^23: 0x4b000000 | c is the float 2^23 + c (no converter pipe); one byte permute each
+              cx[0] = __uint_as_float(__byte_perm(w0, 0x4b000000u, 0x7410)) - 8388608.f;
+              cx[1] = __uint_as_float(__byte_perm(w0, 0x4b000000u, 0x7432)) - 8388608.f;
+              cx[2] = __uint_as_float(__byte_perm(w1, 0x4b000000u, 0x7410)) - 8388608.f;
+              cx[3] = __uint_as_float(__byte_perm(w1, 0x4b000000u, 0x7432)) - 8388608.f;
             } else {
               const float4 raw = cv[i][SRC == 1 ? 0 : j];
               cx[0] = __uint_as_float(0x4b000000u | __float_as_uint(raw.x)) - 8388608.f;
@@ -316,17 +329,28 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
               cx[3] = __uint_as_float(0x4b000000u | __float_as_uint(raw.w)) - 8388608.f;
             }
             const float ctv[4] = {ct.x, ct.y, ct.z, ct.w};
+            if (pad_warp) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int b = b0 + 4 * j + e;
-              float a = real_row ? fmaf(cx[e], f_scale, f_rt + ctv[e]) : 0.f;
-              if (b == r) a = real_row ? a + f_lam : 1.f;
-              o[4 * j + e] = __float_as_uint(a - __uint_as_float(v[4 * j + e]));
+              for (int e = 0; e < 4; ++e) {
+                const float a = real_row ? fmaf(cx[e], f_scale, f_rt + ctv[e]) : (b0 + 4 * j + e == r ? 1.f : 0.f);
+                o[4 * j + e] = __float_as_uint(a - __uint_as_float(v[4 * j + e]));
+              }
+            } else {
+#pragma unroll
+              for (int e = 0; e < 4; ++e)
+                o[4 * j + e] = __float_as_uint(fmaf(cx[e], f_scale, f_rt + ctv[e]) - __uint_as_float(v[4 * j + e]));
+            }
+          }
+          if (b0 < rw0 + 32 && b0 + 32 > rw0) {                  // (warp-uniform) the chunk holds diagonal entries
+            if (real_row) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (b0 + j == r) o[j] = __float_as_uint(__uint_as_float(o[j]) + f_lam);
             }
           }
         } else if (p.mode == 0) {
 #pragma unroll
-          for (int j = 0; j < (SRC == 1 ? 4 : 8); ++j) {
+          for (int j = 0; j < CVN; ++j) {
             o[4 * j] = __float_as_uint(cv[i][j].x - __uint_as_float(v[4 * j]));
             o[4 * j + 1] = __float_as_uint(cv[i][j].y - __uint_as_float(v[4 * j + 1]));
             o[4 * j + 2] = __float_as_uint(cv[i][j].z - __uint_as_float(v[4 * j + 2]));
@@ -336,7 +360,8 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(round_tf32(__uint_as_float(v[j])));
         }
-        if (!(p.mode != 0 && p.skip32)) {
+        if (!(p.mode != 0 && p.skip32) && !tile16) {
+          float* wbase = p.L32 + ((size_t)job * p.ntp + rw0) * p.ntp + b0;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             stage_write16(stg, lane, o + 16 * h);
@@ -345,19 +370,19 @@ tf32_gemm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             for (int it = 0; it < 4; ++it) {
               const uint4 u = stage_read16(stg, lane, it);
               if (rw0 + 8 * it + rl < p.row_end)
-                *reinterpret_cast<uint4*>(wbase + (size_t)(8 * it + rl) * p.ntp + i * 32 + 16 * h + gl) = u;
+                *reinterpret_cast<uint4*>(wbase + (size_t)(8 * it + rl) * p.ntp + 16 * h + gl) = u;
             }
             __syncwarp();
           }
         }
-        if (p.mode != 0 && p.L16) {
+        if ((p.mode != 0 && p.L16) || tile16) {
           uint32_t hv[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const __half2 hh = __floats2half2_rn(__uint_as_float(o[2 * j]), __uint_as_float(o[2 * j + 1]));
             hv[j] = *reinterpret_cast<const uint32_t*>(&hh);
           }
-          __half* hbase = p.L16 + ((size_t)job * p.ntp + rw0) * p.ntp + col_base + i * 32;
+          __half* hbase = p.L16 + ((size_t)job * p.ntp + rw0) * p.ntp + b0;
           stage_write16(stg, lane, hv);
           __syncwarp();
 #pragma unroll
@@ -438,18 +463,24 @@ __device__ __forceinline__ void warp_trinv32(float (&x)[32], const float* L, int
   }
 }
 
-__global__ void __launch_bounds__(256) chol_diag32_kernel(float* __restrict__ L32, float* __restrict__ Linv32,
-                                                          __half* __restrict__ L16, int* __restrict__ status, int ntp,
-                                                          int jb) {
+// 128 threads and 29 KiB of shared memory per block: SEVEN blocks per SM, so 1 000 matrices are one wave (the version
+// with 256 threads / 37 KiB ran four per SM = two waves, with one warp of eight busy in the serial phases).
+constexpr int DT = 128;                                   // threads per block
+constexpr int XLD = 33;
+__global__ void __launch_bounds__(DT) chol_diag32_kernel(float* __restrict__ L32, float* __restrict__ Linv32,
+                                                         __half* __restrict__ L16, int* __restrict__ status, int ntp,
+                                                         int jb) {
   __shared__ float Ls[NB * DLD];
-  __shared__ float Xs[NB * DLD];
-  __shared__ float Ps[32 * 33];
+  __shared__ float X11[32 * XLD];
+  __shared__ float X22[32 * XLD];
+  __shared__ float X21[32 * XLD];
   __shared__ int bad;
+  float* Ps = Ls + 32;                                    // P = L21 X11 lives in the (unused) upper-right quadrant, stride DLD
   const int job = blockIdx.x;
   float* D = L32 + ((size_t)job * ntp + (size_t)jb * NB) * ntp + jb * NB;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (tid == 0) bad = 0;
-  for (int e = tid; e < NB * 16; e += 256) {              // coalesced rows, 16 bytes per thread
+  for (int e = tid; e < NB * 16; e += DT) {               // coalesced rows, 16 bytes per thread
     const int r = e >> 4, c4 = (e & 15) * 4;
     const float4 v = *reinterpret_cast<const float4*>(D + (size_t)r * ntp + c4);
     Ls[r * DLD + c4] = v.x;
@@ -457,7 +488,6 @@ __global__ void __launch_bounds__(256) chol_diag32_kernel(float* __restrict__ L3
     Ls[r * DLD + c4 + 2] = v.z;
     Ls[r * DLD + c4 + 3] = v.w;
   }
-  for (int e = tid; e < NB * NB; e += 256) Xs[(e >> 6) * DLD + (e & 63)] = 0.f;
   __syncthreads();
   float a[32];
   if (warp == 0) {                                        // L11
@@ -477,20 +507,22 @@ __global__ void __launch_bounds__(256) chol_diag32_kernel(float* __restrict__ L3
   } else if (warp == 2) {                                 // X11 = L11^-1
     warp_trinv32(a, Ls, lane);
 #pragma unroll
-    for (int r = 0; r < 32; ++r) Xs[r * DLD + lane] = a[r];
+    for (int r = 0; r < 32; ++r) X11[r * XLD + lane] = a[r];
   }
   __syncthreads();
-  {                                                       // A22 -= L21 L21^T (lower part), 4 entries per thread
-    const int r = tid >> 3, c0 = (tid & 7) * 4;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int p = 0; p < 32; ++p) {
-      const float lr = Ls[(32 + r) * DLD + p];
+  {                                                       // A22 -= L21 L21^T (lower part), 8 entries per thread
+    const int r = tid >> 2, c0 = (tid & 3) * 8;
+    if (c0 <= r) {
+      float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int p = 0; p < 32; ++p) {
+        const float lr = Ls[(32 + r) * DLD + p];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = fmaf(lr, Ls[(32 + c0 + j) * DLD + p], acc[j]);
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(lr, Ls[(32 + c0 + j) * DLD + p], acc[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (c0 + j <= r) Ls[(32 + r) * DLD + 32 + c0 + j] -= acc[j];
     }
-#pragma unroll
-    for (int j = 0; j < 4; ++j)
-      if (c0 + j <= r) Ls[(32 + r) * DLD + 32 + c0 + j] -= acc[j];
   }
   __syncthreads();
   if (warp == 0) {                                        // L22
@@ -499,42 +531,42 @@ __global__ void __launch_bounds__(256) chol_diag32_kernel(float* __restrict__ L3
     if (!warp_potrf32(a)) bad = 1;
 #pragma unroll
     for (int c = 0; c < 32; ++c) Ls[(32 + lane) * DLD + 32 + c] = c <= lane ? round_tf32(a[c]) : 0.f;
-#pragma unroll
-    for (int c = 0; c < 32; ++c) Ls[lane * DLD + 32 + c] = 0.f;           // upper-right block of the factor
-  } else {                                                // P = L21 X11, meanwhile (224 threads, 32 x 32 outputs)
-    for (int e = tid - 32; e < 32 * 32; e += 224) {
+  } else {                                                // P = L21 X11, meanwhile (96 threads, 32 x 32 outputs)
+    for (int e = tid - 32; e < 32 * 32; e += DT - 32) {
       const int r = e >> 5, c = e & 31;
       float s = 0.f;
-      for (int p = c; p < 32; ++p) s = fmaf(Ls[(32 + r) * DLD + p], Xs[p * DLD + c], s);   // X11 is lower triangular
-      Ps[r * 33 + c] = s;
+      for (int p = c; p < 32; ++p) s = fmaf(Ls[(32 + r) * DLD + p], X11[p * XLD + c], s);   // X11 is lower triangular
+      Ps[r * DLD + c] = s;
     }
   }
   __syncthreads();
   if (warp == 3) {                                        // X22 = L22^-1
     warp_trinv32(a, Ls + 32 * DLD + 32, lane);
 #pragma unroll
-    for (int r = 0; r < 32; ++r) Xs[(32 + r) * DLD + 32 + lane] = a[r];
+    for (int r = 0; r < 32; ++r) X22[r * XLD + lane] = a[r];
   }
   __syncthreads();
   {                                                       // X21 = -X22 P
-    const int r = tid >> 3, c0 = (tid & 7) * 4;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    const int r = tid >> 2, c0 = (tid & 3) * 8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     for (int p = 0; p <= r; ++p) {                        // X22 is lower triangular
-      const float xr = Xs[(32 + r) * DLD + 32 + p];
+      const float xr = X22[r * XLD + p];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = fmaf(xr, Ps[p * 33 + c0 + j], acc[j]);
+      for (int j = 0; j < 8; ++j) acc[j] = fmaf(xr, Ps[p * DLD + c0 + j], acc[j]);
     }
-    __syncthreads();
 #pragma unroll
-    for (int j = 0; j < 4; ++j) Xs[(32 + r) * DLD + c0 + j] = -acc[j];
+    for (int j = 0; j < 8; ++j) X21[r * XLD + c0 + j] = -acc[j];
   }
   __syncthreads();
   float* Li = Linv32 + ((size_t)job * ntp + (size_t)jb * NB) * NB;
-  for (int e = tid; e < NB * NB; e += 256) {
+  for (int e = tid; e < NB * NB; e += DT) {
     const int rr = e >> 6, c = e & 63;
-    D[(size_t)rr * ntp + c] = Ls[rr * DLD + c];
-    if (L16) L16[((size_t)job * ntp + (size_t)jb * NB + rr) * ntp + jb * NB + c] = __float2half_rn(Ls[rr * DLD + c]);
-    Li[e] = round_tf32(Xs[rr * DLD + c]);
+    const float l = (rr < 32 && c >= 32) ? 0.f : Ls[rr * DLD + c];      // (the upper-right quadrant held P)
+    D[(size_t)rr * ntp + c] = l;
+    if (L16) L16[((size_t)job * ntp + (size_t)jb * NB + rr) * ntp + jb * NB + c] = __float2half_rn(l);
+    const float x = rr < 32 ? (c < 32 ? X11[rr * XLD + c] : 0.f)
+                            : (c < 32 ? X21[(rr - 32) * XLD + c] : X22[(rr - 32) * XLD + c - 32]);
+    Li[e] = round_tf32(x);
   }
   if (tid == 0 && bad) status[job] = 1;
 }
@@ -577,8 +609,11 @@ __device__ __forceinline__ void block_mma(float (&acc)[4][4], const float* As, c
   }
 }
 
+// X16 (nullable): the inverse goes out as halves [job][256][256] instead of the fp32 Linv256 (its entries are rounded to
+// 10 mantissa bits either way); the wide panel GEMM then runs on fp16 operands.
 __global__ void __launch_bounds__(256) trinv256_kernel(const float* __restrict__ L32, const float* __restrict__ Linv32,
-                                                       float* __restrict__ Linv256, int ntp, int c0) {
+                                                       float* __restrict__ Linv256, __half* __restrict__ X16, int ntp,
+                                                       int c0) {
   extern __shared__ float tsm[];
   float* Xs = tsm;                       // [4][64][XS_LD]  X_kb of the current block column b
   float* As = Xs + 4 * 64 * XS_LD;       // [64][AS_LD]     left operand
@@ -587,8 +622,22 @@ __global__ void __launch_bounds__(256) trinv256_kernel(const float* __restrict__
   const float* Lj = L32 + ((size_t)job * ntp + c0) * ntp + c0;
   const float* Dj = Linv32 + ((size_t)job * ntp + c0) * NB;
   float* Out = Linv256 + (size_t)job * 256 * 256;
+  __half* Out16 = X16 ? X16 + (size_t)job * 256 * 256 : nullptr;
   const int g = lane >> 2, t = lane & 3;
   const int frow = 16 * (warp & 3) + g, fcol = 32 * (warp >> 2) + 2 * t;    // this thread's fragment origin
+  auto put4 = [&](size_t off, const float4 v) {                            // entries off .. off + 3 of this job's inverse
+    if (Out16) {
+      const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+      *reinterpret_cast<uint2*>(Out16 + off) =
+          make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    } else {
+      *reinterpret_cast<float4*>(Out + off) = v;
+    }
+  };
+  auto put2 = [&](size_t off, const float2 v) {
+    if (Out16) *reinterpret_cast<__half2*>(Out16 + off) = __floats2half2_rn(v.x, v.y);
+    else *reinterpret_cast<float2*>(Out + off) = v;
+  };
 
   // 64 x 64 block, row stride ld_src, into smem with row stride ld_dst (16-byte loads, coalesced rows)
   auto load_block = [&](const float* src, size_t ld_src, float* dst, int ld_dst) {
@@ -602,13 +651,12 @@ __global__ void __launch_bounds__(256) trinv256_kernel(const float* __restrict__
   auto column_setup = [&](int b) {
     for (int i = 0; i < b; ++i)
       for (int e = tid; e < 64 * 16; e += 256)
-        *reinterpret_cast<float4*>(Out + (size_t)(64 * i + (e >> 4)) * 256 + 64 * b + (e & 15) * 4) = make_float4(0.f, 0.f, 0.f, 0.f);
+        put4((size_t)(64 * i + (e >> 4)) * 256 + 64 * b + (e & 15) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
     load_block(Dj + (size_t)b * 64 * NB, NB, Xs + b * 64 * XS_LD, XS_LD);
     __syncthreads();
     for (int e = tid; e < 64 * 16; e += 256) {
       const int r = e >> 4, c4 = (e & 15) * 4;
-      *reinterpret_cast<float4*>(Out + (size_t)(64 * b + r) * 256 + 64 * b + c4) =
-          *reinterpret_cast<const float4*>(Xs + b * 64 * XS_LD + r * XS_LD + c4);
+      put4((size_t)(64 * b + r) * 256 + 64 * b + c4, *reinterpret_cast<const float4*>(Xs + b * 64 * XS_LD + r * XS_LD + c4));
     }
   };
   // The left operands form a fixed sequence (b, i, k): L_ik for k = b .. i-1, then Linv_i (written k = i), for
@@ -683,15 +731,15 @@ __global__ void __launch_bounds__(256) trinv256_kernel(const float* __restrict__
         for (int e = 0; e < 4; ++e) acc2[nt][e] = 0.f;
       block_mma(acc2, As, Ss, warp, lane);
       float* Xi = Xs + i * 64 * XS_LD;
-      float* Oi = Out + (size_t)(64 * i) * 256 + 64 * b;
+      const size_t oi = (size_t)(64 * i) * 256 + 64 * b;
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt) {
         const float2 lo = make_float2(round_tf32(-acc2[nt][0]), round_tf32(-acc2[nt][1]));
         const float2 hi = make_float2(round_tf32(-acc2[nt][2]), round_tf32(-acc2[nt][3]));
         *reinterpret_cast<float2*>(Xi + frow * XS_LD + fcol + 8 * nt) = lo;
         *reinterpret_cast<float2*>(Xi + (frow + 8) * XS_LD + fcol + 8 * nt) = hi;
-        *reinterpret_cast<float2*>(Oi + (size_t)frow * 256 + fcol + 8 * nt) = lo;
-        *reinterpret_cast<float2*>(Oi + (size_t)(frow + 8) * 256 + fcol + 8 * nt) = hi;
+        put2(oi + (size_t)frow * 256 + fcol + 8 * nt, lo);
+        put2(oi + (size_t)(frow + 8) * 256 + fcol + 8 * nt, hi);
       }
     }
     __syncthreads();
@@ -850,15 +898,15 @@ cudaError_t tb_chol_tc_init() {
     if (!fn || qres != cudaDriverEntryPointSuccess) return cudaErrorNotSupported;
     g_encode32 = reinterpret_cast<EncodeTiledFn>(fn);
   }
-  cudaError_t e = cudaFuncSetAttribute(tf32_gemm_kernel<false, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
+  cudaError_t e = cudaFuncSetAttribute(trinv256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRINV_SMEM);
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(trinv256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRINV_SMEM);
+#define TB_GEMM_ATTR(F, S, W)                                                                                       \
+  e = cudaFuncSetAttribute(tf32_gemm_kernel<F, S, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem(W)); \
   if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(tf32_gemm_kernel<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(tf32_gemm_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
-  if (e != cudaSuccess) return e;
-  return cudaFuncSetAttribute(tf32_gemm_kernel<true, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, T_SMEM);
+  TB_GEMM_ATTR(false, 0, 8) TB_GEMM_ATTR(true, 0, 8) TB_GEMM_ATTR(true, 1, 8) TB_GEMM_ATTR(true, 2, 8)
+  TB_GEMM_ATTR(false, 0, 16) TB_GEMM_ATTR(true, 0, 16) TB_GEMM_ATTR(true, 1, 16) TB_GEMM_ATTR(true, 2, 16)
+#undef TB_GEMM_ATTR
+  return cudaSuccess;
 }
 
 // Factor every job's fp32 matrix in place.  L32: [n_jobs * ntp + 128 slack rows][ntp]; Linv32: [n_jobs * ntp][64].
@@ -866,14 +914,18 @@ cudaError_t tb_chol_tc_init() {
 // launches[0] / launches[1] receive the number of GEMM / diagonal-block kernel launches.
 cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, float* Linv256, int* status, int n_jobs, int ntp,
                               int n_sm, cudaStream_t st, int* launches, std::string* err,
-                              void (*mark)(void*, int, int), void* mark_ctx, const TbFromC* from_c) {
+                              void (*mark)(void*, int, int), void* mark_ctx, const TbFromC* from_c, int t16, int epi_warps) {
   CUtensorMap tm_l, tm_inv, tm_inv256;
   cudaError_t e = encode_f32(&tm_l, L32, (size_t)ntp, (size_t)n_jobs * ntp + 128, err);
   if (e != cudaSuccess) return e;
   e = encode_f32(&tm_inv, Linv32, (size_t)NB, (size_t)n_jobs * ntp, err);
   if (e != cudaSuccess) return e;
+  CUtensorMap tm_x16;
   if (Linv256) {
     e = encode_f32(&tm_inv256, Linv256, 256, (size_t)n_jobs * 256, err);
+    if (e != cudaSuccess) return e;
+    // the same scratch viewed as halves (first half of the allocation): fp16 inverses of the 256-wide diagonal blocks
+    e = encode_f16(&tm_x16, reinterpret_cast<const __half*>(Linv256), 256, (size_t)n_jobs * 256, err);
     if (e != cudaSuccess) return e;
   }
   // updates (C -= A B^T with both operands finished columns of L) stream the half-precision copy of the factor
@@ -893,20 +945,38 @@ cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, float* Linv2
     if (p.n_mtiles <= 0 || (p.K <= 0 && !p.from_c)) return cudaSuccess;
     const int items = n_jobs * p.n_mtiles;
     const int grid = items < n_sm ? items : n_sm;
-    if (p.mode == 0 && upd16 && p.from_c && p.fc.c16)
-      tf32_gemm_kernel<true, 1><<<grid, T_THREADS, T_SMEM, st>>>(tm_l16, tm_l16, p);
-    else if (p.mode == 0 && upd16 && p.from_c)
-      tf32_gemm_kernel<true, 2><<<grid, T_THREADS, T_SMEM, st>>>(tm_l16, tm_l16, p);
-    else if (p.mode == 0 && upd16)
-      tf32_gemm_kernel<true, 0><<<grid, T_THREADS, T_SMEM, st>>>(tm_l16, tm_l16, p);
-    else
-      tf32_gemm_kernel<false, 0><<<grid, T_THREADS, T_SMEM, st>>>(tm_l, tb, p);
+    // variant: 0 = fp32 operands, 1 = fp16 operands / fp32 entries, 2 = fp16 / int16 cross-products, 3 = fp16 / int32
+    int variant = 0;
+    const CUtensorMap* ta = &tm_l;
+    const CUtensorMap* tbb = &tb;
+    if (p.mode != 0 && p.f16ops) { variant = 1; ta = &tm_l16; }
+    else if (p.mode == 0 && upd16) { variant = p.from_c ? (p.fc.c16 ? 2 : 3) : 1; ta = &tm_l16; tbb = &tm_l16; }
+#define TB_GEMM_LAUNCH(F, S, W) tf32_gemm_kernel<F, S, W><<<grid, t_threads(W), t_smem(W), st>>>(*ta, *tbb, p)
+    if (epi_warps == 16) {
+      if (variant == 0) TB_GEMM_LAUNCH(false, 0, 16);
+      else if (variant == 1) TB_GEMM_LAUNCH(true, 0, 16);
+      else if (variant == 2) TB_GEMM_LAUNCH(true, 1, 16);
+      else TB_GEMM_LAUNCH(true, 2, 16);
+    } else {
+      if (variant == 0) TB_GEMM_LAUNCH(false, 0, 8);
+      else if (variant == 1) TB_GEMM_LAUNCH(true, 0, 8);
+      else if (variant == 2) TB_GEMM_LAUNCH(true, 1, 8);
+      else TB_GEMM_LAUNCH(true, 2, 8);
+    }
+#undef TB_GEMM_LAUNCH
     launches[0]++;
     return cudaGetLastError();
   };
   const int OB = 256;
   for (int c0 = 0; c0 < ntp; c0 += OB) {
     const int w = (ntp - c0) < OB ? (ntp - c0) : OB;
+    // With the inverse of the whole diagonal block the rows below it need ONE GEMM (K = 256) instead of four narrow
+    // update / triangular-solve rounds; the narrow rounds then only cover the 256 rows of the diagonal block itself.
+    const bool wide = Linv256 != nullptr && w == OB && c0 + w < ntp;
+    // ... and when this block column is formed from the cross-products, its rows below the diagonal block never exist
+    // in fp32: the update writes them as halves into L16, the panel GEMM (fp16 operands) replaces them in place by the
+    // factor entries -- 2 + 2 bytes per entry instead of 4 + 4
+    const bool col16 = wide && t16 && upd16 && from_c && !(c0 == 0 && from_c->skip_blk0);
     if (c0 > 0 || (from_c && upd16 && !from_c->skip_blk0)) {
       // (block column 0 with from_c: K = 0, the launch only forms the block column from the cross-products)
       if (mark) mark(mark_ctx, 0, 0);
@@ -916,21 +986,19 @@ cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, float* Linv2
       if (from_c && upd16) {                       // this launch is the first touch of block column c0: form it from C
         p.from_c = 1;
         p.fc = *from_c;
+        p.t16 = col16 ? 1 : 0;
       }
       if ((e = gemm(tm_l, p)) != cudaSuccess) return e;
       if (mark) mark(mark_ctx, 0, 1);
     }
     if (mark) mark(mark_ctx, 1, 0);
-    // With the inverse of the whole diagonal block the rows below it need ONE GEMM (K = 256) instead of four narrow
-    // update / triangular-solve rounds; the narrow rounds then only cover the 256 rows of the diagonal block itself.
-    const bool wide = Linv256 != nullptr && w == OB && c0 + w < ntp;
     const int narrow_end = wide ? c0 + w : ntp;
     if (Linv256 != nullptr && narrow_end == c0 + w) {
       // the narrow rounds only cover the diagonal block itself: potrf + inverse per 64-block, then one small
       // mma.sync kernel per step for the solves below it and the update of the next block column
       const int nbk = w / NB;
       for (int b = 0; b < nbk; ++b) {
-        chol_diag32_kernel<<<n_jobs, 256, DIAG32_SMEM, st>>>(L32, Linv32, static_cast<__half*>(L16), status, ntp,
+        chol_diag32_kernel<<<n_jobs, DT, DIAG32_SMEM, st>>>(L32, Linv32, static_cast<__half*>(L16), status, ntp,
                                                              (c0 + b * NB) / NB);
         launches[1]++;
         if ((e = cudaGetLastError()) != cudaSuccess) return e;
@@ -948,7 +1016,7 @@ cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, float* Linv2
         p.b_rows_per_job = ntp; p.c_col0 = cc; p.N = NB; p.mode = 0;
         if ((e = gemm(tm_l, p)) != cudaSuccess) return e;
       }
-      chol_diag32_kernel<<<n_jobs, 256, DIAG32_SMEM, st>>>(L32, Linv32, static_cast<__half*>(L16), status, ntp, cc / NB);
+      chol_diag32_kernel<<<n_jobs, DT, DIAG32_SMEM, st>>>(L32, Linv32, static_cast<__half*>(L16), status, ntp, cc / NB);
       launches[1]++;
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
       if (cc + NB < narrow_end) {
@@ -959,7 +1027,8 @@ cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, float* Linv2
       }
     }
     if (wide) {
-      trinv256_kernel<<<n_jobs, 256, TRINV_SMEM, st>>>(L32, Linv32, Linv256, ntp, c0);
+      trinv256_kernel<<<n_jobs, 256, TRINV_SMEM, st>>>(L32, Linv32, Linv256,
+                                                       col16 ? reinterpret_cast<__half*>(Linv256) : nullptr, ntp, c0);
       launches[1]++;
       if ((e = cudaGetLastError()) != cudaSuccess) return e;
       GemmParams p{};
@@ -967,7 +1036,8 @@ cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, float* Linv2
       p.N = w; p.mode = 1;
       // rows below the diagonal block: later steps read them only through the fp16 copy (updates, solve sweeps)
       p.skip32 = upd16 ? 1 : 0;
-      if ((e = gemm(tm_inv256, p)) != cudaSuccess) return e;
+      p.f16ops = col16 ? 1 : 0;
+      if ((e = gemm(col16 ? tm_x16 : tm_inv256, p)) != cudaSuccess) return e;
     }
     if (mark) mark(mark_ctx, 1, 1);
   }
