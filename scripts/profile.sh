@@ -16,13 +16,13 @@ FULL="ncu --set full --clock-control none --import-source on"
 if [ "$PREC" = "mixed" ]; then
   $FULL -k regex:solve_mixed_kernel -s 0 -c 1 -o gpurun_out/prof_solve_$TAG -f $CMD > gpurun_out/ncu_solve_$TAG.log 2>&1
   echo "solve capture rc=$?"
-  # tf32_gemm_kernel launches of one evaluation, in order (round 2: the narrow rounds of the diagonal block are their
-  # own mma.sync kernels): block column 0 has 1 (the wide solve), every later full block column J has 2 (its outer
-  # update, then its wide solve).  J = 6: launch 1 + 5 * 2 = 11 is the outer update (fp16 operands, K = 1536, N = 256,
-  # block column formed from the int16 cross-products), launch 12 the wide triangular solve (tf32, K = N = 256)
-  $FULL -k regex:tf32_gemm_kernel -s 11 -c 1 -o gpurun_out/prof_update_$TAG -f $CMD > gpurun_out/ncu_update_$TAG.log 2>&1
+  # tf32_gemm_kernel launches of one evaluation, in order: every full block column J has 2 -- its outer update (J = 0: the
+  # K = 0 launch that only forms the block column from the cross-products), then its wide panel GEMM.  J = 6: launch 12 is
+  # the outer update (fp16 operands, K = 1536, N = 256, block column formed from the int16 cross-products, rows below the
+  # diagonal block written as halves), launch 13 the wide panel GEMM (fp16 operands, K = N = 256, in place in L16)
+  $FULL -k regex:tf32_gemm_kernel -s 12 -c 1 -o gpurun_out/prof_update_$TAG -f $CMD > gpurun_out/ncu_update_$TAG.log 2>&1
   echo "update capture rc=$?"
-  $FULL -k regex:tf32_gemm_kernel -s 12 -c 1 -o gpurun_out/prof_trsm_$TAG -f $CMD > gpurun_out/ncu_trsm_$TAG.log 2>&1
+  $FULL -k regex:tf32_gemm_kernel -s 13 -c 1 -o gpurun_out/prof_trsm_$TAG -f $CMD > gpurun_out/ncu_trsm_$TAG.log 2>&1
   echo "wide trsm capture rc=$?"
 else
   $FULL -k regex:chol_gemm_kernel -s 76 -c 4 -o gpurun_out/prof_chol_$TAG -f $CMD > gpurun_out/ncu_chol_$TAG.log 2>&1

@@ -465,39 +465,36 @@ __device__ __forceinline__ void warp_trinv32(float (&x)[32], const float* L, int
 
 // 128 threads and 29 KiB of shared memory per block: SEVEN blocks per SM, so 1 000 matrices are one wave (the version
 // with 256 threads / 37 KiB ran four per SM = two waves, with one warp of eight busy in the serial phases).
-constexpr int DT = 128;                                   // threads per block
+constexpr int DT = 128;                                   // threads that work on one 64 x 64 diagonal block
 constexpr int XLD = 33;
-__global__ void __launch_bounds__(DT) chol_diag32_kernel(float* __restrict__ L32, float* __restrict__ Linv32,
-                                                         __half* __restrict__ L16, int* __restrict__ status, int ntp,
-                                                         int jb) {
-  __shared__ float Ls[NB * DLD];
-  __shared__ float X11[32 * XLD];
-  __shared__ float X22[32 * XLD];
-  __shared__ float X21[32 * XLD];
-  __shared__ int bad;
+constexpr int DIAG_SCRATCH = NB * DLD + 3 * 32 * XLD;     // floats: Ls, X11, X22, X21
+
+// barrier of the DT threads that run diag64_body: the whole block (stand-alone kernel) or named barrier 1 (fused chain,
+// where the other warps of the block wait at barrier 0)
+template <bool NAMED>
+__device__ __forceinline__ void diag_sync() {
+  if (NAMED) asm volatile("bar.sync 1, 128;" ::: "memory");
+  else __syncthreads();
+}
+
+// Ls [64][DLD]: in = the block (lower triangle meaningful), out = its factor rounded to TF32 (upper-left / lower-right
+// triangles zeroed; the UPPER-RIGHT quadrant is scratch and holds garbage).  X11 / X22 / X21 [32][XLD]: quadrants of
+// the inverse of the factor (not yet rounded).  Called by DT threads (tid 0 .. DT-1) after a barrier that made Ls
+// visible; ends with a diag_sync.  Returns false (to every thread of warp 0 only) on a non-positive pivot.
+template <bool NAMED>
+__device__ __forceinline__ bool diag64_body(float* Ls, float* X11, float* X22, float* X21, int tid) {
   float* Ps = Ls + 32;                                    // P = L21 X11 lives in the (unused) upper-right quadrant, stride DLD
-  const int job = blockIdx.x;
-  float* D = L32 + ((size_t)job * ntp + (size_t)jb * NB) * ntp + jb * NB;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  if (tid == 0) bad = 0;
-  for (int e = tid; e < NB * 16; e += DT) {               // coalesced rows, 16 bytes per thread
-    const int r = e >> 4, c4 = (e & 15) * 4;
-    const float4 v = *reinterpret_cast<const float4*>(D + (size_t)r * ntp + c4);
-    Ls[r * DLD + c4] = v.x;
-    Ls[r * DLD + c4 + 1] = v.y;
-    Ls[r * DLD + c4 + 2] = v.z;
-    Ls[r * DLD + c4 + 3] = v.w;
-  }
-  __syncthreads();
+  const int warp = tid >> 5, lane = tid & 31;
+  bool ok = true;
   float a[32];
   if (warp == 0) {                                        // L11
 #pragma unroll
     for (int c = 0; c < 32; ++c) a[c] = Ls[lane * DLD + c];
-    if (!warp_potrf32(a)) bad = 1;
+    ok = warp_potrf32(a);
 #pragma unroll
     for (int c = 0; c < 32; ++c) Ls[lane * DLD + c] = c <= lane ? round_tf32(a[c]) : 0.f;
   }
-  __syncthreads();
+  diag_sync<NAMED>();
   if (warp == 1) {                                        // L21 = A21 L11^-T
 #pragma unroll
     for (int c = 0; c < 32; ++c) a[c] = Ls[(32 + lane) * DLD + c];
@@ -509,7 +506,7 @@ __global__ void __launch_bounds__(DT) chol_diag32_kernel(float* __restrict__ L32
 #pragma unroll
     for (int r = 0; r < 32; ++r) X11[r * XLD + lane] = a[r];
   }
-  __syncthreads();
+  diag_sync<NAMED>();
   {                                                       // A22 -= L21 L21^T (lower part), 8 entries per thread
     const int r = tid >> 2, c0 = (tid & 3) * 8;
     if (c0 <= r) {
@@ -524,11 +521,11 @@ __global__ void __launch_bounds__(DT) chol_diag32_kernel(float* __restrict__ L32
         if (c0 + j <= r) Ls[(32 + r) * DLD + 32 + c0 + j] -= acc[j];
     }
   }
-  __syncthreads();
+  diag_sync<NAMED>();
   if (warp == 0) {                                        // L22
 #pragma unroll
     for (int c = 0; c < 32; ++c) a[c] = Ls[(32 + lane) * DLD + 32 + c];
-    if (!warp_potrf32(a)) bad = 1;
+    ok = warp_potrf32(a) && ok;
 #pragma unroll
     for (int c = 0; c < 32; ++c) Ls[(32 + lane) * DLD + 32 + c] = c <= lane ? round_tf32(a[c]) : 0.f;
   } else {                                                // P = L21 X11, meanwhile (96 threads, 32 x 32 outputs)
@@ -539,13 +536,13 @@ __global__ void __launch_bounds__(DT) chol_diag32_kernel(float* __restrict__ L32
       Ps[r * DLD + c] = s;
     }
   }
-  __syncthreads();
+  diag_sync<NAMED>();
   if (warp == 3) {                                        // X22 = L22^-1
     warp_trinv32(a, Ls + 32 * DLD + 32, lane);
 #pragma unroll
     for (int r = 0; r < 32; ++r) X22[r * XLD + lane] = a[r];
   }
-  __syncthreads();
+  diag_sync<NAMED>();
   {                                                       // X21 = -X22 P
     const int r = tid >> 2, c0 = (tid & 3) * 8;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -557,18 +554,47 @@ __global__ void __launch_bounds__(DT) chol_diag32_kernel(float* __restrict__ L32
 #pragma unroll
     for (int j = 0; j < 8; ++j) X21[r * XLD + c0 + j] = -acc[j];
   }
+  diag_sync<NAMED>();
+  return ok;
+}
+// entries of the results of diag64_body: the factor (zero above the diagonal) and its inverse
+__device__ __forceinline__ float diag_l(const float* Ls, int rr, int c) {
+  return (rr < 32 && c >= 32) ? 0.f : Ls[rr * DLD + c];
+}
+__device__ __forceinline__ float diag_x(const float* X11, const float* X22, const float* X21, int rr, int c) {
+  return rr < 32 ? (c < 32 ? X11[rr * XLD + c] : 0.f) : (c < 32 ? X21[(rr - 32) * XLD + c] : X22[(rr - 32) * XLD + c - 32]);
+}
+
+__global__ void __launch_bounds__(DT) chol_diag32_kernel(float* __restrict__ L32, float* __restrict__ Linv32,
+                                                         __half* __restrict__ L16, int* __restrict__ status, int ntp,
+                                                         int jb) {
+  __shared__ float sc[DIAG_SCRATCH];
+  float* Ls = sc;
+  float* X11 = Ls + NB * DLD;
+  float* X22 = X11 + 32 * XLD;
+  float* X21 = X22 + 32 * XLD;
+  const int job = blockIdx.x;
+  float* D = L32 + ((size_t)job * ntp + (size_t)jb * NB) * ntp + jb * NB;
+  const int tid = threadIdx.x;
+  for (int e = tid; e < NB * 16; e += DT) {               // coalesced rows, 16 bytes per thread
+    const int r = e >> 4, c4 = (e & 15) * 4;
+    const float4 v = *reinterpret_cast<const float4*>(D + (size_t)r * ntp + c4);
+    Ls[r * DLD + c4] = v.x;
+    Ls[r * DLD + c4 + 1] = v.y;
+    Ls[r * DLD + c4 + 2] = v.z;
+    Ls[r * DLD + c4 + 3] = v.w;
+  }
   __syncthreads();
+  const bool ok = diag64_body<false>(Ls, X11, X22, X21, tid);
+  if (!ok && tid < 32) status[job] = 1;                   // (warp 0 holds the verdict)
   float* Li = Linv32 + ((size_t)job * ntp + (size_t)jb * NB) * NB;
   for (int e = tid; e < NB * NB; e += DT) {
     const int rr = e >> 6, c = e & 63;
-    const float l = (rr < 32 && c >= 32) ? 0.f : Ls[rr * DLD + c];      // (the upper-right quadrant held P)
+    const float l = diag_l(Ls, rr, c);
     D[(size_t)rr * ntp + c] = l;
     if (L16) L16[((size_t)job * ntp + (size_t)jb * NB + rr) * ntp + jb * NB + c] = __float2half_rn(l);
-    const float x = rr < 32 ? (c < 32 ? X11[rr * XLD + c] : 0.f)
-                            : (c < 32 ? X21[(rr - 32) * XLD + c] : X22[(rr - 32) * XLD + c - 32]);
-    Li[e] = round_tf32(x);
+    Li[e] = round_tf32(diag_x(X11, X22, X21, rr, c));
   }
-  if (tid == 0 && bad) status[job] = 1;
 }
 
 // Inverse of the 256 x 256 lower-triangular diagonal block of the factor, from its 64 x 64 blocks and the inverses of
@@ -587,8 +613,10 @@ __device__ __forceinline__ void mma_tf32_16x8x8(float (&c)[4], const uint32_t (&
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
 
-// acc[nt] (16 x 8 fragments, nt = 0..3) += As[64][AS_LD] (rows 16 (warp & 3) ..) * Bs[64][XS_LD] (cols 32 (warp >> 2) ..)
+// acc[nt] (16 x 8 fragments, nt = 0..3) += As[64][AS_LD] (rows 16 (warp & 3) ..) * Bs[64][BLD] (cols 32 (warp >> 2) ..)
+template <int BLD = XS_LD>
 __device__ __forceinline__ void block_mma(float (&acc)[4][4], const float* As, const float* Bs, int warp, int lane) {
+  constexpr int XS_LD = BLD;
   const int g = lane >> 2, t = lane & 3;
   const float* a_base = As + (16 * (warp & 3) + g) * AS_LD + t;
   const float* b_base = Bs + t * XS_LD + 32 * (warp >> 2) + g;
@@ -851,6 +879,177 @@ __global__ void __launch_bounds__(256) chol_narrow_kernel(float* __restrict__ L3
   }
 }
 
+// The whole diagonal-block chain of one block column in ONE kernel, for small batches (n_jobs <= ~ SM count: strong
+// scaling at 125 genomes per GPU, config 4's waves).  There the eight launches per block column (diag32 x 4,
+// narrow x 3 ...) are pure dependent latency: every stage re-loads its operands from global memory behind a kernel
+// boundary.  Here one CTA per job keeps the lower triangle of the (up to) 256 x 256 block in shared memory (ten
+// 64 x 64 blocks, 174 KB) and walks the same stages -- the device code of chol_diag32_kernel and chol_narrow_kernel on
+// shared-memory operands, same order of operations, bit-identical results.  The slot of a diagonal block receives the
+// inverse of its factor once it is known (the right operand of the solves below it).  trinv256_kernel follows as before.
+constexpr int CH_BLK = 64 * AS_LD;                        // floats per block slot
+constexpr int CHAIN_SMEM = 13 * CH_BLK * 4;               // ten blocks + three for the inverse (they overlap the diagonal scratch)
+static_assert(DIAG_SCRATCH <= 3 * CH_BLK, "diagonal scratch must fit into the inverse's buffers");
+__device__ __forceinline__ int ch_slot(int i, int j) { return (i * (i + 1) / 2 + j) * CH_BLK; }   // i >= j
+
+__global__ void __launch_bounds__(256, 1) chol_chain256_kernel(float* __restrict__ L32, float* __restrict__ Linv32,
+                                                               __half* __restrict__ L16, int* __restrict__ status,
+                                                               float* __restrict__ X32, __half* __restrict__ X16,
+                                                               int ntp, int c0, int nbk) {
+  extern __shared__ float csm[];
+  float* S = csm;
+  float* Ls = S + 10 * CH_BLK;
+  float* X11 = Ls + NB * DLD;
+  float* X22 = X11 + 32 * XLD;
+  float* X21 = X22 + 32 * XLD;
+  const int job = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float* base = L32 + ((size_t)job * ntp + c0) * ntp + c0;
+  __half* base16 = L16 ? L16 + ((size_t)job * ntp + c0) * ntp + c0 : nullptr;
+  const int g = lane >> 2, t = lane & 3;
+  const int frow = 16 * (warp & 3) + g, fcol = 32 * (warp >> 2) + 2 * t;
+  for (int i = 0; i < nbk; ++i)
+    for (int j = 0; j <= i; ++j) {
+      float* dst = S + ch_slot(i, j);
+      const float* src = base + (size_t)(64 * i) * ntp + 64 * j;
+      for (int e = tid; e < 64 * 16; e += 256) {
+        const int r = e >> 4, c4 = (e & 15) * 4;
+        *reinterpret_cast<float4*>(dst + r * AS_LD + c4) = *reinterpret_cast<const float4*>(src + (size_t)r * ntp + c4);
+      }
+    }
+  __syncthreads();
+  float acc[4][4];
+  auto clear = [&]() {
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[nt][e] = 0.f;
+  };
+  for (int b = 0; b < nbk; ++b) {
+    float* Sbb = S + ch_slot(b, b);
+    for (int e = tid; e < NB * NB; e += 256) Ls[(e >> 6) * DLD + (e & 63)] = Sbb[(e >> 6) * AS_LD + (e & 63)];
+    __syncthreads();
+    if (tid < DT) {
+      const bool ok = diag64_body<true>(Ls, X11, X22, X21, tid);
+      if (!ok && tid < 32) status[job] = 1;
+    }
+    __syncthreads();
+    float* Li = Linv32 + ((size_t)job * ntp + c0 + 64 * b) * NB;
+    for (int e = tid; e < NB * NB; e += 256) {
+      const int rr = e >> 6, c = e & 63;
+      const float l = diag_l(Ls, rr, c);
+      base[(size_t)(64 * b + rr) * ntp + 64 * b + c] = l;
+      if (base16) base16[(size_t)(64 * b + rr) * ntp + 64 * b + c] = __float2half_rn(l);
+      const float x = round_tf32(diag_x(X11, X22, X21, rr, c));
+      Li[e] = x;
+      Sbb[rr * AS_LD + c] = x;
+    }
+    __syncthreads();
+    if (b + 1 >= nbk) break;
+    // (i) triangular solves of block column b: L_ib = T_ib Linv_b^T
+    for (int i = b + 1; i < nbk; ++i) {
+      float* Sib = S + ch_slot(i, b);
+      clear();
+      block_mma_nt(acc, Sib, Sbb, warp, lane);
+      __syncthreads();                 // every warp has read Sib before anybody replaces it
+      float* blk = base + (size_t)(64 * i) * ntp + 64 * b;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float2 lo = make_float2(round_tf32(acc[nt][0]), round_tf32(acc[nt][1]));
+        const float2 hi = make_float2(round_tf32(acc[nt][2]), round_tf32(acc[nt][3]));
+        *reinterpret_cast<float2*>(Sib + frow * AS_LD + fcol + 8 * nt) = lo;
+        *reinterpret_cast<float2*>(Sib + (frow + 8) * AS_LD + fcol + 8 * nt) = hi;
+        *reinterpret_cast<float2*>(blk + (size_t)frow * ntp + fcol + 8 * nt) = lo;
+        *reinterpret_cast<float2*>(blk + (size_t)(frow + 8) * ntp + fcol + 8 * nt) = hi;
+        if (base16) {
+          __half* h = base16 + (size_t)(64 * i) * ntp + 64 * b;
+          *reinterpret_cast<__half2*>(h + (size_t)frow * ntp + fcol + 8 * nt) = __floats2half2_rn(lo.x, lo.y);
+          *reinterpret_cast<__half2*>(h + (size_t)(frow + 8) * ntp + fcol + 8 * nt) = __floats2half2_rn(hi.x, hi.y);
+        }
+      }
+    }
+    __syncthreads();
+    // (ii) left-looking update of block column j = b + 1 with every finished column of the diagonal block
+    const int j = b + 1;
+    for (int i = j; i < nbk; ++i) {
+      clear();
+      for (int k = 0; k <= b; ++k) block_mma_nt(acc, S + ch_slot(i, k), S + ch_slot(j, k), warp, lane);
+      float* Sij = S + ch_slot(i, j);  // (nobody reads column j during this phase: fragments are private)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        float2* p0 = reinterpret_cast<float2*>(Sij + frow * AS_LD + fcol + 8 * nt);
+        float2* p1 = reinterpret_cast<float2*>(Sij + (frow + 8) * AS_LD + fcol + 8 * nt);
+        float2 v0 = *p0, v1 = *p1;
+        v0.x -= acc[nt][0];
+        v0.y -= acc[nt][1];
+        v1.x -= acc[nt][2];
+        v1.y -= acc[nt][3];
+        *p0 = v0;
+        *p1 = v1;
+      }
+    }
+    __syncthreads();
+  }
+  if (X32 == nullptr && X16 == nullptr) return;
+  // Inverse of the 256 x 256 factor (trinv256_kernel's recurrence in the same order, operands already in shared memory:
+  // off-diagonal slots hold L_ik, diagonal slots Linv_i):  X_bb = Linv_b,  X_ib = -Linv_i sum_{k=b}^{i-1} L_ik X_kb.
+  float* Out = X32 ? X32 + (size_t)job * 256 * 256 : nullptr;
+  __half* Out16 = X16 ? X16 + (size_t)job * 256 * 256 : nullptr;
+  auto put4 = [&](size_t off, const float4 v) {
+    if (Out16) {
+      const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+      *reinterpret_cast<uint2*>(Out16 + off) =
+          make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+    } else {
+      *reinterpret_cast<float4*>(Out + off) = v;
+    }
+  };
+  auto put2 = [&](size_t off, const float2 v) {
+    if (Out16) *reinterpret_cast<__half2*>(Out16 + off) = __floats2half2_rn(v.x, v.y);
+    else *reinterpret_cast<float2*>(Out + off) = v;
+  };
+  float* Ss = S + 10 * CH_BLK;         // (the diagonal scratch is free now)
+  float* XA = Ss + CH_BLK;             // X_{b+1, b}
+  float* XB = XA + CH_BLK;             // X_{b+2, b}
+  for (int b = 0; b < 4; ++b) {
+    for (int i = 0; i < b; ++i)
+      for (int e = tid; e < 64 * 16; e += 256)
+        put4((size_t)(64 * i + (e >> 4)) * 256 + 64 * b + (e & 15) * 4, make_float4(0.f, 0.f, 0.f, 0.f));
+    const float* Xbb = S + ch_slot(b, b);
+    for (int e = tid; e < 64 * 16; e += 256) {
+      const int r = e >> 4, c4 = (e & 15) * 4;
+      put4((size_t)(64 * b + r) * 256 + 64 * b + c4, *reinterpret_cast<const float4*>(Xbb + r * AS_LD + c4));
+    }
+  }
+  for (int b = 0; b < 3; ++b) {
+    for (int i = b + 1; i < 4; ++i) {
+      clear();
+      for (int k = b; k < i; ++k)
+        block_mma<AS_LD>(acc, S + ch_slot(i, k), k == b ? S + ch_slot(b, b) : (k == b + 1 ? XA : XB), warp, lane);
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        *reinterpret_cast<float2*>(Ss + frow * AS_LD + fcol + 8 * nt) = make_float2(round_tf32(acc[nt][0]), round_tf32(acc[nt][1]));
+        *reinterpret_cast<float2*>(Ss + (frow + 8) * AS_LD + fcol + 8 * nt) = make_float2(round_tf32(acc[nt][2]), round_tf32(acc[nt][3]));
+      }
+      __syncthreads();
+      clear();
+      block_mma<AS_LD>(acc, S + ch_slot(i, i), Ss, warp, lane);
+      float* Xi = i == b + 1 ? XA : (i == b + 2 ? XB : nullptr);
+      const size_t oi = (size_t)(64 * i) * 256 + 64 * b;
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt) {
+        const float2 lo = make_float2(round_tf32(-acc[nt][0]), round_tf32(-acc[nt][1]));
+        const float2 hi = make_float2(round_tf32(-acc[nt][2]), round_tf32(-acc[nt][3]));
+        if (Xi) {
+          *reinterpret_cast<float2*>(Xi + frow * AS_LD + fcol + 8 * nt) = lo;
+          *reinterpret_cast<float2*>(Xi + (frow + 8) * AS_LD + fcol + 8 * nt) = hi;
+        }
+        put2(oi + (size_t)frow * 256 + fcol + 8 * nt, lo);
+        put2(oi + (size_t)(frow + 8) * 256 + fcol + 8 * nt, hi);
+      }
+      __syncthreads();
+    }
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -900,6 +1099,8 @@ cudaError_t tb_chol_tc_init() {
   }
   cudaError_t e = cudaFuncSetAttribute(trinv256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TRINV_SMEM);
   if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(chol_chain256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CHAIN_SMEM);
+  if (e != cudaSuccess) return e;
 #define TB_GEMM_ATTR(F, S, W)                                                                                       \
   e = cudaFuncSetAttribute(tf32_gemm_kernel<F, S, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, t_smem(W)); \
   if (e != cudaSuccess) return e;
@@ -914,7 +1115,10 @@ cudaError_t tb_chol_tc_init() {
 // launches[0] / launches[1] receive the number of GEMM / diagonal-block kernel launches.
 cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, float* Linv256, int* status, int n_jobs, int ntp,
                               int n_sm, cudaStream_t st, int* launches, std::string* err,
-                              void (*mark)(void*, int, int), void* mark_ctx, const TbFromC* from_c, int t16, int epi_warps) {
+                              void (*mark)(void*, int, int), void* mark_ctx, const TbFromC* from_c, int t16, int epi_warps,
+                              int chain_fused_jobs) {
+  const bool chain_inverse = chain_fused_jobs >= 0;      // (negative: fused chain for -n jobs without the inverse; A/B)
+  if (chain_fused_jobs < 0) chain_fused_jobs = -chain_fused_jobs;
   CUtensorMap tm_l, tm_inv, tm_inv256;
   cudaError_t e = encode_f32(&tm_l, L32, (size_t)ntp, (size_t)n_jobs * ntp + 128, err);
   if (e != cudaSuccess) return e;
@@ -993,10 +1197,20 @@ cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, float* Linv2
     }
     if (mark) mark(mark_ctx, 1, 0);
     const int narrow_end = wide ? c0 + w : ntp;
+    bool chain_has_inverse = false;      // the fused chain kernel also wrote the inverse of the diagonal block
     if (Linv256 != nullptr && narrow_end == c0 + w) {
       // the narrow rounds only cover the diagonal block itself: potrf + inverse per 64-block, then one small
       // mma.sync kernel per step for the solves below it and the update of the next block column
       const int nbk = w / NB;
+      if (n_jobs <= chain_fused_jobs) {
+        // small batch: the whole chain of this block column in one launch, one CTA per job
+        chol_chain256_kernel<<<n_jobs, 256, CHAIN_SMEM, st>>>(
+            L32, Linv32, static_cast<__half*>(L16), status, wide && chain_inverse && !col16 ? Linv256 : nullptr,
+            wide && chain_inverse && col16 ? reinterpret_cast<__half*>(Linv256) : nullptr, ntp, c0, nbk);
+        chain_has_inverse = wide && chain_inverse;
+        launches[1]++;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      } else
       for (int b = 0; b < nbk; ++b) {
         chol_diag32_kernel<<<n_jobs, DT, DIAG32_SMEM, st>>>(L32, Linv32, static_cast<__half*>(L16), status, ntp,
                                                              (c0 + b * NB) / NB);
@@ -1027,10 +1241,12 @@ cudaError_t tb_chol_tc_factor(float* L32, float* Linv32, void* L16, float* Linv2
       }
     }
     if (wide) {
-      trinv256_kernel<<<n_jobs, 256, TRINV_SMEM, st>>>(L32, Linv32, Linv256,
-                                                       col16 ? reinterpret_cast<__half*>(Linv256) : nullptr, ntp, c0);
-      launches[1]++;
-      if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      if (!chain_has_inverse) {
+        trinv256_kernel<<<n_jobs, 256, TRINV_SMEM, st>>>(L32, Linv32, Linv256,
+                                                         col16 ? reinterpret_cast<__half*>(Linv256) : nullptr, ntp, c0);
+        launches[1]++;
+        if ((e = cudaGetLastError()) != cudaSuccess) return e;
+      }
       GemmParams p{};
       p.row0 = c0 + w; p.a_col0 = c0; p.K = w; p.b_row0 = 0; p.b_col0 = 0; p.b_rows_per_job = 256; p.c_col0 = c0;
       p.N = w; p.mode = 1;

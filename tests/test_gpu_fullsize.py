@@ -70,6 +70,44 @@ def test_mixed_agrees_with_fp64_and_waves_do_not_matter(big):
     assert np.all(np.isfinite(test_fit)) and np.all((test_fit >= 0) & (test_fit <= 1))
 
 
+def test_fused_chain_equals_launch_per_stage_chain(big):
+    """Small waves run the diagonal-block chain of a block column as ONE kernel on shared-memory operands
+    (chol_chain256_kernel), large ones as a launch per stage (chol_diag32 / chol_narrow): same device code, same order of
+    operations, so the factor and with it every fitness is bit-identical; neither path may lean on the fp64 fallback.
+    Slot 1 (4 000 training animals) ends in a partial block column."""
+    from tblup_b200 import engine as E, synth
+    eng = big[0]
+    flat, off = synth.random_genomes(12, M, K, seed=11)
+    eng.set_precision("mixed")
+    out = {}
+    for fused, inverse in ((0, 1), (1 << 20, 0), (1 << 20, 1)):
+        eng.set_option("chain_fused", fused)
+        eng.set_option("chain_inverse", inverse)       # 0: the fused kernel leaves the 256-block inverse to trinv256_kernel
+        out[fused, inverse] = [eng.evaluate_packed(flat, off, slots=[s], mode=E.MODE_AUTO)[:, 0] for s in (0, 1)]
+        assert eng.last_precision() == "mixed" and eng.info("last_fallbacks") == 0
+    eng.set_option("chain_fused", -1)
+    for key in ((1 << 20, 0), (1 << 20, 1)):
+        for a, b in zip(out[0, 1], out[key]):
+            assert np.all(np.isfinite(a)) and np.array_equal(a, b), key
+
+
+def test_half_precision_block_columns_agree_with_fp32_block_columns(big):
+    """t16 (default): the entries of a block column below its diagonal block live as halves between the update that forms
+    them and the panel GEMM that turns them into factor entries (fp16 operands); t16 = 0 keeps them in fp32 and multiplies
+    in TF32.  Both are 10-bit preconditioners of the same exact operator: the refined fitness agrees far inside the bar."""
+    from tblup_b200 import engine as E, synth
+    eng = big[0]
+    flat, off = synth.random_genomes(6, M, K, seed=13)
+    eng.set_precision("mixed")
+    out = {}
+    for t16 in (1, 0):
+        eng.set_option("t16", t16)
+        out[t16] = eng.evaluate_packed(flat, off, slots=[0], mode=E.MODE_AUTO)[:, 0]
+        assert eng.last_precision() == "mixed" and eng.info("last_fallbacks") == 0
+    eng.set_option("t16", 1)
+    assert np.abs(out[1] - out[0]).max() < 1e-8
+
+
 def test_two_genomes_against_the_reference_algorithm(big):
     from oracle import gblup_oracle as O
     from tblup_b200 import engine as E
