@@ -59,9 +59,10 @@ DEFAULT_WORKLOAD = "c2_5000x50000_k5001_pop1000"
 # captures (profiles/README.md says how each was taken); filled in after every re-profile
 NCU_TRAFFIC = {
     "solve_c32": {"bytes_per_unit": 164.06e6, "source": "profiles/r01p_solve_raw.csv"},
-    "solve_c16": {"bytes_per_unit": 91.13e6, "source": "profiles/r02_solve_raw.csv (1 000 matrices per launch)"},
+    "solve_c16": {"bytes_per_unit": 91.10e6, "source": "profiles/r02b_solve_raw.csv (1 000 matrices per launch)"},
     "gram_fused_c16": {"bytes_per_unit": 58.93e6, "source": "profiles/r01q_gram_raw.csv (1 000 genomes per launch)"},
-    "gram_fp4_fused_c16": {"bytes_per_unit": 35.55e6, "source": "profiles/r02_gram_raw.csv (1 000 genomes per launch)"},
+    "gram_fp4_fused_c16": {"bytes_per_unit": 27.11e6, "source": "profiles/r02b_gram_raw.csv (1 000 genomes per launch; 10.49 GB read + "
+                                                                "16.62 GB written)"},
 }
 H2 = 0.4
 METRIC = "gblup_fitness_evals_per_sec"
