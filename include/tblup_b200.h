@@ -122,7 +122,14 @@ int tb_debug_fetch(tb_ctx* ctx, int what, int job, void* out, size_t nbytes);
  * shared B tile fetched half by each and TMA-multicast to both), "fuse_in_gram" (0/1, default 0: the Gram epilogue writes
  * the whole scaled fp32 matrix as in round 1; by default the Cholesky updates form it from the cross-products),
  * "perm_rows" (0/1, default 1: a single scattered row set -- Monte-Carlo split, unaligned fold, custom splitter -- is
- * turned into a prefix by permuting the panel rows at gather time, so it runs the contiguous kernels) */
+ * turned into a prefix by permuting the panel rows at gather time, so it runs the contiguous kernels),
+ * "solve_pair" (0 = one CTA per matrix, 2 = a cluster of two, 1 = by batch size [default]),
+ * "t16" (0/1, default 1: the entries of a Cholesky block column below its diagonal block are kept as halves between
+ * the update that forms them and the panel GEMM that finishes them in place; 0 = fp32 / TF32 as in the first version),
+ * "epi_warps" (8 or 16 [default]: epilogue warps of the Cholesky GEMM kernel), "chain_fused" (the 64 x 64
+ * diagonal-block chain of a block column runs as ONE shared-memory kernel for waves of at most this many jobs;
+ * -1 = the SM count [default], 0 = never), "chain_inverse" (0/1, default 1: that kernel also forms the inverse of the
+ * 256-wide diagonal block).  The A/B options change speed, never results beyond the refinement tolerance. */
 int tb_set_option(tb_ctx* ctx, const char* name, long long value);
 
 /* Facts about the last evaluation / the context: "last_c16", "last_fused_scale", "last_mixed", "last_wave",

@@ -50,3 +50,9 @@ def test_algorithmic_work_formulas():
     b = bench.chol_update_bytes(n, 256)
     rmw = sum((n - c0) * min(256, n - c0) * 8 for c0 in range(256, n, 256))
     assert b > rmw and abs(b / 80.2e6 - 1) < 0.01
+    # block column formed from int16 cross-products (2 B read + 4 B written per entry), and with t16 the rows below the
+    # diagonal block of every full-width block column written as halves (2 + 2 B): the figures quoted in DESIGN.md §5
+    assert abs(bench.chol_update_bytes(n, 256, 2) / 70.8e6 - 1) < 0.01
+    b16 = bench.chol_update_bytes(n, 256, 2, True)
+    below = sum((n - c0 - 256) * 256 for c0 in range(256, n, 256) if c0 + 256 < n)
+    assert b16 == bench.chol_update_bytes(n, 256, 2) - 2 * below and abs(b16 / 62.9e6 - 1) < 0.01
