@@ -85,6 +85,15 @@ int tb_storage_info(const tb_ctx* ctx, int* storage, uint64_t* bytes);
  * (np.mean(X_train, axis=0) of evaluator.py:304) and the centred phenotypes. */
 int tb_set_rowset(tb_ctx* ctx, int slot, const int32_t* train, int n_train, const int32_t* valid, int n_valid);
 
+/* Host helper (no device work, no context): pack P index lists -- the `genome` arrays of P individuals, each a
+ * contiguous int32 (elem_bytes 4) or int64 (8) numpy buffer -- into one flat int32 list for tb_stage_genomes / tb_eval,
+ * with numpy fancy-indexing semantics (tblup/evaluator.py:275, :298): an index in [-m, 0) wraps to index + m,
+ * anything else outside [0, m) fails: returns -3 with *bad_index = the first offending value of the lowest-numbered
+ * list that has one.  idx_off (P + 1 entries) receives the offsets.  Takes the place of the per-individual pickling of
+ * evaluator.py:392-393 on the way to the workers; runs on up to 8 host threads for a generation-sized batch. */
+int tb_pack_index_lists(const void* const* lists, const int64_t* lens, const int32_t* elem_bytes, int P, int64_t m,
+                        int32_t* idx_flat, int64_t* idx_off, int64_t* bad_index);
+
 /* Copy a batch of genomes (ragged marker-index lists, duplicates allowed; idx_off has P+1 entries) to
  * the device: the payload of P enqueue() calls (tblup/evaluator.py:227-241, :392-393). */
 int tb_stage_genomes(tb_ctx* ctx, const int32_t* idx_flat, const int64_t* idx_off, int P);

@@ -23,6 +23,8 @@ SYMBOLS = {
     "tb_destroy": (C.c_int, [C.c_void_p]),
     "tb_clone": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]),
     "tb_set_rowset": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "tb_pack_index_lists": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
+                                      C.POINTER(C.c_int64)]),
     "tb_stage_genomes": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]),
     "tb_eval_staged": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_int]),
     "tb_eval": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int,

@@ -1105,6 +1105,87 @@ int tb_stage_genomes(tb_ctx* c, const int32_t* idx_flat, const int64_t* idx_off,
   return 0;
 }
 
+int tb_pack_index_lists(const void* const* lists, const int64_t* lens, const int32_t* elem_bytes, int P, int64_t m,
+                        int32_t* idx_flat, int64_t* idx_off, int64_t* bad_index) {
+  if (!lens || !idx_off || P < 0 || m <= 0 || m > 0x7fffffffLL) return -1;
+  idx_off[0] = 0;
+  for (int i = 0; i < P; ++i) {
+    if (lens[i] < 0 || (lens[i] > 0 && (!lists || !lists[i])) || !elem_bytes || (elem_bytes[i] != 4 && elem_bytes[i] != 8))
+      return -1;
+    idx_off[i + 1] = idx_off[i] + lens[i];
+  }
+  const int64_t total = idx_off[P];
+  if (total > 0 && !idx_flat) return -1;
+  // lists [lo, hi): copy + narrow + wrap; returns the number of the first list with an index out of range (or P)
+  auto run = [&](int lo, int hi, int64_t* bad) -> int {
+    for (int i = lo; i < hi; ++i) {
+      int32_t* dst = idx_flat + idx_off[i];
+      const int64_t n = lens[i];
+      unsigned flag = 0;
+      if (elem_bytes[i] == 8) {
+        const int64_t* src = static_cast<const int64_t*>(lists[i]);
+        for (int64_t q = 0; q < n; ++q) {
+          int64_t v = src[q];
+          v += v < 0 ? m : 0;
+          flag |= (unsigned)((uint64_t)v >= (uint64_t)m);
+          dst[q] = (int32_t)v;
+        }
+      } else {
+        const int32_t* src = static_cast<const int32_t*>(lists[i]);
+        for (int64_t q = 0; q < n; ++q) {
+          int64_t v = src[q];
+          v += v < 0 ? m : 0;
+          flag |= (unsigned)((uint64_t)v >= (uint64_t)m);
+          dst[q] = (int32_t)v;
+        }
+      }
+      if (flag) {                                   // slow path: name the value
+        for (int64_t q = 0; q < n; ++q) {
+          const int64_t v = elem_bytes[i] == 8 ? static_cast<const int64_t*>(lists[i])[q]
+                                               : (int64_t) static_cast<const int32_t*>(lists[i])[q];
+          if (v >= m || v < -m) {
+            *bad = v;
+            return i;
+          }
+        }
+      }
+    }
+    return P;
+  };
+  int first_bad = P;
+  int64_t bad_value = 0;
+  const int nt = total >= ((int64_t)1 << 20)
+                     ? (int)std::max(1u, std::min(8u, std::min((unsigned)P, std::thread::hardware_concurrency())))
+                     : 1;
+  if (nt > 1) {
+    // contiguous groups of lists with about the same number of indices each
+    std::vector<int> cut(nt + 1, P);
+    cut[0] = 0;
+    for (int t = 1, i = 0; t < nt; ++t) {
+      while (i < P && idx_off[i] < total * t / nt) ++i;
+      cut[t] = i;
+    }
+    std::vector<int> where(nt, P);
+    std::vector<int64_t> what(nt, 0);
+    std::vector<std::thread> th;
+    for (int t = 1; t < nt; ++t) th.emplace_back([&, t] { where[t] = run(cut[t], cut[t + 1], &what[t]); });
+    where[0] = run(cut[0], cut[1], &what[0]);
+    for (auto& x : th) x.join();
+    for (int t = 0; t < nt; ++t)
+      if (where[t] < first_bad) {
+        first_bad = where[t];
+        bad_value = what[t];
+      }
+  } else {
+    first_bad = run(0, P, &bad_value);
+  }
+  if (first_bad < P) {
+    if (bad_index) *bad_index = bad_value;
+    return -3;
+  }
+  return 0;
+}
+
 int tb_eval_staged(tb_ctx* c, const int32_t* slots, int n_slots, double h2, int mode_rule, double* fitness_out,
                    int out_is_device) {
   if (!c) return -1;

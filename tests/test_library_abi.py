@@ -70,6 +70,26 @@ def test_genome_packing_semantics():
         pack_genomes([[10]], 10)
     with pytest.raises(IndexError):
         pack_genomes([[-11]], 10)
+    # the threaded path of tb_pack_index_lists (>= 2^20 indices) against numpy's own fancy-index arithmetic, mixed
+    # element widths, strided / unsigned / float-valued inputs, and the error names the first offending value
+    rng = np.random.default_rng(0)
+    m = 5000
+    big = [rng.integers(-m, m, size=rng.integers(900, 1300)).astype(np.int32 if i % 3 else np.int64) for i in range(1100)]
+    big[7] = big[7][::2]
+    big[8] = big[8].astype(np.float64)
+    big[9] = (big[9] % 200).astype(np.uint8)
+    flat, off = pack_genomes(big, m)
+    want = np.concatenate([np.arange(m)[np.asarray(b, dtype=np.int64)] for b in big])
+    assert flat.dtype == np.int32 and np.array_equal(flat, want) and off[-1] == len(want) >= 1 << 20
+    assert np.array_equal(np.diff(off), [len(b) for b in big])
+    big[600] = big[600].copy()
+    big[600][5] = m + 3
+    big[900] = big[900].copy()
+    big[900][0] = -m - 1
+    with pytest.raises(IndexError, match="index %d is out of bounds" % (m + 3)):
+        pack_genomes(big, m)
+    with pytest.raises(IndexError, match="integer type"):
+        pack_genomes([np.array([1.5])], m)
     with pytest.raises(ValueError):
         as_dosage_int8(np.array([[0.5, 1.0]]))
     with pytest.raises(ValueError):
